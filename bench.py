@@ -1,0 +1,338 @@
+#!/usr/bin/env python3
+"""Benchmark of the batched iLQR hot path (BASELINE.json metric: trajectory-iterations / second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload quadrotor_classic] [--impl reference]
+
+Workload (default, BASELINE.json configs[2]): quadrotor 12-state / 4-control classic iLQR, horizon 50,
+batch 16 384 trajectories PER GPU (weak scaling; trajectories are independent MPC instances, so
+ranks share nothing and there is no collective on the path — one NCCL all_gather of the final
+costs closes the timed region).  A "step" is ONE iLQR iteration over the whole batch in
+fixed-iteration mode (every trajectory forced active): linearise -> Riccati -> line search; the
+problem is reset (nominal rollout) every 10 steps so the steps cover the first ten iterations of a
+solve, like SURVEY.md 8(d) prescribes.  The expansion buffer alone is 1.36 GB per pass, far larger
+than the 126 MB L2, so no explicit flush is needed between iterations.
+
+Printed JSON (one line, rank 0): value = device-timed throughput with inputs resident in HBM;
+e2e = the same metric with host (pinned) inputs copied in and results copied out every step;
+roofline = dominant kernel vs MEASURED_PEAKS.json; cpu_baseline = the scalar oracle port (the
+reference's algorithm and cost profile, oracle/ilqr_port.py) on this box's host cores.
+`--impl reference` times that CPU path alone (the reference is pure Python + NumPy and cannot
+travel to the GPU box; the port is pinned bit-for-bit to it in tests/test_oracle.py).
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (system, horizon, per-GPU batch, transformer?)
+    "quadrotor_classic": ("quadrotor", 50, 16384, False),
+    "cartpole_classic": ("cartpole", 30, 16384, False),
+    "quadrotor_tf": ("quadrotor", 50, 8192, True),
+    "cartpole_tf": ("cartpole", 30, 4096, True),
+}
+RESET_EVERY = 10
+# algorithmic bytes per trajectory per launch, SURVEY.md section 8(d) (quadrotor / cart-pole)
+ALGO_BYTES = {
+    "quadrotor": {"linearize": 87072, "riccati": 94224, "linesearch": 16924, "rollout": 3300},
+    "cartpole": {"linearize": 6216, "riccati": 6200, "linesearch": 1860, "rollout": 636},
+}
+# x,u are kept in fp64 on the device: their share of the figures above doubles
+FP64_EXTRA = {"quadrotor": {"linearize": 3248, "riccati": 0, "linesearch": 3248 + 3276, "rollout": 3300},
+              "cartpole": {"linearize": 616, "riccati": 0, "linesearch": 616 + 620, "rollout": 636}}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------- CPU reference arm
+def _cpu_worker(args):
+    system, x0, iters = args
+    from oracle.ilqr_port import ILQRPort
+    from oracle.models import make_model
+    model = make_model(system)
+    N = {"cartpole": 30, "quadrotor": 50}[system]
+    p = ILQRPort(model, x0, [np.zeros(model.m) for _ in range(N)], N, max_iter=iters, tol=0.0)
+    p.optimize(model.x_ref)
+    return p.total_iter + 1
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference(system, steps, warmup, iters_per_step=1):
+    """Each step: every host core runs `iters_per_step` iLQR iterations of one trajectory."""
+    from oracle.models import sample_x0
+    cores = cpu_cores()
+    x0 = sample_x0(system, cores, seed=0)
+    with mp.get_context("fork").Pool(cores) as pool:
+        for _ in range(warmup):
+            pool.map(_cpu_worker, [(system, x, iters_per_step) for x in x0])
+        t0 = time.perf_counter()
+        done = 0
+        for _ in range(steps):
+            done += sum(pool.map(_cpu_worker, [(system, x, iters_per_step) for x in x0]))
+        dt = time.perf_counter() - t0
+    return done / dt, cores, dt / steps, f"{cores} trajectories x {iters_per_step} iteration(s) per step, one process per core"
+
+
+# ------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) == 6 and r[0].isdigit()]
+        if not rows:
+            return None
+        sm = sorted(int(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i] == "Active" for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def gpu_bench(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as graft
+    from oracle.models import sample_x0                      # input distribution only
+    from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel, TransformerILQR, TransformerPredictor
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        graft.build()
+    if world > 1:
+        dist.barrier()
+
+    system, N, B, use_tf = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    model = DeviceModel(system)
+    n, m = model.n, model.m
+    tf = None
+    if use_tf:
+        tf = TransformerILQR(1, 1).load(os.path.join(ROOT, "tests", "golden", "checkpoints", system))
+        torch.manual_seed(0)                                  # random-init fp32 weights of the repo architecture
+        tf.model = TransformerPredictor(tf.state_dim, tf.control_dim, tf.d_model, tf.nhead, tf.num_decoder_layers,
+                                        tf.dim_feedforward, tf.dropout, tf.max_seq_len, tf.target_len, tf.prompt_len).eval()
+        tf.invalidate()
+        shift = np.zeros(n)
+        if system == "quadrotor":
+            shift[2] = 0.5 - 0.5                              # state_offset - x_ref
+        tf.set_shift(shift, dev)
+    eng = BatchedILQR(model, B, N, device=dev, tf=tf)
+    # each rank owns a contiguous shard of the global batch (seeded per shard)
+    x0_h = torch.as_tensor(sample_x0(system, B, seed=rank)).pin_memory()
+    u0_h = torch.zeros((B, N, m), dtype=torch.float64).pin_memory()
+    x0_d, u0_d = x0_h.to(dev), u0_h.to(dev)
+    tol = 1e-3 if system == "quadrotor" else 1e-1
+
+    def run_steps(k, state):
+        for _ in range(k):
+            if state["i"] % RESET_EVERY == 0:
+                eng.set_problem(x0_d, u0_d)
+            eng.iterate(tol, force=True)
+            state["i"] += 1
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    state = {"i": 0}
+    run_steps(args.warmup, state)
+    sampler = ClockSampler(local)
+    sync_all()
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    state["i"] = 0
+    ev0.record()
+    run_steps(args.steps, state)
+    if world > 1:                                            # the path's only collective: final gather of costs
+        all_cost = torch.empty(world * B, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(all_cost, eng.cost)
+    ev1.record()
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.launches - launches0
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the host-facing call: pinned inputs in, results out, every step -------
+    u_out = torch.empty((B, N, m), dtype=torch.float64).pin_memory()
+    x_out = torch.empty((B, N + 1, n), dtype=torch.float64).pin_memory()
+    c_out = torch.empty(B, dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        eng.set_problem(x0_h, u0_h)                           # H2D + nominal rollout
+        eng.iterate(tol, force=True)
+        u_out.copy_(eng.u_batch(), non_blocking=True)         # D2H
+        x_out.copy_(eng.x_batch(), non_blocking=True)
+        c_out.copy_(eng.cost, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    sync_all()
+    e2e_steps = max(3, min(args.steps, 10))
+    ev0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ev1.record()
+    sync_all()
+    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / (float(t.item()) * 1e-3)
+    h2d = x0_h.numel() * 8 + u0_h.numel() * 8
+    d2h = (u_out.numel() + x_out.numel() + c_out.numel()) * 8
+
+    # ---- per-kernel durations (CUDA events on the launching stream), rank 0 only --------------------
+    kernels = {}
+    if rank == 0:
+        names = ["linearize", "riccati"] + (["transformer"] if use_tf else []) + ["linesearch"]
+        acc = {k: [] for k in names}
+        eng.set_problem(x0_d, u0_d)
+        for it in range(6):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+            start = 0 if tf is None else N - tf.prompt_len
+            evs[0].record()
+            eng.linearize(start); evs[1].record()
+            eng.riccati(start); evs[2].record()
+            j = 2
+            if use_tf:
+                tf.forward_device(eng); j += 1; evs[j].record()
+            eng.linesearch(tol, force=True); evs[j + 1].record()
+            torch.cuda.synchronize(dev)
+            if it >= 1:
+                for q, k in enumerate(names):
+                    acc[k].append(evs[q].elapsed_time(evs[q + 1]))
+        hbm, how = peaks()
+        for k in names:
+            ms_k = float(np.mean(acc[k]))
+            entry = {"ms": round(ms_k, 4)}
+            if k in ALGO_BYTES[system]:
+                frac_T = (N - (0 if tf is None else N - tf.prompt_len)) / N if k in ("linearize", "riccati") and use_tf else 1.0
+                by = (ALGO_BYTES[system][k] + FP64_EXTRA[system][k]) * frac_T
+                gbs = by * B / (ms_k * 1e-3) / 1e9
+                entry.update({"algo_bytes_per_traj": by, "GBps": round(gbs, 1), "frac_hbm": round(gbs / hbm, 4)})
+            kernels[k] = entry
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    dom = max((k for k in kernels if "GBps" in kernels[k]), key=lambda k: kernels[k]["ms"])
+    hbm, how = peaks()
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["GBps"], "peak": hbm, "unit": "GB/s",
+                "frac": kernels[dom]["frac_hbm"], "traffic": None, "peak_source": how,
+                "algo_bytes_per_launch": kernels[dom]["algo_bytes_per_traj"] * B}
+    cpu_val, cores, _, sample = cpu_reference(system, steps=2, warmup=1, iters_per_step=2)
+    out = {
+        "metric": "batched iLQR trajectory-iterations/sec (quadrotor, horizon 50)" if system == "quadrotor"
+        else "batched iLQR trajectory-iterations/sec (cart-pole, horizon 30)",
+        "value": value, "unit": "trajectory-iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (linearise/Riccati/transformer) + f64 (rollouts, costs)", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {system} n={n} m={m} horizon={N}, {B} trajectories per GPU, "
+                               f"fixed-iteration mode, problem reset every {RESET_EVERY} steps",
+                   "global_batch": world * B, "parallelism": f"dp{world} (independent trajectory shards)",
+                   "l2": "inputs larger than L2 (1.36 GB expansion buffer per pass)"},
+        "e2e": {"value": e2e_value, "unit": "trajectory-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
+        "cpu_baseline": {"value": cpu_val, "unit": "trajectory-iterations/s", "cores": cores, "kind": "port", "sample": sample},
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    system, N, B, _ = WORKLOADS[args.workload]
+    t0 = time.perf_counter()
+    val, cores, step_s, sample = cpu_reference(system, args.steps, args.warmup)
+    n, m = (12, 4) if system == "quadrotor" else (4, 1)
+    print(json.dumps({
+        "impl": "reference",
+        "metric": "batched iLQR trajectory-iterations/sec (quadrotor, horizon 50)" if system == "quadrotor"
+        else "batched iLQR trajectory-iterations/sec (cart-pole, horizon 30)",
+        "value": val, "unit": "trajectory-iterations/s", "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {system} n={n} m={m} horizon={N}; CPU path: scalar finite-difference iLQR "
+                               f"(oracle/ilqr_port.py, bit-identical to the reference's quattro_ilqr_tf.py)"},
+        "cpu_baseline": {"value": val, "unit": "trajectory-iterations/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "trajectory-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="quadrotor_classic", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_bench(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,145 @@
+/*
+ * quattro_b200.h — C ABI of libquattro_sm100a.so, the B200 (sm_100a) batched iLQR hot path.
+ *
+ * The reference (salemon/quattro-transformer-ilqr) has no native layer: its boundary is the
+ * Python class iLQR_TF (quattro_ilqr_tf/quattro_ilqr_tf.py:50-612) and the duck-typed
+ * predictor TransformerILQR.predict (quattro_ilqr_tf/transformer_ilqr.py:311-325).  Each entry
+ * point below replaces the body of one reference method for a BATCH of B independent
+ * trajectories; the Python host (quattro_transformer_ilqr_b200/) keeps the reference's class
+ * API on top of these calls.  All citations are relative to /root/reference.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer owned by the caller
+ *    (PyTorch tensors' data_ptr()); the library never allocates, frees or synchronises;
+ *  - work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *  - return 0 on success, a negative QX_E* code otherwise; qx_last_error() gives the text
+ *    (thread-local); nothing is thrown across the boundary;
+ *  - no global mutable state; re-entrant across streams.
+ *
+ * Device data layout (B = batch, N = horizon, n = state dim, m = control dim, b fastest)
+ *   x      double [N+1][n][B]      trajectories (fp64: rollouts and costs are fp64)
+ *   u      double [N][m][B]
+ *   cost   double [B]
+ *   status int32  [B]              0 = active, 1 = finished (converged or no alpha accepted)
+ *   iters  int32  [B]              iterations executed so far
+ *   alpha  int32  [B]              index into {1,.5,.25,.1,.05,.01} accepted last, -1 = none
+ *   expansion / terminal / gains: float, layout depends on the model's "record" kind:
+ *     QX_LAYOUT_REC (quadrotor; warp-per-trajectory Riccati, one contiguous record per (t,b))
+ *        expansion float [N][B][REC]   REC = [A n*n | B n*m | lx n | lu m | lxx n*n | luu m*m | lux m*n]
+ *        terminal  float [B][n + n*n]  [Vx | Vxx]
+ *        gains     float [N][B][m + m*n]  [k | K row-major]
+ *     QX_LAYOUT_SOA (cart-pole; thread-per-trajectory Riccati, b fastest)
+ *        expansion float [N][REC][B], terminal float [n + n*n][B], gains float [N][m + m*n][B]
+ */
+#ifndef QUATTRO_B200_H
+#define QUATTRO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QX_ABI_VERSION 1
+
+#define QX_MODEL_CARTPOLE 0   /* examples/cartpole/cartpole_dynamics.py:48-105, cartpole_mpc.py:187-269 */
+#define QX_MODEL_QUADROTOR 1  /* examples/quadrotor/quadrotor_dynamics.py:64-195, quadrotor_mpc.py:40-100 */
+
+#define QX_EULER 0
+#define QX_RK4 1
+
+#define QX_LAYOUT_SOA 0
+#define QX_LAYOUT_REC 1
+
+#define QX_MAX_N 12
+#define QX_MAX_M 4
+#define QX_NUM_ALPHA 6
+
+#define QX_OK 0
+#define QX_EINVAL (-1)   /* bad argument (null pointer, unknown model, size out of range) */
+#define QX_ECUDA (-2)    /* a CUDA runtime call failed; see qx_last_error() */
+#define QX_EUNSUPPORTED (-3)
+
+/* flags of qx_linesearch */
+#define QX_LS_FORCE_ACTIVE 1u   /* fixed-iteration (benchmark) mode: never mark a trajectory finished */
+
+/* Model parameters, refreshed by the host from the MPC object at every optimize() because the
+ * reference's callers mutate them between calls ("Config / flags"). */
+typedef struct QxParams {
+  int32_t model_id;      /* QX_MODEL_* */
+  int32_t integrator;    /* QX_EULER | QX_RK4  (discrete_dynamics, cartpole_dynamics.py:94-105) */
+  int32_t n, m;
+  int32_t diag_cost;     /* 1 when Q, R, Qf are diagonal (fast path; same values) */
+  int32_t _pad;
+  double dt;
+  double phys[8];        /* cart-pole: m_cart, m_pole, length, gravity;
+                            quadrotor: mass, Ix, Iy, Iz, arm, gravity, k_yaw */
+  double Q[QX_MAX_N * QX_MAX_N];   /* row-major n x n (running_cost, cartpole_mpc.py:255, quadrotor_mpc.py:86-93) */
+  double R[QX_MAX_M * QX_MAX_M];
+  double Qf[QX_MAX_N * QX_MAX_N];  /* final_cost, cartpole_mpc.py:268, quadrotor_mpc.py:99 */
+  double x_ref[QX_MAX_N];
+  double barrier_alpha;  /* quadrotor soft barrier weight (quadrotor_mpc.py:45); 0 for cart-pole */
+  double barrier_beta;   /* softplus sharpness (quadrotor_mpc.py:46) */
+} QxParams;
+
+/* Transformer hyper-parameters (TransformerPredictor.__init__, transformer_model.py:97-116). */
+typedef struct QxTfConfig {
+  int32_t state_dim;     /* n */
+  int32_t control_dim;   /* c = m (1 + n) */
+  int32_t d_model, nhead, num_layers, dim_ff;
+  int32_t target_len, prompt_len, horizon;   /* tokens: (horizon+1) states | prompt | targets */
+  int32_t m;             /* control dimension of the system (for the K/k unpack) */
+} QxTfConfig;
+
+int qx_abi_version(void);
+const char* qx_last_error(void);
+
+/* Layout queries (pure host functions). */
+int qx_layout(int model_id);                       /* QX_LAYOUT_* for the model, or QX_EINVAL */
+int qx_record_floats(int model_id);                /* REC */
+size_t qx_expansion_bytes(int model_id, int B, int N);
+size_t qx_terminal_bytes(int model_id, int B);
+size_t qx_gains_bytes(int model_id, int B, int N);
+
+/* simulate + compute_total_cost  (quattro_ilqr_tf.py:127-143).
+ * x0 double [n][B]; writes x[N+1][n][B] and cost[B].  status may be NULL (all trajectories). */
+int qx_rollout_cost(const QxParams* p, const double* x0, const double* u, double* x, double* cost,
+                    const int32_t* status, int B, int N, void* stream);
+
+/* _compute_dynamics_jacobians + _compute_cost_derivatives for t in [t_start, N) and the terminal
+ * V_x, V_xx (quattro_ilqr_tf.py:149-275), exact derivatives, one launch for the whole horizon. */
+int qx_linearize(const QxParams* p, const double* x, const double* u, float* expansion, float* terminal,
+                 const int32_t* status, int B, int N, int t_start, void* stream);
+
+/* backward_pass (t_start = 0, quattro_ilqr_tf.py:282-319) / backward_pass_segment (t_start > 0,
+ * :327-366): gains for t in [t_start, N) written at their absolute t. reg = 1e-6 in the reference. */
+int qx_riccati(int model_id, const float* expansion, const float* terminal, float* gains,
+               const int32_t* status, int B, int N, int t_start, float reg, void* stream);
+
+/* The line search of optimize (quattro_ilqr_tf.py:440-451) with forward_pass (:377-390) inside:
+ * first alpha in {1,.5,.25,.1,.05,.01} whose candidate cost <= cost[b]; all in one launch.
+ * On return (x_out,u_out,cost) hold the next iterate of every ACTIVE trajectory (the accepted
+ * candidate, or an unchanged copy when no alpha is accepted); status/iters/alpha are updated with
+ * the reference's stopping rule (:472): finished iff no alpha accepted or |cost - new| < tol.
+ * A trajectory that finishes has its final iterate in BOTH (x_in,u_in) and (x_out,u_out), so the
+ * caller can ping-pong the buffers.  n_active (device int32, may be NULL) is incremented by the
+ * number of trajectories still active afterwards. */
+int qx_linesearch(const QxParams* p, double* x_in, double* u_in, const float* gains, double* cost,
+                  int32_t* status, int32_t* iters, int32_t* alpha, double* x_out, double* u_out,
+                  int32_t* n_active, double tol, uint32_t flags, int B, int N, void* stream);
+
+/* ---- Quattro transformer: TransformerILQR.predict for a batch (transformer_ilqr.py:311-325,
+ * transformer_model.py:122-138) fused with the prompt pack / prediction unpack of optimize
+ * (quattro_ilqr_tf.py:496-518).  Weights are one packed float buffer laid out by
+ * qx_tf_weight_offsets(); scratch is qx_tf_workspace_bytes().  Reads x (trajectories) and the
+ * last prompt_len gain records, writes gain records for t in [0, target_len). */
+size_t qx_tf_weight_floats(const QxTfConfig* cfg);
+size_t qx_tf_workspace_bytes(const QxTfConfig* cfg, int B);
+int qx_tf_forward(const QxTfConfig* cfg, const float* weights, const double* x, const double* x_shift,
+                  float* gains, int model_id, const int32_t* status, void* workspace, int B, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUATTRO_B200_H */

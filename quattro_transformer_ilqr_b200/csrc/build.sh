@@ -1,0 +1,17 @@
+#!/bin/bash
+# Build libquattro_sm100a.so in-tree (nvcc cross-compiles sm_100a without a GPU).
+set -euo pipefail
+cd "$(dirname "$0")"
+OUT=../libquattro_sm100a.so
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr"
+SRCS=$(ls *.cu)
+mkdir -p build
+pids=()
+for s in $SRCS; do
+  ( $NVCC $FLAGS -c "$s" -o "build/${s%.cu}.o" > "build/${s%.cu}.log" 2>&1 || { cat "build/${s%.cu}.log"; exit 1; } ) &
+  pids+=($!)
+done
+for p in "${pids[@]}"; do wait "$p"; done
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" build/*.o -lcudart
+echo "built $OUT"

@@ -1,0 +1,49 @@
+// Shared device/host helpers for libquattro_sm100a.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/quattro_b200.h"
+
+namespace qx {
+
+// ---- error plumbing (thread-local text, C ABI returns a code) -------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define QX_CHECK_ARG(cond, msg)                         \
+  do {                                                  \
+    if (!(cond)) {                                      \
+      qx::set_error("invalid argument: %s", msg);       \
+      return QX_EINVAL;                                 \
+    }                                                   \
+  } while (0)
+
+#define QX_CHECK_LAUNCH(what)                           \
+  do {                                                  \
+    cudaError_t e__ = cudaGetLastError();               \
+    if (e__ != cudaSuccess) return qx::cuda_fail(e__, what); \
+  } while (0)
+
+// ---- record layout (see include/quattro_b200.h) ----------------------------------------------
+template <int n, int m>
+struct Rec {
+  static constexpr int A = 0;
+  static constexpr int Bm = A + n * n;
+  static constexpr int lx = Bm + n * m;
+  static constexpr int lu = lx + n;
+  static constexpr int lxx = lu + m;
+  static constexpr int luu = lxx + n * n;
+  static constexpr int lux = luu + m * m;
+  static constexpr int size = lux + m * n;      // 416 (quadrotor), 46 (cart-pole)
+  static constexpr int term = n + n * n;        // [Vx | Vxx]
+  static constexpr int gain = m + m * n;        // [k | K]
+};
+
+__host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+static __constant__ double kAlphas[QX_NUM_ALPHA] = {1.0, 0.5, 0.25, 0.1, 0.05, 0.01};
+
+}  // namespace qx

@@ -1,0 +1,261 @@
+// Linearisation of a whole horizon in one launch.
+//
+//   linearize_kernel = _compute_dynamics_jacobians (quattro_ilqr_tf.py:182-204)
+//                    + _compute_cost_derivatives   (:217-275)
+//                    + _finite_diff_gradient_final / _finite_diff_hessian_final (:149-174)
+// with closed-form derivatives instead of the reference's central differences.
+//
+// One thread per (t, b).  The kernel is a pure HBM-write stream (quadrotor: 3 248 B read,
+// 83 824 B written per trajectory), so the only thing that matters is that the stores are full
+// 128-B lines:
+//   * SOA layout (cart-pole): the record index is slower than b, every store is coalesced as is;
+//   * REC layout (quadrotor): a thread produces one contiguous 1 664-B record; each warp stages
+//     half a record per lane (208 floats, row pitch 209 -> conflict-free) in shared memory and
+//     streams it out as 128-B row segments.
+#include "qx_models.cuh"
+
+namespace qx {
+
+// A = d f / d x, Bm = d f / d u of the DISCRETE map, row-major, in float.
+template <class Mdl, int INTEG>
+__device__ __forceinline__ void discrete_jacobians(const float* x, const float* u, const QxParams& p, float* A,
+                                                   float* Bm) {
+  constexpr int n = Mdl::n, m = Mdl::m;
+  const float dt = float(p.dt);
+  if (INTEG == QX_EULER) {
+    Mdl::template fc_jac<float>(x, u, p, A, Bm);
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+#pragma unroll
+      for (int j = 0; j < n; ++j) A[i * n + j] = (i == j ? 1.f : 0.f) + dt * A[i * n + j];
+#pragma unroll
+    for (int i = 0; i < n * m; ++i) Bm[i] = dt * Bm[i];
+    return;
+  }
+  // RK4: chain rule through the four stages.  D_s = d k_s / d(x,u).
+  float k[n], xs[n], J[n * n], G[n * m], Dx[n * n], Du[n * m], Tx[n * n], Tu[n * m];
+  const float w[4] = {1.f, 2.f, 2.f, 1.f};
+  const float c[4] = {0.f, 0.5f, 0.5f, 1.f};
+#pragma unroll
+  for (int i = 0; i < n * n; ++i) { A[i] = 0.f; Dx[i] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < n * m; ++i) { Bm[i] = 0.f; Du[i] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < n; ++i) k[i] = 0.f;
+  for (int s = 0; s < 4; ++s) {
+    const float h = c[s] * dt;
+    for (int i = 0; i < n; ++i) xs[i] = x[i] + h * k[i];
+    Mdl::template fc_jac<float>(xs, u, p, J, G);
+    // D_s,x = J (I + h D_{s-1},x),  D_s,u = J (h D_{s-1},u) + G
+    for (int i = 0; i < n; ++i) {
+      for (int j = 0; j < n; ++j) {
+        float acc = J[i * n + j];
+        for (int l = 0; l < n; ++l) acc += h * J[i * n + l] * Dx[l * n + j];
+        Tx[i * n + j] = acc;
+      }
+      for (int j = 0; j < m; ++j) {
+        float acc = G[i * m + j];
+        for (int l = 0; l < n; ++l) acc += h * J[i * n + l] * Du[l * m + j];
+        Tu[i * m + j] = acc;
+      }
+    }
+    for (int i = 0; i < n * n; ++i) { Dx[i] = Tx[i]; A[i] += w[s] * Tx[i]; }
+    for (int i = 0; i < n * m; ++i) { Du[i] = Tu[i]; Bm[i] += w[s] * Tu[i]; }
+    Mdl::template fc<float>(xs, u, p, k);
+  }
+  const float s6 = dt / 6.f;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) A[i * n + j] = (i == j ? 1.f : 0.f) + s6 * A[i * n + j];
+  for (int i = 0; i < n * m; ++i) Bm[i] = s6 * Bm[i];
+}
+
+// Sinks: where element e of the (t,b) record goes.
+struct SoaSink {
+  float* base; size_t stride;   // base + e*stride
+  __device__ __forceinline__ void operator()(int e, float v) const { base[(size_t)e * stride] = v; }
+};
+struct StageSink {
+  float* row;                   // this lane's staging row
+  __device__ __forceinline__ void operator()(int e, float v) const { row[e] = v; }
+};
+
+template <class Mdl, int INTEG, class Sink>
+__device__ __forceinline__ void emit_dynamics(const float* x, const float* u, const QxParams& p, Sink out) {
+  constexpr int n = Mdl::n, m = Mdl::m;
+  using R = Rec<n, m>;
+  float A[n * n], Bm[n * m];
+  discrete_jacobians<Mdl, INTEG>(x, u, p, A, Bm);
+#pragma unroll
+  for (int i = 0; i < n * n; ++i) out(R::A + i, A[i]);
+#pragma unroll
+  for (int i = 0; i < n * m; ++i) out(R::Bm + i, Bm[i]);
+  float dx[n], g[n];
+#pragma unroll
+  for (int i = 0; i < n; ++i) dx[i] = x[i] - float(p.x_ref[i]);
+  quad_grad<float, n>(p.Q, dx, p.diag_cost, g);
+#pragma unroll
+  for (int i = 0; i < n; ++i) out(R::lx + i, g[i]);
+  float gu[m], bg[m], bh[m];
+  quad_grad<float, m>(p.R, u, p.diag_cost, gu);
+  Mdl::template barrier_d<float>(u, p, bg, bh);
+#pragma unroll
+  for (int j = 0; j < m; ++j) out(R::lu + j, gu[j] + bg[j]);
+}
+
+// second half of the record: l_xx, l_uu, l_ux (offset so that it starts at 0 when off = R::lxx)
+template <class Mdl, class Sink>
+__device__ __forceinline__ void emit_hessians(const float* u, const QxParams& p, Sink out, int off) {
+  constexpr int n = Mdl::n, m = Mdl::m;
+  using R = Rec<n, m>;
+  float bg[m], bh[m];
+  Mdl::template barrier_d<float>(u, p, bg, bh);
+#pragma unroll
+  for (int i = 0; i < n; ++i)
+#pragma unroll
+    for (int j = 0; j < n; ++j) out(R::lxx - off + i * n + j, float(p.Q[i * n + j] + p.Q[j * n + i]));
+#pragma unroll
+  for (int i = 0; i < m; ++i)
+#pragma unroll
+    for (int j = 0; j < m; ++j)
+      out(R::luu - off + i * m + j, float(p.R[i * m + j] + p.R[j * m + i]) + (i == j ? bh[i] : 0.f));
+#pragma unroll
+  for (int i = 0; i < m * n; ++i) out(R::lux - off + i, 0.f);
+}
+
+template <class Mdl, class Sink>
+__device__ __forceinline__ void emit_terminal(const float* x, const QxParams& p, Sink out) {
+  constexpr int n = Mdl::n;
+  float dx[n], g[n];
+#pragma unroll
+  for (int i = 0; i < n; ++i) dx[i] = x[i] - float(p.x_ref[i]);
+  quad_grad<float, n>(p.Qf, dx, p.diag_cost, g);
+#pragma unroll
+  for (int i = 0; i < n; ++i) out(i, g[i]);
+#pragma unroll
+  for (int i = 0; i < n; ++i)
+#pragma unroll
+    for (int j = 0; j < n; ++j) out(n + i * n + j, float(p.Qf[i * n + j] + p.Qf[j * n + i]));
+}
+
+template <class Mdl>
+__device__ __forceinline__ void load_xu(const double* __restrict__ x, const double* __restrict__ u, int t, int b,
+                                        int B, float* xs, float* us) {
+#pragma unroll
+  for (int i = 0; i < Mdl::n; ++i) xs[i] = float(x[((size_t)t * Mdl::n + i) * B + b]);
+#pragma unroll
+  for (int j = 0; j < Mdl::m; ++j) us[j] = float(u[((size_t)t * Mdl::m + j) * B + b]);
+}
+
+// ---- SOA: every store already coalesced --------------------------------------------------------
+template <class Mdl, int INTEG>
+__global__ void __launch_bounds__(128)
+linearize_soa_kernel(const __grid_constant__ QxParams p, const double* __restrict__ x, const double* __restrict__ u,
+                     float* __restrict__ expansion, float* __restrict__ terminal,
+                     const int32_t* __restrict__ status, int B, int N, int t_start) {
+  constexpr int n = Mdl::n, m = Mdl::m;
+  using R = Rec<n, m>;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = t_start + blockIdx.y;
+  if (b >= B) return;
+  if (status != nullptr && status[b] != 0) return;
+  float xs[n], us[m];
+  load_xu<Mdl>(x, u, t, b, B, xs, us);
+  SoaSink sink{expansion + (size_t)t * R::size * B + b, (size_t)B};
+  emit_dynamics<Mdl, INTEG>(xs, us, p, sink);
+  emit_hessians<Mdl>(us, p, sink, 0);
+  if (t == N - 1) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) xs[i] = float(x[((size_t)N * n + i) * B + b]);
+    emit_terminal<Mdl>(xs, p, SoaSink{terminal + b, (size_t)B});
+  }
+}
+
+// ---- REC: stage half records per warp, stream out full lines -----------------------------------
+constexpr int kLinWarps = 1;
+
+template <class Mdl, int INTEG>
+__global__ void __launch_bounds__(32 * kLinWarps)
+linearize_rec_kernel(const __grid_constant__ QxParams p, const double* __restrict__ x, const double* __restrict__ u,
+                     float* __restrict__ expansion, float* __restrict__ terminal,
+                     const int32_t* __restrict__ status, int B, int N, int t_start) {
+  constexpr int n = Mdl::n, m = Mdl::m;
+  using R = Rec<n, m>;
+  constexpr int HALF = R::lxx;                 // first half = [A | B | lx | lu]
+  static_assert(HALF * 2 == R::size, "record must split in two equal halves");
+  static_assert(R::term <= HALF, "terminal record must fit the staging row");
+  constexpr int PITCH = HALF + 1;              // odd pitch: lane-strided writes hit 32 distinct banks
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ float stage[kLinWarps][32 * PITCH];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b0 = (blockIdx.x * kLinWarps + warp) * 32;
+  const int b = b0 + lane;
+  const int t = t_start + blockIdx.y;
+  const bool mine = (b < B) && (status == nullptr || status[b] == 0);
+  const unsigned live = __ballot_sync(FULL, mine);
+  if (live == 0u) return;
+  float* row = &stage[warp][lane * PITCH];
+  float xs[n], us[m];
+  if (mine) load_xu<Mdl>(x, u, t, b, B, xs, us);
+
+  auto flush = [&](float* dst0, size_t rec_stride, int count) {
+    // dst0: destination of lane 0's chunk; record r of the warp goes to dst0 + r * rec_stride
+    __syncwarp();
+    for (int r = 0; r < 32; ++r) {
+      if (!((live >> r) & 1u)) continue;
+      const float* src = &stage[warp][r * PITCH];
+      float* dst = dst0 + (size_t)r * rec_stride;
+      for (int e = lane; e < count; e += 32) dst[e] = src[e];
+    }
+    __syncwarp();
+  };
+
+  float* rec0 = expansion + ((size_t)t * B + b0) * R::size;
+  if (mine) emit_dynamics<Mdl, INTEG>(xs, us, p, StageSink{row});
+  flush(rec0, R::size, HALF);
+  if (mine) emit_hessians<Mdl>(us, p, StageSink{row}, HALF);
+  flush(rec0 + HALF, R::size, HALF);
+  if (t == N - 1) {
+    if (mine) {
+#pragma unroll
+      for (int i = 0; i < n; ++i) xs[i] = float(x[((size_t)N * n + i) * B + b]);
+      emit_terminal<Mdl>(xs, p, StageSink{row});
+    }
+    flush(terminal + (size_t)b0 * R::term, R::term, R::term);
+  }
+}
+
+}  // namespace qx
+
+extern "C" int qx_linearize(const QxParams* p, const double* x, const double* u, float* expansion, float* terminal,
+                            const int32_t* status, int B, int N, int t_start, void* stream) {
+  QX_CHECK_ARG(p && x && u && expansion && terminal, "null pointer");
+  QX_CHECK_ARG(B > 0 && N > 0 && t_start >= 0 && t_start < N, "need B > 0 and 0 <= t_start < N");
+  QX_CHECK_ARG(p->integrator == QX_EULER || p->integrator == QX_RK4, "unknown integrator");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int T = N - t_start;
+  switch (p->model_id) {
+    case QX_MODEL_CARTPOLE: {
+      dim3 grid(qx::ceil_div(B, 128), T);
+      if (p->integrator == QX_EULER)
+        qx::linearize_soa_kernel<qx::CartPole, QX_EULER><<<grid, 128, 0, st>>>(*p, x, u, expansion, terminal, status, B, N, t_start);
+      else
+        qx::linearize_soa_kernel<qx::CartPole, QX_RK4><<<grid, 128, 0, st>>>(*p, x, u, expansion, terminal, status, B, N, t_start);
+      QX_CHECK_LAUNCH("linearize_soa_kernel");
+      return QX_OK;
+    }
+    case QX_MODEL_QUADROTOR: {
+      dim3 grid(qx::ceil_div(B, 32 * qx::kLinWarps), T);
+      if (p->integrator == QX_EULER)
+        qx::linearize_rec_kernel<qx::Quadrotor, QX_EULER><<<grid, 32 * qx::kLinWarps, 0, st>>>(*p, x, u, expansion, terminal,
+                                                                                             status, B, N, t_start);
+      else
+        qx::linearize_rec_kernel<qx::Quadrotor, QX_RK4><<<grid, 32 * qx::kLinWarps, 0, st>>>(*p, x, u, expansion, terminal,
+                                                                                           status, B, N, t_start);
+      QX_CHECK_LAUNCH("linearize_rec_kernel");
+      return QX_OK;
+    }
+  }
+  qx::set_error("unknown model_id %d", p->model_id);
+  return QX_EINVAL;
+}

@@ -1,0 +1,276 @@
+// Forward rollouts: nominal simulate+cost, and the fused line search.
+//
+//   rollout_cost_kernel  = iLQR_TF.simulate + compute_total_cost   (quattro_ilqr_tf.py:127-143)
+//   linesearch_kernel    = the alpha loop of optimize (:440-451) around forward_pass (:377-390)
+//                          plus the stopping rule (:472), one launch for the whole batch.
+//
+// One thread owns one trajectory (a rollout is a strictly sequential recursion over t); the
+// batch index is the fastest-varying index of x/u so every global access of a warp is one
+// fully used 256-B (fp64) segment.  All arithmetic is fp64: the accept test compares costs
+// whose relative difference is routinely 1e-7..1e-9 near convergence (SURVEY.md hard part 3).
+//
+// Gains in the REC layout ([t][b][52] floats, written by the warp-per-trajectory Riccati kernel)
+// are staged per warp through shared memory with 1-D bulk async copies (TMA, SASS UBLKCP): for a
+// fixed t the 32 records of a warp are one contiguous 6656-B chunk; a 4-stage mbarrier ring keeps
+// the copy of step t+3 in flight while step t is computed.
+#include "qx_async.cuh"
+#include "qx_models.cuh"
+
+namespace qx {
+
+template <class Mdl>
+__global__ void __launch_bounds__(128)
+rollout_cost_kernel(const __grid_constant__ QxParams p, const double* __restrict__ x0,
+                    const double* __restrict__ u, double* __restrict__ x, double* __restrict__ cost,
+                    const int32_t* __restrict__ status, int B, int N) {
+  constexpr int n = Mdl::n, m = Mdl::m;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (status != nullptr && status[b] != 0) return;
+  double xs[n], us[m], xn[n];
+#pragma unroll
+  for (int i = 0; i < n; ++i) xs[i] = x0[(size_t)i * B + b];
+  double c = 0.0;
+  for (int t = 0; t < N; ++t) {
+#pragma unroll
+    for (int j = 0; j < m; ++j) us[j] = u[((size_t)t * m + j) * B + b];
+#pragma unroll
+    for (int i = 0; i < n; ++i) x[((size_t)t * n + i) * B + b] = xs[i];
+    c += running_cost<Mdl, double>(xs, us, p);
+    discrete_step<Mdl, double>(xs, us, p, xn);
+#pragma unroll
+    for (int i = 0; i < n; ++i) xs[i] = xn[i];
+  }
+#pragma unroll
+  for (int i = 0; i < n; ++i) x[((size_t)N * n + i) * B + b] = xs[i];
+  c += final_cost<Mdl, double>(xs, p);
+  cost[b] = c;
+}
+
+// ------------------------------------------------------------------------------------------
+constexpr int kLsStages = 4;
+
+template <class Mdl>
+struct LsSmem {
+  static constexpr int G = Rec<Mdl::n, Mdl::m>::gain;
+  alignas(128) float ring[kLsStages][32 * G];
+  alignas(8) uint64_t bar[kLsStages];
+};
+
+template <class Mdl>
+__global__ void __launch_bounds__(32)
+linesearch_kernel(const __grid_constant__ QxParams p, double* __restrict__ x_in, double* __restrict__ u_in,
+                  const float* __restrict__ gains, double* __restrict__ cost, int32_t* __restrict__ status,
+                  int32_t* __restrict__ iters, int32_t* __restrict__ alpha_out, double* __restrict__ x_out,
+                  double* __restrict__ u_out, int32_t* __restrict__ n_active, double tol, uint32_t flags,
+                  int B, int N) {
+  constexpr int n = Mdl::n, m = Mdl::m;
+  constexpr int G = Rec<n, m>::gain;
+  constexpr bool kRec = (Mdl::layout == QX_LAYOUT_REC);
+  constexpr unsigned FULL = 0xffffffffu;
+
+  const int lane = threadIdx.x;
+  const int b0 = blockIdx.x * 32;
+  const int b = b0 + lane;
+  const bool mine = (b < B) && (status[b] == 0);
+  if (!__any_sync(FULL, mine)) return;
+  const int nb = min(32, B - b0);                       // trajectories covered by this warp
+
+  __shared__ LsSmem<Mdl> sm;
+  uint32_t seq_issue = 0, seq_wait = 0;                 // ring positions (warp-uniform)
+  if (kRec) {
+    if (lane == 0) {
+      for (int s = 0; s < kLsStages; ++s) mbar_init(&sm.bar[s], 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+  }
+  auto issue = [&](int t) {                             // lane 0 only
+    const int s = seq_issue % kLsStages;
+    const uint32_t bytes = (uint32_t)nb * G * sizeof(float);
+    mbar_arrive_expect_tx(&sm.bar[s], bytes);
+    bulk_g2s(sm.ring[s], gains + ((size_t)t * B + b0) * G, bytes, &sm.bar[s]);
+  };
+
+  const double cur = mine ? cost[b] : 0.0;
+  double x_first[n];
+#pragma unroll
+  for (int i = 0; i < n; ++i) x_first[i] = mine ? x_in[(size_t)i * B + b] : 0.0;
+
+  bool accepted = !mine;          // lanes without work never roll out
+  int idx = -1;
+  double new_cost = cur;
+
+  for (int a = 0; a < QX_NUM_ALPHA; ++a) {
+    if (!__any_sync(FULL, !accepted)) break;
+    const bool run = !accepted;
+    const double alpha = kAlphas[a];
+    double xh[n], xn[n], un[m], uh[m], xnext[n];
+    double xn_nx[n], un_nx[m];        // nominal of step t+1, fetched while step t is computed
+    float g_nx[kRec ? 1 : G];         // SOA gains of step t+1 (the REC layout comes through the ring)
+#pragma unroll
+    for (int i = 0; i < n; ++i) xh[i] = x_first[i];
+    double c = 0.0;
+
+    if (kRec) {
+      if (lane == 0)
+        for (int t = 0; t < kLsStages - 1 && t < N; ++t) { issue(t); ++seq_issue; }
+      seq_issue = __shfl_sync(FULL, seq_issue, 0);
+    }
+    auto fetch = [&](int t) {
+#pragma unroll
+      for (int i = 0; i < n; ++i) xn_nx[i] = x_in[((size_t)t * n + i) * B + b];
+#pragma unroll
+      for (int j = 0; j < m; ++j) un_nx[j] = u_in[((size_t)t * m + j) * B + b];
+      if (!kRec) {
+#pragma unroll
+        for (int q = 0; q < G; ++q) g_nx[q] = gains[((size_t)t * G + q) * B + b];
+      }
+    };
+    if (run) fetch(0);
+    for (int t = 0; t < N; ++t) {
+      if (kRec) {
+        // all lanes finished reading the stage that is about to be refilled (step t-1's)
+        __syncwarp();
+        if (t + kLsStages - 1 < N) {
+          if (lane == 0) issue(t + kLsStages - 1);
+          ++seq_issue;
+        }
+        mbar_wait(&sm.bar[seq_wait % kLsStages], (seq_wait / kLsStages) & 1u);
+      }
+      if (run) {
+        float g[G];
+#pragma unroll
+        for (int i = 0; i < n; ++i) xn[i] = xn_nx[i];
+#pragma unroll
+        for (int j = 0; j < m; ++j) un[j] = un_nx[j];
+        if (kRec) {
+          const float4* r4 = reinterpret_cast<const float4*>(&sm.ring[seq_wait % kLsStages][lane * G]);
+#pragma unroll
+          for (int q = 0; q < G / 4; ++q) {
+            const float4 v = r4[q];
+            g[4 * q + 0] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < G; ++q) g[q] = g_nx[q];
+        }
+        if (t + 1 < N) fetch(t + 1);
+        // du = k + K (x_hat - x);  u_hat = u + alpha * du   (alpha scales the feedback too)
+#pragma unroll
+        for (int j = 0; j < m; ++j) {
+          double kd = 0.0;
+#pragma unroll
+          for (int i = 0; i < n; ++i) kd += (double)g[m + j * n + i] * (xh[i] - xn[i]);
+          const double du = (double)g[j] + kd;
+          uh[j] = un[j] + alpha * du;
+        }
+#pragma unroll
+        for (int i = 0; i < n; ++i) x_out[((size_t)t * n + i) * B + b] = xh[i];
+#pragma unroll
+        for (int j = 0; j < m; ++j) u_out[((size_t)t * m + j) * B + b] = uh[j];
+        c += running_cost<Mdl, double>(xh, uh, p);
+        discrete_step<Mdl, double>(xh, uh, p, xnext);
+#pragma unroll
+        for (int i = 0; i < n; ++i) xh[i] = xnext[i];
+      }
+      if (kRec) ++seq_wait;
+    }
+    if (run) {
+#pragma unroll
+      for (int i = 0; i < n; ++i) x_out[((size_t)N * n + i) * B + b] = xh[i];
+      c += final_cost<Mdl, double>(xh, p);
+      if (c <= cur) {              // first accepted alpha, "<=" (quattro_ilqr_tf.py:444)
+        accepted = true;
+        idx = a;
+        new_cost = c;
+      }
+    }
+  }
+
+  bool still_active = false;
+  if (mine) {
+    const bool found = idx >= 0;
+    bool done = (!found) || (fabs(cur - new_cost) < tol);        // quattro_ilqr_tf.py:472
+    if (flags & QX_LS_FORCE_ACTIVE) done = false;
+    if (!found) {
+      // keep the nominal: (x_out,u_out) <- (x_in,u_in)
+      for (int t = 0; t <= N; ++t)
+#pragma unroll
+        for (int i = 0; i < n; ++i) x_out[((size_t)t * n + i) * B + b] = x_in[((size_t)t * n + i) * B + b];
+      for (int t = 0; t < N; ++t)
+#pragma unroll
+        for (int j = 0; j < m; ++j) u_out[((size_t)t * m + j) * B + b] = u_in[((size_t)t * m + j) * B + b];
+    } else if (done) {
+      // finished: leave the final iterate in both buffers so the caller may keep ping-ponging
+      for (int t = 0; t <= N; ++t)
+#pragma unroll
+        for (int i = 0; i < n; ++i) x_in[((size_t)t * n + i) * B + b] = x_out[((size_t)t * n + i) * B + b];
+      for (int t = 0; t < N; ++t)
+#pragma unroll
+        for (int j = 0; j < m; ++j) u_in[((size_t)t * m + j) * B + b] = u_out[((size_t)t * m + j) * B + b];
+    }
+    cost[b] = new_cost;
+    alpha_out[b] = idx;
+    iters[b] += 1;
+    if (done) status[b] = 1;
+    still_active = !done;
+  }
+  const unsigned act = __ballot_sync(FULL, still_active);
+  if (lane == 0 && n_active != nullptr && act != 0u) atomicAdd(n_active, __popc(act));
+}
+
+// ------------------------------------------------------------------------------------------
+template <class Mdl>
+static int launch_rollout(const QxParams* p, const double* x0, const double* u, double* x, double* cost,
+                          const int32_t* status, int B, int N, cudaStream_t st) {
+  const int threads = 128;
+  rollout_cost_kernel<Mdl><<<ceil_div(B, threads), threads, 0, st>>>(*p, x0, u, x, cost, status, B, N);
+  QX_CHECK_LAUNCH("rollout_cost_kernel");
+  return QX_OK;
+}
+
+template <class Mdl>
+static int launch_linesearch(const QxParams* p, double* x_in, double* u_in, const float* gains, double* cost,
+                             int32_t* status, int32_t* iters, int32_t* alpha, double* x_out, double* u_out,
+                             int32_t* n_active, double tol, uint32_t flags, int B, int N, cudaStream_t st) {
+  linesearch_kernel<Mdl><<<ceil_div(B, 32), 32, 0, st>>>(*p, x_in, u_in, gains, cost, status, iters, alpha,
+                                                         x_out, u_out, n_active, tol, flags, B, N);
+  QX_CHECK_LAUNCH("linesearch_kernel");
+  return QX_OK;
+}
+
+}  // namespace qx
+
+extern "C" int qx_rollout_cost(const QxParams* p, const double* x0, const double* u, double* x, double* cost,
+                               const int32_t* status, int B, int N, void* stream) {
+  QX_CHECK_ARG(p && x0 && u && x && cost, "null pointer");
+  QX_CHECK_ARG(B > 0 && N > 0, "B and N must be positive");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (p->model_id) {
+    case QX_MODEL_CARTPOLE: return qx::launch_rollout<qx::CartPole>(p, x0, u, x, cost, status, B, N, st);
+    case QX_MODEL_QUADROTOR: return qx::launch_rollout<qx::Quadrotor>(p, x0, u, x, cost, status, B, N, st);
+  }
+  qx::set_error("unknown model_id %d", p->model_id);
+  return QX_EINVAL;
+}
+
+extern "C" int qx_linesearch(const QxParams* p, double* x_in, double* u_in, const float* gains, double* cost,
+                             int32_t* status, int32_t* iters, int32_t* alpha, double* x_out, double* u_out,
+                             int32_t* n_active, double tol, uint32_t flags, int B, int N, void* stream) {
+  QX_CHECK_ARG(p && x_in && u_in && gains && cost && status && iters && alpha && x_out && u_out, "null pointer");
+  QX_CHECK_ARG(B > 0 && N > 0, "B and N must be positive");
+  QX_CHECK_ARG(x_in != x_out && u_in != u_out, "in and out buffers must differ");
+  QX_CHECK_ARG((reinterpret_cast<uintptr_t>(gains) & 15u) == 0, "gains must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (p->model_id) {
+    case QX_MODEL_CARTPOLE:
+      return qx::launch_linesearch<qx::CartPole>(p, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out,
+                                                 n_active, tol, flags, B, N, st);
+    case QX_MODEL_QUADROTOR:
+      return qx::launch_linesearch<qx::Quadrotor>(p, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out,
+                                                  n_active, tol, flags, B, N, st);
+  }
+  qx::set_error("unknown model_id %d", p->model_id);
+  return QX_EINVAL;
+}

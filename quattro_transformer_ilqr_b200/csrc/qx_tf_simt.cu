@@ -1,0 +1,269 @@
+// Quattro transformer forward — CUDA-core (SIMT fp32) path.
+//
+//   TransformerILQR.predict          quattro_ilqr_tf/transformer_ilqr.py:311-325
+//   TransformerPredictor.forward     quattro_ilqr_tf/transformer_model.py:122-138
+//   prompt pack / prediction unpack  quattro_ilqr_tf/quattro_ilqr_tf.py:496-518
+// Encoder layer semantics are torch's nn.TransformerEncoderLayer defaults (post-LN, ReLU,
+// LayerNorm eps 1e-5, causal -inf mask over ALL L tokens, 1/sqrt(head_dim) scaling).
+//
+// This file holds the exact-fp32 reference path used for small batches and as the numerics
+// anchor of the tensor-core path (qx_tf_tc.cu): embed -> [QKV GEMM -> attention -> out-proj GEMM
+// -> add+LN -> FFN1 GEMM+ReLU -> FFN2 GEMM -> add+LN] x layers -> output head + de-normalise +
+// unpack into gain records.
+#include "qx_tf_common.cuh"
+
+namespace qx {
+
+// ---- token embedding ---------------------------------------------------------------------------
+// grid (L, B), block d threads.  Token rows: [0, N] states, (N, N+P] prompt, rest targets.
+template <int LAYOUT>
+__global__ void tf_embed_kernel(const QxTfConfig cfg, const float* __restrict__ w, const double* __restrict__ x,
+                                const double* __restrict__ x_shift, const float* __restrict__ gains,
+                                float* __restrict__ h, int B) {
+  const TfLayout lay(cfg);
+  const int tok = blockIdx.x, b = blockIdx.y, ch = threadIdx.x;
+  const int N = cfg.horizon, n = lay.n, c = lay.c, d = lay.d, P = lay.P, m = cfg.m;
+  __shared__ float in[64];
+  float acc;
+  if (tok <= N) {
+    if (ch < n) {
+      // (x - x_ref + state_offset - mean) / std in fp64, then float32  (transformer_ilqr.py:312-315)
+      const double v = x[((size_t)tok * n + ch) * B + b] + x_shift[ch];
+      in[ch] = (float)((v - (double)w[lay.x_mean + ch]) / (double)w[lay.x_std + ch]);
+    }
+    __syncthreads();
+    acc = w[lay.bs + ch];
+    for (int i = 0; i < n; ++i) acc += w[lay.ws + (size_t)ch * n + i] * in[i];
+  } else if (tok <= N + P) {
+    const int t = N - P + (tok - N - 1);             // absolute time of this prompt row
+    if (ch < c) {
+      const int G = m + m * n;
+      const float g = (LAYOUT == QX_LAYOUT_REC) ? gains[((size_t)t * B + b) * G + ch]
+                                                : gains[((size_t)t * G + ch) * B + b];
+      in[ch] = (float)(((double)g - (double)w[lay.u_mean + ch]) / (double)w[lay.u_std + ch]);
+    }
+    __syncthreads();
+    acc = w[lay.bc + ch];
+    for (int i = 0; i < c; ++i) acc += w[lay.wc + (size_t)ch * c + i] * in[i];
+  } else {
+    acc = w[lay.tgt + (size_t)(tok - N - 1 - P) * d + ch];
+  }
+  h[((size_t)b * lay.L + tok) * d + ch] = acc + w[lay.pe + (size_t)tok * d + ch];
+}
+
+// ---- C[M][N] = act(A[M][K] W[N][K]^T + bias) ----------------------------------------------------
+// 64x64 tile, 16-wide K slabs, 256 threads, 4x4 outputs per thread.  N, K multiples of 16 / 64.
+template <bool RELU>
+__global__ void __launch_bounds__(256)
+tf_gemm_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
+               float* __restrict__ C, int M, int N, int K) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Ws[16][64 + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      const int r = e >> 4, kk = e & 15;
+      const int gm = m0 + r, gn = n0 + r;
+      As[kk][r] = (gm < M) ? A[(size_t)gm * K + k0 + kk] : 0.f;
+      Ws[kk][r] = (gn < N) ? W[(size_t)gn * K + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], wv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wv[j] = Ws[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * wv[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j] + bias[gn];
+      if (RELU) v = fmaxf(v, 0.f);
+      C[(size_t)gm * N + gn] = v;
+    }
+  }
+}
+
+// ---- causal multi-head attention: grid (nhead, B), block 128 threads (one query row each) ------
+template <int HD>
+__global__ void __launch_bounds__(128)
+tf_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int L, int d) {
+  extern __shared__ float sm[];
+  float* Ks = sm;                    // [L][HD + 1]
+  float* Vs = sm + (size_t)L * (HD + 1);
+  const int head = blockIdx.x, b = blockIdx.y;
+  const float* base = qkv + (size_t)b * L * 3 * d;
+  for (int e = threadIdx.x; e < L * HD; e += blockDim.x) {
+    const int r = e / HD, cc = e % HD;
+    Ks[r * (HD + 1) + cc] = base[(size_t)r * 3 * d + d + head * HD + cc];
+    Vs[r * (HD + 1) + cc] = base[(size_t)r * 3 * d + 2 * d + head * HD + cc];
+  }
+  __syncthreads();
+  const float scale = rsqrtf((float)HD);
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    float q[HD];
+#pragma unroll
+    for (int cc = 0; cc < HD; ++cc) q[cc] = base[(size_t)i * 3 * d + head * HD + cc];
+    // two passes over keys j <= i: max, then exp-sum and weighted V
+    float mx = -INFINITY;
+    for (int j = 0; j <= i; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < HD; ++cc) s += q[cc] * Ks[j * (HD + 1) + cc];
+      mx = fmaxf(mx, s * scale);
+    }
+    float den = 0.f, o[HD];
+#pragma unroll
+    for (int cc = 0; cc < HD; ++cc) o[cc] = 0.f;
+    for (int j = 0; j <= i; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < HD; ++cc) s += q[cc] * Ks[j * (HD + 1) + cc];
+      const float pj = expf(s * scale - mx);
+      den += pj;
+#pragma unroll
+      for (int cc = 0; cc < HD; ++cc) o[cc] += pj * Vs[j * (HD + 1) + cc];
+    }
+    const float inv = 1.f / den;
+#pragma unroll
+    for (int cc = 0; cc < HD; ++cc) out[((size_t)b * L + i) * d + head * HD + cc] = o[cc] * inv;
+  }
+}
+
+// ---- h = LayerNorm(h + y) * w + b, one warp per row (d == 128) -------------------------------
+__global__ void __launch_bounds__(256)
+tf_add_ln_kernel(float* __restrict__ h, const float* __restrict__ y, const float* __restrict__ w,
+                 const float* __restrict__ bvec, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float4 a = reinterpret_cast<const float4*>(h + (size_t)row * 128)[lane];
+  const float4 r = reinterpret_cast<const float4*>(y + (size_t)row * 128)[lane];
+  a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+  float s = a.x + a.y + a.z + a.w;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mu = s * (1.f / 128.f);
+  const float dx = a.x - mu, dy = a.y - mu, dz = a.z - mu, dw = a.w - mu;
+  float v = dx * dx + dy * dy + dz * dz + dw * dw;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const float rs = rsqrtf(v * (1.f / 128.f) + 1e-5f);
+  const float4 g = reinterpret_cast<const float4*>(w)[lane];
+  const float4 be = reinterpret_cast<const float4*>(bvec)[lane];
+  float4 o4;
+  o4.x = dx * rs * g.x + be.x; o4.y = dy * rs * g.y + be.y; o4.z = dz * rs * g.z + be.z; o4.w = dw * rs * g.w + be.w;
+  reinterpret_cast<float4*>(h + (size_t)row * 128)[lane] = o4;
+}
+
+// ---- output head on the target rows + de-normalise + unpack into gain records ------------------
+// grid (T, B), block 64 threads (>= c).  pred[t].reshape(m, 1+n): k = [:,0], K = [:,1:]
+template <int LAYOUT>
+__global__ void tf_output_kernel(const QxTfConfig cfg, const float* __restrict__ w, const float* __restrict__ h,
+                                 float* __restrict__ gains, const int32_t* __restrict__ status, int B) {
+  const TfLayout lay(cfg);
+  const int t = blockIdx.x, b = blockIdx.y, o = threadIdx.x;
+  if (status != nullptr && status[b] != 0) return;
+  const int d = lay.d, c = lay.c, m = cfg.m, n = lay.n;
+  __shared__ float row[128];
+  const float* hr = h + ((size_t)b * lay.L + (lay.L - lay.T + t)) * d;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) row[i] = hr[i];
+  __syncthreads();
+  if (o >= c) return;
+  float acc = w[lay.bo + o];
+  for (int i = 0; i < d; ++i) acc += w[lay.wo + (size_t)o * d + i] * row[i];
+  const float val = acc * w[lay.u_std + o] + w[lay.u_mean + o];      // float32 de-normalisation
+  const int a = o / (1 + n), j = o % (1 + n);                        // row a of [k_a | K_a,:]
+  const int slot = (j == 0) ? a : (m + a * n + (j - 1));
+  const int G = m + m * n;
+  if (LAYOUT == QX_LAYOUT_REC) gains[((size_t)t * B + b) * G + slot] = val;
+  else gains[((size_t)t * G + slot) * B + b] = val;
+}
+
+static int gemm(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, bool relu,
+                cudaStream_t st) {
+  dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
+  if (relu) tf_gemm_kernel<true><<<grid, 256, 0, st>>>(A, W, bias, C, M, N, K);
+  else tf_gemm_kernel<false><<<grid, 256, 0, st>>>(A, W, bias, C, M, N, K);
+  QX_CHECK_LAUNCH("tf_gemm_kernel");
+  return QX_OK;
+}
+
+int tf_forward_simt(const QxTfConfig* cfg, const float* w, const double* x, const double* x_shift, float* gains,
+                    int layout, const int32_t* status, float* ws, int B, cudaStream_t st) {
+  const TfLayout lay(*cfg);
+  const int d = lay.d, L = lay.L, ff = lay.ff, rows = B * L;
+  float* h = ws;
+  float* qkv = h + (size_t)rows * d;
+  float* att = qkv + (size_t)rows * 3 * d;
+  float* y = att + (size_t)rows * d;
+  float* ffh = y + (size_t)rows * d;
+  dim3 ge(L, B);
+  if (layout == QX_LAYOUT_REC) tf_embed_kernel<QX_LAYOUT_REC><<<ge, d, 0, st>>>(*cfg, w, x, x_shift, gains, h, B);
+  else tf_embed_kernel<QX_LAYOUT_SOA><<<ge, d, 0, st>>>(*cfg, w, x, x_shift, gains, h, B);
+  QX_CHECK_LAUNCH("tf_embed_kernel");
+  const int hd = d / cfg->nhead;
+  const size_t att_smem = (size_t)2 * L * (hd + 1) * sizeof(float);
+  for (int l = 0; l < lay.layers; ++l) {
+    const float* lw = w + lay.layer0 + (size_t)l * lay.layer_stride;
+    int rc = gemm(h, lw + lay.l_inw, lw + lay.l_inb, qkv, rows, 3 * d, d, false, st);
+    if (rc) return rc;
+    tf_attention_kernel<32><<<dim3(cfg->nhead, B), 128, att_smem, st>>>(qkv, att, L, d);
+    QX_CHECK_LAUNCH("tf_attention_kernel");
+    if ((rc = gemm(att, lw + lay.l_outw, lw + lay.l_outb, y, rows, d, d, false, st))) return rc;
+    tf_add_ln_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(h, y, lw + lay.l_n1w, lw + lay.l_n1b, rows);
+    QX_CHECK_LAUNCH("tf_add_ln_kernel");
+    if ((rc = gemm(h, lw + lay.l_w1, lw + lay.l_b1, ffh, rows, ff, d, true, st))) return rc;
+    if ((rc = gemm(ffh, lw + lay.l_w2, lw + lay.l_b2, y, rows, d, ff, false, st))) return rc;
+    tf_add_ln_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(h, y, lw + lay.l_n2w, lw + lay.l_n2b, rows);
+    QX_CHECK_LAUNCH("tf_add_ln_kernel");
+  }
+  dim3 go(lay.T, B);
+  if (layout == QX_LAYOUT_REC) tf_output_kernel<QX_LAYOUT_REC><<<go, 64, 0, st>>>(*cfg, w, h, gains, status, B);
+  else tf_output_kernel<QX_LAYOUT_SOA><<<go, 64, 0, st>>>(*cfg, w, h, gains, status, B);
+  QX_CHECK_LAUNCH("tf_output_kernel");
+  return QX_OK;
+}
+
+}  // namespace qx
+
+extern "C" size_t qx_tf_weight_floats(const QxTfConfig* cfg) {
+  if (!cfg) return 0;
+  return qx::TfLayout(*cfg).total;
+}
+
+extern "C" size_t qx_tf_workspace_bytes(const QxTfConfig* cfg, int B) {
+  if (!cfg || B <= 0) return 0;
+  const qx::TfLayout lay(*cfg);
+  return (size_t)B * lay.L * (6 * (size_t)lay.d + lay.ff) * sizeof(float);
+}
+
+extern "C" int qx_tf_forward(const QxTfConfig* cfg, const float* weights, const double* x, const double* x_shift,
+                             float* gains, int model_id, const int32_t* status, void* workspace, int B,
+                             void* stream) {
+  QX_CHECK_ARG(cfg && weights && x && x_shift && gains && workspace, "null pointer");
+  QX_CHECK_ARG(B > 0, "B must be positive");
+  QX_CHECK_ARG(cfg->d_model == 128 && cfg->d_model / cfg->nhead == 32, "kernels are built for d_model 128, head_dim 32");
+  QX_CHECK_ARG(cfg->control_dim <= 64 && cfg->state_dim <= 64, "state/control dims must be <= 64");
+  QX_CHECK_ARG(cfg->dim_ff % 64 == 0, "dim_feedforward must be a multiple of 64");
+  QX_CHECK_ARG(cfg->control_dim == cfg->m * (1 + cfg->state_dim), "control_dim must equal m (1 + n)");
+  QX_CHECK_ARG(cfg->horizon == cfg->target_len + cfg->prompt_len, "horizon must equal target_len + prompt_len");
+  const int layout = qx_layout(model_id);
+  if (layout < 0) return layout;
+  return qx::tf_forward_simt(cfg, weights, x, x_shift, gains, layout, status, static_cast<float*>(workspace), B,
+                             static_cast<cudaStream_t>(stream));
+}

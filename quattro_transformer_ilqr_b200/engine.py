@@ -1,0 +1,188 @@
+"""Batched iLQR engine: device buffers + the per-iteration kernel sequence.
+
+One iteration of the reference's ``optimize`` loop (quattro_ilqr_tf/quattro_ilqr_tf.py:428-475)
+for B independent trajectories is
+
+    [rollout + cost]      only before the first iteration; afterwards the accepted candidate of the
+                          line search IS the next nominal (SURVEY.md a-Q(11))
+    qx_linearize          A_t, B_t, cost expansions for the whole horizon     (:182-275)
+    qx_riccati            K_t, k_t                                             (:282-319 / :327-366)
+    [qx_tf_forward]       transformer mode: predicted gains for t < N - P      (:489-543)
+    qx_linesearch         first accepted alpha, stopping rule, next iterate    (:440-472)
+
+PyTorch only owns memory and streams here; all arithmetic is in libquattro_sm100a.so.
+Device layouts are documented in include/quattro_b200.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .device_models import DeviceModel
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class BatchedILQR:
+    def __init__(self, model: DeviceModel, B: int, N: int, device=None, tf=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("quattro_transformer_ilqr_b200 needs a CUDA device (B200, sm_100a); no CPU fallback")
+        self.lib = _lib.load()
+        self.model, self.B, self.N = model, int(B), int(N)
+        self.n, self.m = model.n, model.m
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.tf = tf
+        n, m, mid = self.n, self.m, model.model_id
+        dev, f64, f32, i32 = self.device, torch.float64, torch.float32, torch.int32
+        self.layout = self.lib.qx_layout(mid)
+        self.rec = self.lib.qx_record_floats(mid)
+        self.x = [torch.zeros((N + 1, n, B), dtype=f64, device=dev) for _ in range(2)]
+        self.u = [torch.zeros((N, m, B), dtype=f64, device=dev) for _ in range(2)]
+        self.x0 = torch.zeros((n, B), dtype=f64, device=dev)
+        self.cost = torch.zeros(B, dtype=f64, device=dev)
+        self.status = torch.zeros(B, dtype=i32, device=dev)
+        self.iters = torch.zeros(B, dtype=i32, device=dev)
+        self.alpha = torch.full((B,), -1, dtype=i32, device=dev)
+        self.n_active = torch.zeros(1, dtype=i32, device=dev)
+        self.expansion = torch.zeros(self.lib.qx_expansion_bytes(mid, B, N) // 4, dtype=f32, device=dev)
+        self.terminal = torch.zeros(self.lib.qx_terminal_bytes(mid, B) // 4, dtype=f32, device=dev)
+        self.gains = torch.zeros(self.lib.qx_gains_bytes(mid, B, N) // 4, dtype=f32, device=dev)
+        self.cur = 0
+        self.params = model.params()
+        self.launches = 0          # kernels launched through the C ABI (bench.py reports it)
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def refresh_params(self):
+        self.params = self.model.params()
+
+    def set_problem(self, x0, u_init, rollout=True):
+        """x0 (B, n), u_init (B, N, m): host arrays or tensors (any device); resets the solver state."""
+        B, N, n, m = self.B, self.N, self.n, self.m
+        x0 = torch.as_tensor(x0, dtype=torch.float64)
+        u = torch.as_tensor(u_init, dtype=torch.float64)
+        if tuple(x0.shape) != (B, n) or tuple(u.shape) != (B, N, m):
+            raise ValueError(f"expected x0 {(B, n)} and u_init {(B, N, m)}, got {tuple(x0.shape)}, {tuple(u.shape)}")
+        self.x0.copy_(x0.to(self.device, non_blocking=True).t())
+        self.u[self.cur].copy_(u.to(self.device, non_blocking=True).permute(1, 2, 0))
+        self.status.zero_()
+        self.iters.zero_()
+        self.alpha.fill_(-1)
+        self.refresh_params()
+        if rollout:
+            self.rollout()
+
+    # ------------------------------------------------------------------ kernels
+    def rollout(self):
+        c = self.cur
+        _lib.check(self.lib.qx_rollout_cost(C.byref(self.params), _ptr(self.x0), _ptr(self.u[c]), _ptr(self.x[c]),
+                                            _ptr(self.cost), None, self.B, self.N, self.stream), "qx_rollout_cost")
+        self.launches += 1
+
+    def linearize(self, t_start=0):
+        c = self.cur
+        _lib.check(self.lib.qx_linearize(C.byref(self.params), _ptr(self.x[c]), _ptr(self.u[c]), _ptr(self.expansion),
+                                         _ptr(self.terminal), _ptr(self.status), self.B, self.N, t_start, self.stream),
+                   "qx_linearize")
+        self.launches += 1
+
+    def riccati(self, t_start=0, reg=1e-6):
+        _lib.check(self.lib.qx_riccati(self.model.model_id, _ptr(self.expansion), _ptr(self.terminal), _ptr(self.gains),
+                                       _ptr(self.status), self.B, self.N, t_start, C.c_float(reg), self.stream),
+                   "qx_riccati")
+        self.launches += 1
+
+    def linesearch(self, tol, force=False):
+        c = self.cur
+        self.n_active.zero_()
+        _lib.check(self.lib.qx_linesearch(C.byref(self.params), _ptr(self.x[c]), _ptr(self.u[c]), _ptr(self.gains),
+                                          _ptr(self.cost), _ptr(self.status), _ptr(self.iters), _ptr(self.alpha),
+                                          _ptr(self.x[1 - c]), _ptr(self.u[1 - c]), _ptr(self.n_active), float(tol),
+                                          _lib.QX_LS_FORCE_ACTIVE if force else 0, self.B, self.N, self.stream),
+                   "qx_linesearch")
+        self.launches += 1
+        self.cur = 1 - c
+
+    def backward(self):
+        """Gains for the whole horizon: Riccati, or Riccati tail + transformer head."""
+        if self.tf is None:
+            self.linearize(0)
+            self.riccati(0)
+        else:
+            start = self.N - self.tf.prompt_len
+            self.linearize(start)
+            self.riccati(start)
+            self.tf.forward_device(self)
+
+    def iterate(self, tol=1e-3, force=False):
+        self.backward()
+        self.linesearch(tol, force)
+
+    def solve(self, max_iter=100, tol=1e-3, fixed_iters=None, check_every=1):
+        """Run to convergence (reference stopping rule, per trajectory) or for exactly
+        ``fixed_iters`` forced iterations.  Returns the number of batch iterations launched."""
+        if fixed_iters is not None:
+            for _ in range(fixed_iters):
+                self.iterate(tol, force=True)
+            return fixed_iters
+        done = 0
+        for it in range(max_iter):
+            self.iterate(tol)
+            done = it + 1
+            if (it + 1) % check_every == 0 and int(self.n_active.item()) == 0:
+                break
+        return done
+
+    # ------------------------------------------------------------------ views in the user layout
+    def u_batch(self):
+        return self.u[self.cur].permute(2, 0, 1).contiguous()          # (B, N, m)
+
+    def x_batch(self):
+        return self.x[self.cur].permute(2, 0, 1).contiguous()          # (B, N+1, n)
+
+    def gains_batch(self):
+        """K (B, N, m, n), k (B, N, m) as float32 tensors."""
+        B, N, n, m = self.B, self.N, self.n, self.m
+        G = m + m * n
+        if self.layout == _lib.QX_LAYOUT_REC:
+            g = self.gains.view(N, B, G).permute(1, 0, 2)
+        else:
+            g = self.gains.view(N, G, B).permute(2, 0, 1)
+        return g[..., m:].reshape(B, N, m, n).contiguous(), g[..., :m].contiguous()
+
+    def load_gains(self, K, k):
+        """Upload gains given as K (B, N, m, n), k (B, N, m) into the device record layout."""
+        B, N, n, m = self.B, self.N, self.n, self.m
+        g = torch.cat([torch.as_tensor(k, dtype=torch.float32).reshape(B, N, m),
+                       torch.as_tensor(K, dtype=torch.float32).reshape(B, N, m * n)], dim=-1).to(self.device)
+        if self.layout == _lib.QX_LAYOUT_REC:
+            self.gains.copy_(g.permute(1, 0, 2).reshape(-1))
+        else:
+            self.gains.copy_(g.permute(1, 2, 0).reshape(-1))
+
+    def expansion_batch(self):
+        """dict of (B, N, ...) float32 tensors decoded from the record layout (tests / debugging)."""
+        B, N, n, m, R = self.B, self.N, self.n, self.m, self.rec
+        if self.layout == _lib.QX_LAYOUT_REC:
+            e = self.expansion.view(N, B, R).permute(1, 0, 2)
+            t = self.terminal.view(B, n + n * n)
+        else:
+            e = self.expansion.view(N, R, B).permute(2, 0, 1)
+            t = self.terminal.view(n + n * n, B).t()
+        o, out = 0, {}
+        for name, shape in (("A", (n, n)), ("B", (n, m)), ("lx", (n,)), ("lu", (m,)), ("lxx", (n, n)),
+                            ("luu", (m, m)), ("lux", (m, n))):
+            sz = int(np.prod(shape))
+            out[name] = e[..., o:o + sz].reshape((B, N) + shape)
+            o += sz
+        out["VxN"] = t[:, :n]
+        out["VxxN"] = t[:, n:].reshape(B, n, n)
+        return out

@@ -1,0 +1,252 @@
+"""``TransformerILQR`` — load / save / predict wrapper around the CUDA transformer kernels.
+
+Mirror of quattro_ilqr_tf/transformer_ilqr.py:24-325 of the reference: same constructor, ``load``
+(:259-304), ``save`` (:213-254), ``predict`` (:311-325), ``fit`` (:102-208), attributes ``model``,
+``normalizer``, ``device``, ``prompt_len``, ``target_len``.  ``predict`` and the in-solver
+``forward_device`` run csrc/qx_tf_*.cu through the C ABI (``qx_tf_forward``): normalise -> embed ->
+encoder layers -> output head -> de-normalise -> unpack, with no PyTorch operator on the path.
+
+Checkpoints saved with ``quant_mode="float16"`` (both shipped ones) are loaded as the same fp16
+values widened to fp32: the kernels compute in fp32, which is MORE accurate than the reference's
+fp16 CPU inference (measured gap of the reference's own two modes: ~3e-4 relative).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import datetime
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from .transformer_model import DataNormalizer, TransformerPredictor
+
+
+class TransformerILQR:
+    def __init__(self, state_dim, control_dim, prompt_len=10, d_model=64, nhead=8, num_decoder_layers=3,
+                 dim_feedforward=128, dropout=0.1, max_seq_len=100, quant_mode="none"):
+        self.state_dim, self.control_dim, self.prompt_len = state_dim, control_dim, prompt_len
+        self.d_model, self.nhead, self.num_decoder_layers = d_model, nhead, num_decoder_layers
+        self.dim_feedforward, self.dropout, self.max_seq_len = dim_feedforward, dropout, max_seq_len
+        self.quant_mode = quant_mode
+        self.target_len = None
+        self.num_epochs = 0
+        self.device = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+        self.model = None
+        self.normalizer = DataNormalizer()
+        self._packed = None          # (device, float32 tensor) cache of the packed weights
+        self._shift = None
+        self._ws = None
+        self._solo = None            # 1-trajectory scratch engine state for predict()
+
+    # ------------------------------------------------------------------ checkpoint wire format
+    def _build_model(self):
+        return TransformerPredictor(self.state_dim, self.control_dim, self.d_model, self.nhead,
+                                    self.num_decoder_layers, self.dim_feedforward, self.dropout, self.max_seq_len,
+                                    self.target_len, self.prompt_len)
+
+    def load(self, model_path):
+        data = np.load(os.path.join(model_path, "tf_model_normalizer.npz"), allow_pickle=True)
+        nz = self.normalizer
+        nz.x_mean, nz.x_std, nz.u_mean, nz.u_std = data["x_mean"], data["x_std"], data["u_mean"], data["u_std"]
+        for key in ("target_len", "prompt_len", "state_dim", "control_dim", "d_model", "nhead",
+                    "num_decoder_layers", "dim_feedforward", "max_seq_len", "num_epochs"):
+            setattr(self, key, int(data[key]))
+        self.dropout = float(data["dropout"])
+        self.quant_mode = str(data["quant_mode"])
+        if self.quant_mode == "int8":
+            raise NotImplementedError("int8 dynamically-quantised checkpoints are not supported by the CUDA path")
+        self.model = self._build_model()
+        sd = torch.load(os.path.join(model_path, "tf_model.pt"), map_location="cpu")
+        self.model.load_state_dict({k: v.float() for k, v in sd.items()})
+        self.model.eval()
+        self._packed = None
+        print(f"Model loaded from directory: {model_path}")
+        return self
+
+    def save(self, base_name):
+        total = sum(p.numel() for p in self.model.parameters())
+        size = f"{total / 1e6:.1f}M" if total >= 1e6 else (f"{total / 1e3:.1f}k" if total >= 1e3 else str(total))
+        hyper = (f"decoder_dec{self.num_decoder_layers}_dmodel{self.d_model}_nhead{self.nhead}_ff{self.dim_feedforward}"
+                 f"_drop{self.dropout}_epoch{self.num_epochs}_promptlen{self.prompt_len}")
+        stamp = datetime.datetime.now().strftime("%Y%m%d_%H%M")
+        dir_name = f"{stamp}_{base_name}_{hyper}_{size}"
+        os.makedirs(dir_name, exist_ok=True)
+        sd = self.model.state_dict()
+        if self.quant_mode == "float16":
+            sd = {k: v.half() for k, v in sd.items()}
+        elif self.quant_mode == "int8":
+            raise NotImplementedError("int8 export is not supported")
+        torch.save(sd, os.path.join(dir_name, "tf_model.pt"))
+        nz = self.normalizer
+        np.savez(os.path.join(dir_name, "tf_model_normalizer.npz"), x_mean=nz.x_mean, x_std=nz.x_std,
+                 u_mean=nz.u_mean, u_std=nz.u_std, target_len=self.target_len, prompt_len=self.prompt_len,
+                 state_dim=self.state_dim, control_dim=self.control_dim, d_model=self.d_model, nhead=self.nhead,
+                 num_decoder_layers=self.num_decoder_layers, dim_feedforward=self.dim_feedforward,
+                 dropout=self.dropout, max_seq_len=self.max_seq_len, num_epochs=self.num_epochs,
+                 quant_mode=self.quant_mode)
+        print(f"Model saved to {dir_name}")
+        return dir_name
+
+    # ------------------------------------------------------------------ device side
+    def _m(self):
+        return self.control_dim // (1 + self.state_dim)
+
+    def config(self):
+        cfg = _lib.QxTfConfig()
+        cfg.state_dim, cfg.control_dim, cfg.d_model, cfg.nhead = self.state_dim, self.control_dim, self.d_model, self.nhead
+        cfg.num_layers, cfg.dim_ff = self.num_decoder_layers, self.dim_feedforward
+        cfg.target_len, cfg.prompt_len = self.target_len, self.prompt_len
+        cfg.horizon = self.target_len + self.prompt_len
+        cfg.m = self._m()
+        return cfg
+
+    def pack_weights(self):
+        """Flatten normaliser + state_dict into the order of csrc/qx_tf_common.cuh (host tensor)."""
+        sd = {k: v.detach().float().cpu() for k, v in self.model.state_dict().items()}
+        nz = self.normalizer
+        L = (self.target_len + self.prompt_len + 1) + self.prompt_len + self.target_len
+        parts = [torch.as_tensor(np.asarray(a, dtype=np.float32)) for a in (nz.x_mean, nz.x_std, nz.u_mean, nz.u_std)]
+        parts += [sd["state_embed.weight"], sd["state_embed.bias"], sd["control_embed.weight"], sd["control_embed.bias"],
+                  sd["target_embedding"], sd["pos_encoder.pe"][0, :L]]
+        for l in range(self.num_decoder_layers):
+            p = f"transformer_decoder.layers.{l}."
+            parts += [sd[p + k] for k in ("self_attn.in_proj_weight", "self_attn.in_proj_bias", "self_attn.out_proj.weight",
+                                          "self_attn.out_proj.bias", "linear1.weight", "linear1.bias", "linear2.weight",
+                                          "linear2.bias", "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias")]
+        parts += [sd["output_linear.weight"], sd["output_linear.bias"]]
+        flat = torch.cat([p.reshape(-1) for p in parts]).contiguous()
+        cfg = self.config()
+        expect = _lib.load().qx_tf_weight_floats(C.byref(cfg))
+        if flat.numel() != expect:
+            raise RuntimeError(f"packed weights have {flat.numel()} floats, the library expects {expect}")
+        return flat
+
+    def _device_weights(self, device):
+        if self._packed is None or self._packed[0] != device:
+            self._packed = (device, self.pack_weights().to(device))
+        return self._packed[1]
+
+    def invalidate(self):
+        """Call after mutating ``model`` / ``normalizer`` in place (e.g. after training)."""
+        self._packed = None
+
+    def set_shift(self, shift, device):
+        """x_seq_err = x_seq + shift, shift = state_offset - x_ref (quattro_ilqr_tf.py:504/:532)."""
+        self._shift = torch.as_tensor(np.asarray(shift, dtype=np.float64), device=device)
+
+    def forward_device(self, engine):
+        """Predict gains for t < target_len from the engine's current trajectories and the Riccati
+        tail already in ``engine.gains``; writes the predicted records into ``engine.gains``."""
+        lib = _lib.load()
+        cfg = self.config()
+        dev = engine.device
+        w = self._device_weights(dev)
+        need = lib.qx_tf_workspace_bytes(C.byref(cfg), engine.B)
+        if self._ws is None or self._ws.device != dev or self._ws.numel() * 4 < need:
+            self._ws = torch.empty(need // 4, dtype=torch.float32, device=dev)
+        if self._shift is None or self._shift.device != dev:
+            self.set_shift(np.zeros(self.state_dim), dev)
+        c = engine.cur
+        _lib.check(lib.qx_tf_forward(C.byref(cfg), C.c_void_p(w.data_ptr()), C.c_void_p(engine.x[c].data_ptr()),
+                                     C.c_void_p(self._shift.data_ptr()), C.c_void_p(engine.gains.data_ptr()),
+                                     engine.model.model_id, C.c_void_p(engine.status.data_ptr()),
+                                     C.c_void_p(self._ws.data_ptr()), engine.B, engine.stream), "qx_tf_forward")
+        engine.launches += 3 + 7 * self.num_decoder_layers
+
+    def predict(self, x_seq, kK_seq):
+        """x_seq (T, n) [or (B, T, n)], kK_seq (>= prompt_len, c): de-normalised predictions
+        (target_len, c) as float32 — reference ``predict`` (transformer_ilqr.py:311-325)."""
+        from .device_models import DeviceModel
+        from .engine import BatchedILQR
+        x = np.asarray(x_seq, dtype=np.float64)
+        kK = np.asarray(kK_seq, dtype=np.float64)
+        single = x.ndim == 2
+        if single:
+            x, kK = x[None], kK[None]
+        B, N, n, m, P = x.shape[0], x.shape[1] - 1, self.state_dim, self._m(), self.prompt_len
+        name = {(4, 1): "cartpole", (12, 4): "quadrotor"}.get((n, m))
+        if name is None:
+            raise ValueError("predict needs a built-in system shape (4x1 or 12x4)")
+        solo = self._solo
+        if solo is None or solo.B != B or solo.N != N or solo.model.name != name:
+            solo = self._solo = BatchedILQR(DeviceModel(name), B, N)
+        solo.x[solo.cur].copy_(torch.as_tensor(x).to(solo.device).permute(1, 2, 0))
+        # prompt rows -> the last P gain records, inverse of the pack [k | K row-major]
+        K_full = torch.zeros((B, N, m, n), dtype=torch.float32)
+        k_full = torch.zeros((B, N, m), dtype=torch.float32)
+        tail = torch.as_tensor(kK[:, -P:, :], dtype=torch.float32)
+        k_full[:, N - P:] = tail[..., :m]
+        K_full[:, N - P:] = tail[..., m:].reshape(B, P, m, n)
+        solo.load_gains(K_full, k_full)
+        solo.status.zero_()
+        self.set_shift(np.zeros(n), solo.device)
+        self.forward_device(solo)
+        K, k = solo.gains_batch()
+        T = self.target_len
+        pred = torch.cat([k[:, :T, :, None], K[:, :T]], dim=-1).reshape(B, T, m * (1 + n)).cpu().numpy()
+        return pred[0] if single else pred
+
+    # ------------------------------------------------------------------ training (PyTorch autograd; off the hot path)
+    def _create_dataset(self, df):
+        xs, kKs = [], []
+        for _, row in df.iterrows():
+            x = np.array(row["x_seq"], dtype=np.float32)
+            k = np.array(row["k_seq"], dtype=np.float32)[..., None]
+            K = np.array(row["K_seq"], dtype=np.float32)
+            kK = np.concatenate([k, K], axis=-1).reshape(k.shape[0], -1)
+            if kK.shape[0] <= self.prompt_len:
+                continue
+            xs.append(x)
+            kKs.append(kK)
+        return np.array(xs), np.array(kKs)
+
+    def fit(self, df, test_df=None, num_epochs=50, batch_size=16, learning_rate=1e-3, patience=5):
+        x_data, kK_data = self._create_dataset(df)
+        T = x_data.shape[1]
+        self.target_len = T - self.prompt_len
+        nz = self.normalizer
+        nz.fit(x_data, kK_data)
+        xin = torch.tensor(nz.transform_x(x_data)).float()
+        kK = torch.tensor(nz.transform_u(kK_data)).float()
+        prompt, target = kK[:, -self.prompt_len:], kK[:, : T - self.prompt_len]
+        self.model = self._build_model().to(self.device)
+        self.num_epochs = num_epochs
+        opt = torch.optim.Adam(self.model.parameters(), lr=learning_rate)
+        loss_fn = torch.nn.MSELoss()
+        if test_df is not None:
+            xt, kKt = self._create_dataset(test_df)
+            xt = torch.tensor(nz.transform_x(xt)).float().to(self.device)
+            kKt = torch.tensor(nz.transform_u(kKt)).float().to(self.device)
+        best, stale, best_state = float("inf"), 0, None
+        self.train_loss_history, self.test_loss_history = [], []
+        ds = torch.utils.data.TensorDataset(xin, prompt, target)
+        loader = torch.utils.data.DataLoader(ds, batch_size=batch_size, shuffle=True)
+        for epoch in range(num_epochs):
+            self.model.train()
+            tot = 0.0
+            for xb, pb, tb in loader:
+                xb, pb, tb = xb.to(self.device), pb.to(self.device), tb.to(self.device)
+                opt.zero_grad()
+                loss = loss_fn(self.model(xb, pb), tb)
+                loss.backward()
+                opt.step()
+                tot += loss.item() * xb.size(0)
+            self.train_loss_history.append(tot / len(ds))
+            if test_df is not None:
+                self.model.eval()
+                with torch.no_grad():
+                    tl = loss_fn(self.model(xt, kKt[:, -self.prompt_len:]), kKt[:, : xt.shape[1] - self.prompt_len]).item()
+                self.test_loss_history.append(tl)
+                if tl < best:
+                    best, stale = tl, 0
+                    best_state = {k: v.clone() for k, v in self.model.state_dict().items()}
+                else:
+                    stale += 1
+                if stale >= patience:
+                    self.model.load_state_dict(best_state)
+                    break
+        self.model.eval()
+        self._packed = None
+        return self

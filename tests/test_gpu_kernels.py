@@ -1,0 +1,181 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (engine methods are 1:1 wrappers).
+
+Each CUDA kernel is checked against the NumPy oracle on the same seeded inputs.  Tolerances:
+fp64 rollouts/costs 1e-12; fp32 linearisation 2e-6; fp32 Riccati gains 1e-5 (max-norm relative per
+tensor, SURVEY.md hard part 2); line-search decisions identical.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ilqr_batched as ob
+from oracle.models import make_model, sample_x0
+from tests.util import HORIZON, relmax
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(system, B, method="euler", **kw):
+    from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel
+    return BatchedILQR(DeviceModel(system, integration_method=method, **kw), B, HORIZON[system])
+
+
+def _problem(system, B, seed, u_scale):
+    rng = np.random.default_rng(seed)
+    model = make_model(system)
+    x0 = sample_x0(system, B, seed=seed)
+    u = u_scale * rng.standard_normal((B, HORIZON[system], model.m))
+    if system == "quadrotor":
+        u += 2.45                                  # around hover thrust, both signs of the barrier
+    return x0, u
+
+
+CASES = [("cartpole", 257, 5.0), ("quadrotor", 97, 1.5)]
+
+
+@pytest.mark.parametrize("system,B,us", CASES)
+@pytest.mark.parametrize("method", ["euler", "rk4"])
+def test_rollout_cost(system, B, us, method):
+    x0, u = _problem(system, B, 1, us)
+    e = _engine(system, B, method)
+    e.set_problem(x0, u)
+    x_ref, c_ref = ob.rollout(make_model(system, method=method), x0, u)
+    assert relmax(e.x_batch().cpu().numpy(), x_ref) < 1e-12
+    assert relmax(e.cost.cpu().numpy(), c_ref) < 1e-12
+
+
+@pytest.mark.parametrize("system,B,us", CASES)
+@pytest.mark.parametrize("method", ["euler", "rk4"])
+def test_linearize(system, B, us, method):
+    x0, u = _problem(system, B, 2, us)
+    e = _engine(system, B, method)
+    e.set_problem(x0, u)
+    e.linearize(0)
+    got = {k: v.cpu().numpy() for k, v in e.expansion_batch().items()}
+    model = make_model(system, method=method)
+    ref = ob.linearize(model, *ob.rollout(model, x0, u)[:1], u)
+    for key in ("A", "B", "lx", "lu", "lxx", "luu", "lux", "VxN", "VxxN"):
+        if np.abs(ref[key]).max() == 0:
+            assert np.abs(got[key]).max() == 0, key
+        else:
+            assert relmax(got[key], ref[key]) < (2e-6 if method == "euler" else 5e-6), key
+
+
+def test_linearize_dense_cost_matrices():
+    """Non-diagonal Q / R / Qf take the general path (L_x = (Q + Q^T) dx, L_xx = Q + Q^T)."""
+    rng = np.random.default_rng(5)
+    Q = np.diag([5.0, 0.1, 10.0, 0.1]) + 0.05 * rng.standard_normal((4, 4))
+    Qf = np.diag([50.0, 6.0, 100.0, 0.1]) + 0.5 * rng.standard_normal((4, 4))
+    x0, u = _problem("cartpole", 64, 5, 5.0)
+    e = _engine("cartpole", 64, Q=Q, Qf=Qf, x_ref=np.array([0.1, 0, -0.05, 0]))
+    e.set_problem(x0, u)
+    e.linearize(0)
+    model = make_model("cartpole", Q=Q, Qf=Qf, x_ref=np.array([0.1, 0, -0.05, 0]))
+    x_ref, c_ref = ob.rollout(model, x0, u)
+    assert relmax(e.cost.cpu().numpy(), c_ref) < 1e-12
+    ref = ob.linearize(model, x_ref, u)
+    got = {k: v.cpu().numpy() for k, v in e.expansion_batch().items()}
+    for key in ("lx", "lxx", "VxN", "VxxN"):
+        assert relmax(got[key], ref[key]) < 2e-6, key
+
+
+@pytest.mark.parametrize("system,B,us", CASES)
+@pytest.mark.parametrize("t_start", [0, "segment"])
+def test_riccati(system, B, us, t_start):
+    """Full pass and the segment variant (backward_pass_segment) against the fp64 oracle."""
+    x0, u = _problem(system, B, 3, 0.3 * us)
+    N = HORIZON[system]
+    ts = 0 if t_start == 0 else (N - 5 if system == "cartpole" else N - 1)
+    e = _engine(system, B)
+    e.set_problem(x0, u)
+    e.gains.fill_(float("nan"))
+    e.linearize(ts)
+    e.riccati(ts)
+    K, k = (t.cpu().numpy() for t in e.gains_batch())
+    model = make_model(system)
+    x_ref, _ = ob.rollout(model, x0, u)
+    K_ref, k_ref = ob.riccati(ob.linearize(model, x_ref, u), ts)
+    assert np.isnan(K[:, :ts]).all() and not np.isnan(K[:, ts:]).any()        # only [t_start, N) written
+    assert relmax(K[:, ts:], K_ref) < 1e-5 and relmax(k[:, ts:], k_ref) < 1e-5
+    # per time step too (early steps have much smaller gains than the tail)
+    for t in range(ts, N):
+        assert relmax(K[:, t], K_ref[:, t - ts]) < 5e-5, t
+
+
+@pytest.mark.parametrize("system,B,us", CASES)
+def test_linesearch_decisions_and_candidates(system, B, us):
+    """Same gains on both sides (the oracle's, rounded to fp32): identical accepted alpha,
+    candidates and costs to fp64 round-off; covers alphas other than 1 and the no-accept case."""
+    x0, u = _problem(system, B, 4, 0.5 * us)
+    model = make_model(system)
+    x_ref, c_ref = ob.rollout(model, x0, u)
+    K, k = ob.riccati(ob.linearize(model, x_ref, u))
+    rng = np.random.default_rng(0)
+    # spoil some gains so that smaller alphas (and outright rejection) occur
+    scale = rng.choice([1.0, 3.0, 8.0, -1.0], size=B, p=[0.4, 0.25, 0.2, 0.15])
+    k = (k * scale[:, None, None]).astype(np.float32)
+    K = K.astype(np.float32)
+    e = _engine(system, B)
+    e.set_problem(x0, u)
+    e.load_gains(K, k)
+    e.linesearch(tol=1e-3)
+    xn, un, cn, idx, margins = ob.line_search(model, x_ref, u, K.astype(np.float64), k.astype(np.float64), c_ref)
+    got_idx = e.alpha.cpu().numpy()
+    assert len(set(idx.tolist())) >= 3, "test should exercise several alphas"
+    assert (idx == -1).any()
+    assert np.array_equal(got_idx, idx)
+    assert relmax(e.cost.cpu().numpy(), cn) < 1e-12
+    assert relmax(e.u_batch().cpu().numpy(), un) < 1e-11
+    assert relmax(e.x_batch().cpu().numpy(), xn) < 1e-11
+    done_ref = (idx < 0) | (np.abs(c_ref - cn) < 1e-3)
+    assert np.array_equal(e.status.cpu().numpy() != 0, done_ref)
+    assert int(e.n_active.item()) == int((~done_ref).sum())
+    assert (e.iters.cpu().numpy() == 1).all()
+    # finished trajectories hold their final iterate in BOTH ping-pong buffers
+    fin = torch.as_tensor(done_ref, device=e.device)
+    assert torch.equal(e.u[0][:, :, fin], e.u[1][:, :, fin]) and torch.equal(e.x[0][:, :, fin], e.x[1][:, :, fin])
+
+
+def test_inactive_trajectories_are_untouched():
+    x0, u = _problem("quadrotor", 70, 6, 0.5)
+    e = _engine("quadrotor", 70)
+    e.set_problem(x0, u)
+    e.status[::3] = 1
+    before = (e.u[e.cur].clone(), e.cost.clone())
+    e.iterate(tol=1e-3)
+    frozen = (e.status != 0).cpu()
+    assert (e.iters.cpu()[::3] == 0).all() and (e.iters.cpu()[1::3] == 1).all()
+    assert torch.equal(e.cost[::3], before[1][::3])
+    assert not torch.equal(e.cost[1::3], before[1][1::3])
+    assert frozen[::3].all()
+
+
+@pytest.mark.parametrize("B", [1, 31, 33, 129])
+def test_ragged_batch_sizes(B):
+    """Tail warps / partial bulk-copy chunks: every trajectory equals its B=1 solve bit for bit."""
+    x0, u = _problem("quadrotor", B, 7, 0.5)
+    e = _engine("quadrotor", B)
+    e.set_problem(x0, u)
+    e.solve(fixed_iters=2)
+    ref = ob.optimize(make_model("quadrotor"), x0, u, fixed_iters=2)
+    assert np.array_equal(e.alpha.cpu().numpy(), ref["alpha_idx"])
+    assert relmax(e.cost.cpu().numpy(), ref["cost"]) < 1e-5
+    e1 = _engine("quadrotor", 1)
+    e1.set_problem(x0[-1:], u[-1:])
+    e1.solve(fixed_iters=2)
+    assert torch.equal(e1.u_batch()[0], e.u_batch()[-1])       # no cross-trajectory arithmetic
+
+
+def test_abi_rejects_bad_arguments():
+    import ctypes as C
+    from quattro_transformer_ilqr_b200 import _lib
+    e = _engine("cartpole", 8)
+    lib = _lib.load()
+    rc = lib.qx_linesearch(C.byref(e.params), e.x[0].data_ptr(), e.u[0].data_ptr(), e.gains.data_ptr(),
+                           e.cost.data_ptr(), e.status.data_ptr(), e.iters.data_ptr(), e.alpha.data_ptr(),
+                           e.x[0].data_ptr(), e.u[0].data_ptr(), None, 1e-3, 0, 8, 30, None)
+    assert rc == -1 and b"must differ" in lib.qx_last_error()
+    with pytest.raises(ValueError):
+        e.set_problem(np.zeros((8, 5)), np.zeros((8, 30, 1)))
+    with pytest.raises(RuntimeError, match="qx_riccati failed"):
+        e.riccati(t_start=30)

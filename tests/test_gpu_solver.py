@@ -1,0 +1,209 @@
+"""GPU parity tests of the whole solve: against the batched oracle, against golden runs of the
+unmodified reference (through the reference-facing iLQR_TF API), and size-independent properties
+at the benchmark's full batch size."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ilqr_batched as ob
+from oracle.models import make_model, sample_x0
+from tests.util import HORIZON, TOL, checkpoint_dir, golden_runs, relmax
+
+pytestmark = pytest.mark.gpu
+
+
+def _mpc(system, **kw):
+    from quattro_transformer_ilqr_b200.mpc import CartPoleMPC, QuadrotorMPC
+    if system == "cartpole":
+        return CartPoleMPC(horizon=30, dt=0.01, integration_method=kw.pop("method", "euler"), ilqr_only="transformer_model" not in kw,
+                           ilqr_tf_only="transformer_model" in kw, **kw)
+    return QuadrotorMPC(horizon=50, dt=0.01, integration_method=kw.pop("method", "euler"), **kw)
+
+
+@pytest.mark.parametrize("system,B", [("cartpole", 512), ("quadrotor", 128)])
+def test_batched_solve_matches_oracle(system, B):
+    """Run to convergence: per-trajectory iteration counts, every line-search decision, final
+    u / x / cost vs the fp64 exact-derivative oracle (1e-5, the north-star tolerance)."""
+    from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel
+    N = HORIZON[system]
+    model = make_model(system)
+    x0 = sample_x0(system, B, seed=21)
+    u0 = np.zeros((B, N, model.m))
+    e = BatchedILQR(DeviceModel(system), B, N)
+    e.set_problem(x0, u0)
+    alphas = []
+    for it in range(100):
+        act = (e.status == 0).cpu().numpy()
+        e.iterate(tol=TOL[system])
+        alphas.append(np.where(act, e.alpha.cpu().numpy(), -9))
+        if int(e.n_active.item()) == 0:
+            break
+    ref = ob.optimize(model, x0, u0, tol=TOL[system], keep_logs=True)
+    ref_alphas = [np.where(l["active"], l["alpha_idx"], -9) for l in ref["logs"]]
+    iters = e.iters.cpu().numpy()
+    agree_iters = (iters == ref["iters"]).mean()
+    n_dec = sum(int((a != -9).sum()) for a in ref_alphas)
+    n_same = sum(int(((a == b) & (b != -9)).sum()) for a, b in zip(alphas, ref_alphas))
+    print(f"{system}: iteration counts equal {agree_iters:.4f}, decisions equal {n_same}/{n_dec}")
+    assert len(alphas) == len(ref_alphas)
+    assert agree_iters == 1.0 and n_same == n_dec
+    assert relmax(e.cost.cpu().numpy(), ref["cost"]) < 1e-5
+    # per trajectory max-norm relative error
+    u, x = e.u_batch().cpu().numpy(), e.x_batch().cpu().numpy()
+    eu = np.abs(u - ref["u"]).reshape(B, -1).max(1) / np.abs(ref["u"]).reshape(B, -1).max(1)
+    ex = np.abs(x - ref["x"]).reshape(B, -1).max(1) / np.abs(ref["x"]).reshape(B, -1).max(1)
+    print(f"{system}: u relerr median {np.median(eu):.2e} max {eu.max():.2e}; x median {np.median(ex):.2e} max {ex.max():.2e}")
+    assert np.median(eu) < 1e-5 and eu.max() < 1e-4 and ex.max() < 1e-4
+
+
+@pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
+@pytest.mark.parametrize("method", ["euler", "rk4"])
+def test_reference_api_matches_golden_runs(system, method):
+    """iLQR_TF used exactly like the reference's MPC classes use it (B = 1, lists of arrays),
+    against logs of the unmodified reference: alphas, iteration count, costs, gains, final u/x."""
+    runs = golden_runs(f"ilqr_{system}_classic" + ("_rk4" if method == "rk4" else ""))
+    for r in runs[:4]:
+        mpc = _mpc(system, method=method)
+        il = mpc.ilqr
+        il.x0 = r["x0"]
+        u, x = il.optimize(mpc.x_ref)
+        assert isinstance(u, list) and u[0].shape == (mpc.u_init[0].shape) and x.shape == r["x_final"].shape
+        assert il.total_iter == int(r["total_iter"])
+        L = il.logs
+        got_alpha = [(-1 if l["alpha"] is None else ob.ALPHAS.tolist().index(l["alpha"])) for l in L]
+        assert got_alpha == list(r["alpha_idx"])
+        costs = np.array([l["current_cost"] for l in L])
+        assert abs(costs[0] - r["cost"][0]) <= 1e-12 * abs(r["cost"][0])
+        assert abs(costs[-1] - r["cost"][-1]) <= 1e-5 * abs(r["cost"][-1])
+        assert np.max(np.abs(costs - r["cost"]) / np.abs(r["cost"])) < 2e-3        # reference FD noise, see test_oracle
+        assert relmax(np.array(L[0]["K_seq"]), r["K"][0]) < 5e-4 and relmax(np.array(L[0]["k_seq"]), r["k"][0]) < 5e-4
+        assert relmax(np.array(u), r["u_final"]) < 1e-4 and relmax(x, r["x_final"]) < 1e-4
+        assert len(il.get_time()) == 3 and len(il.total_time) == 1 and len(il.backward_pass_time) == len(L)
+
+
+def test_known_answer_quadrotor():
+    """x0 z=0.5 roll=0.1 -> 11 iterations, alphas [1,1,1,1,.5,1,...], u*[0]."""
+    mpc = _mpc("quadrotor")
+    x0 = np.zeros(12); x0[2] = 0.5; x0[6] = 0.1
+    mpc.ilqr.x0 = x0
+    u, x = mpc.ilqr.optimize(mpc.x_ref)
+    assert mpc.ilqr.total_iter == 10
+    assert [l["alpha"] for l in mpc.ilqr.logs] == [1.0, 1.0, 1.0, 1.0, 0.5] + [1.0] * 6
+    assert np.allclose([l["current_cost"] for l in mpc.ilqr.logs][:6],
+                       [2997.738432876904, 2113.314492958847, 1779.5520273040233, 1413.2685744742648,
+                        128.84477638503364, 57.292297508613494], rtol=1e-5)
+    assert np.allclose(u[0], [4.064699, 0.711285, 0.711285, 4.064699], atol=2e-5)
+
+
+def test_mpc_control_step_warm_start():
+    """control_step: x0 update + u <- u[1:] + [u[-1]] shift, closed loop for a few steps."""
+    mpc = _mpc("cartpole")
+    x = np.array([0.0, 0.0, 0.1, 0.0])
+    first = None
+    for step in range(3):
+        x_seq, u0 = mpc.control_step(x)
+        if first is None:
+            first = float(u0[0])
+        assert len(mpc.ilqr.u) == 30 and np.array_equal(mpc.ilqr.u[-1], mpc.ilqr.u[-2])
+        x = mpc.discrete_dynamics(x, u0)
+    assert first == pytest.approx(-6.755067, abs=2e-5)
+    assert abs(x[2]) < 0.1
+
+
+def test_batched_mpc_equals_single():
+    from quattro_transformer_ilqr_b200.mpc import QuadrotorMPC
+    B = 5
+    x0 = sample_x0("quadrotor", B, seed=3)
+    mb = QuadrotorMPC(horizon=50, integration_method="euler", batch=B)
+    mb.ilqr.enable_log = False
+    xs, us = mb.control_step(x0)
+    assert us.shape == (B, 50, 4) and xs.shape == (B, 51, 12)
+    ms = QuadrotorMPC(horizon=50, integration_method="euler")
+    ms.ilqr.x0 = x0[2]
+    u, x = ms.ilqr.optimize(ms.x_ref)
+    assert np.array_equal(np.array(u), us[2]) and mb.ilqr.total_iter[2] == ms.ilqr.total_iter
+
+
+def test_full_size_properties():
+    """BASELINE config 3 size (quadrotor, B = 16 384): properties that need no oracle run."""
+    from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel
+    B, N = 16384, 50
+    x0 = sample_x0("quadrotor", B, seed=0)
+    e = BatchedILQR(DeviceModel("quadrotor"), B, N)
+    e.set_problem(x0, np.zeros((B, N, 4)))
+    costs = [e.cost.clone()]
+    for _ in range(4):
+        e.iterate(tol=1e-3, force=True)
+        costs.append(e.cost.clone())
+        # accepted candidates never increase the cost; rejected ones keep it
+        assert bool((costs[-1] <= costs[-2]).all())
+    # the stored trajectory is the rollout of the stored controls, and cost is its cost
+    u_now = e.u_batch().cpu().numpy()
+    chk = BatchedILQR(DeviceModel("quadrotor"), B, N)
+    chk.set_problem(x0, u_now)
+    assert torch.equal(chk.x[chk.cur], e.x[e.cur]) and torch.equal(chk.cost, e.cost)
+    # sharding invariance: any slice solved alone gives bit-identical results (section 8e)
+    sl = slice(5000, 5000 + 1031)
+    part = BatchedILQR(DeviceModel("quadrotor"), 1031, N)
+    part.set_problem(x0[sl], np.zeros((1031, N, 4)))
+    part.solve(fixed_iters=4)
+    assert torch.equal(part.u_batch(), e.u_batch()[sl]) and torch.equal(part.cost, e.cost[sl])
+    # spot-check 32 trajectories of the big batch against the oracle
+    idx = np.arange(0, B, B // 32)
+    ref = ob.optimize(make_model("quadrotor"), x0[idx], np.zeros((len(idx), N, 4)), fixed_iters=4)
+    assert np.array_equal(e.alpha.cpu().numpy()[idx], ref["alpha_idx"])
+    assert relmax(e.cost.cpu().numpy()[idx], ref["cost"]) < 1e-5
+    assert relmax(u_now[idx], ref["u"]) < 1e-4
+
+
+# ---------------------------------------------------------------------------- transformer mode
+def _wrapper(system, mode):
+    from quattro_transformer_ilqr_b200 import TransformerILQR, TransformerPredictor
+    w = TransformerILQR(1, 1).load(checkpoint_dir(system))
+    if mode == "rand":
+        torch.manual_seed(0)
+        w.model = TransformerPredictor(w.state_dim, w.control_dim, w.d_model, w.nhead, w.num_decoder_layers,
+                                       w.dim_feedforward, w.dropout, w.max_seq_len, w.target_len, w.prompt_len).eval()
+        w.invalidate()
+    return w
+
+
+@pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
+@pytest.mark.parametrize("mode", ["fp32", "rand"])
+def test_transformer_predict_matches_reference(system, mode, golden_dir):
+    """TransformerILQR.predict (CUDA) vs the reference's predict on the same inputs / weights."""
+    g = np.load(f"{golden_dir}/tf_forward_{system}.npz")
+    w = _wrapper(system, mode)
+    pred = np.array([w.predict(x, kK) for x, kK in zip(g["x_err"][:4], g["kK"][:4])])
+    assert pred.dtype == np.float32 and pred.shape == g[f"pred_{mode}"][:4].shape
+    assert relmax(pred, g[f"pred_{mode}"][:4]) < 1e-5
+    batch = w.predict(g["x_err"], g["kK"])
+    assert relmax(batch, g[f"pred_{mode}"]) < 1e-5
+    if mode == "fp32":      # shipped fp16 checkpoint run by the reference in fp16: its own quantisation gap
+        assert relmax(batch, g["pred_fp16"]) < 5e-2
+
+
+@pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
+@pytest.mark.parametrize("mode", ["fp32", "rand"])
+def test_transformer_mode_matches_golden_runs(system, mode):
+    """optimize() with the transformer in the loop vs the reference (same weights, fp32)."""
+    runs = golden_runs(f"ilqr_{system}_tf_{mode}")
+    w = _wrapper(system, mode)
+    n_ok = 0
+    for r in runs[:4]:
+        mpc = _mpc(system, transformer_model=w)
+        il = mpc.ilqr
+        il.x0 = r["x0"]
+        u, x = il.optimize(mpc.x_ref)
+        L = il.logs
+        got_alpha = [(-1 if l["alpha"] is None else ob.ALPHAS.tolist().index(l["alpha"])) for l in L]
+        same = got_alpha == list(r["alpha_idx"])
+        n_ok += same
+        costs = np.array([l["current_cost"] for l in L])
+        assert abs(costs[0] - r["cost"][0]) <= 1e-12 * abs(r["cost"][0])
+        if same:
+            assert il.total_iter == int(r["total_iter"])
+            assert np.max(np.abs(costs - r["cost"]) / np.abs(r["cost"])) < 2e-3
+            assert relmax(np.array(u), r["u_final"]) < 2e-3
+        assert len(il.get_time()) == 4 and len(il.inference_time) == len(L)
+    assert n_ok >= 3, f"line-search decisions differ from the reference in {4 - n_ok}/4 runs"
