@@ -25,7 +25,8 @@
  *   alpha  int32  [B]              index into {1,.5,.25,.1,.05,.01} accepted last, -1 = none
  *   expansion / terminal / gains: float, layout depends on the model's "record" kind:
  *     QX_LAYOUT_REC (quadrotor; warp-per-trajectory Riccati, one contiguous record per (t,b))
- *        expansion float [N][B][REC]   REC = [A n*n | B n*m | lx n | lu m | lxx n*n | luu m*m | lux m*n]
+ *        expansion float [N][B][REC]   REC = [F n*(n+m) | lx n | lu m | lxx n*n | luu m*m | lux m*n],
+ *                                      F = [A | B] interleaved: row i = A[i][0..n) then B[i][0..m)
  *        terminal  float [B][n + n*n]  [Vx | Vxx]
  *        gains     float [N][B][m + m*n]  [k | K row-major]
  *     QX_LAYOUT_SOA (cart-pole; thread-per-trajectory Riccati, b fastest)

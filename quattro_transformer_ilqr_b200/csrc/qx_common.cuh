@@ -30,9 +30,12 @@ int cuda_fail(cudaError_t e, const char* what);
 // ---- record layout (see include/quattro_b200.h) ----------------------------------------------
 template <int n, int m>
 struct Rec {
-  static constexpr int A = 0;
-  static constexpr int Bm = A + n * n;
-  static constexpr int lx = Bm + n * m;
+  // F = [A | B] interleaved row by row: row i holds A[i][0..n) then B[i][0..m)  (pitch n + m)
+  static constexpr int F = 0;
+  static constexpr int pitch = n + m;
+  __host__ __device__ static constexpr int a(int i, int j) { return i * pitch + j; }
+  __host__ __device__ static constexpr int b(int i, int j) { return i * pitch + n + j; }
+  static constexpr int lx = n * pitch;          // [lx | lu] contiguous
   static constexpr int lu = lx + n;
   static constexpr int lxx = lu + m;
   static constexpr int luu = lxx + n * n;

@@ -86,9 +86,12 @@ __device__ __forceinline__ void emit_dynamics(const float* x, const float* u, co
   float A[n * n], Bm[n * m];
   discrete_jacobians<Mdl, INTEG>(x, u, p, A, Bm);
 #pragma unroll
-  for (int i = 0; i < n * n; ++i) out(R::A + i, A[i]);
+  for (int i = 0; i < n; ++i) {
 #pragma unroll
-  for (int i = 0; i < n * m; ++i) out(R::Bm + i, Bm[i]);
+    for (int j = 0; j < n; ++j) out(R::a(i, j), A[i * n + j]);
+#pragma unroll
+    for (int j = 0; j < m; ++j) out(R::b(i, j), Bm[i * m + j]);
+  }
   float dx[n], g[n];
 #pragma unroll
   for (int i = 0; i < n; ++i) dx[i] = x[i] - float(p.x_ref[i]);

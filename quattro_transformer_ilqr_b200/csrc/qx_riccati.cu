@@ -10,13 +10,12 @@
 //   V_xx = Q_xx + K^T Q_uu K + K^T Q_ux + Q_ux^T K ; V_xx = (V_xx + V_xx^T)/2   (:316-317)
 //
 // Two kernels:
-//  * riccati_warp_kernel<12,4> (quadrotor): one warp per trajectory.  The step's 1 664-B
-//    expansion record streams HBM -> shared memory through a 3-stage ring of 1-D bulk async
-//    copies (TMA; SASS UBLKCP) completed on mbarriers, so the copy of steps t-1..t-3 overlaps the
-//    arithmetic of step t.  With F = [A | B] (12x16) the step is W = V F, Q = L + F^T W; each
-//    lane owns a 2x4 register tile of W and of Q (one 8-B and one 16-B shared load per 8 FMAs,
-//    both warp-broadcast -> one wavefront each), the 4x4 solve is done redundantly per lane with
-//    partial pivoting, V_xx / V_x stay in shared memory between steps.
+//  * riccati_warp_kernel (quadrotor, n = 12, m = 4): two trajectories per warp, 16 lanes each.
+//    The step's 1 664-B expansion record streams HBM -> shared memory through a 2-stage ring of
+//    1-D bulk async copies (TMA; SASS UBLKCP) completed on mbarriers, so the copies of steps
+//    t-1, t-2 overlap the arithmetic of step t.  With F = [A | B] (12x16, stored interleaved) the
+//    step is W = V F, Q = L + F^T W on register tiles (two 16-B shared loads, both broadcast
+//    inside the half-warp, per 12-16 FMAs); V_xx / V_x stay in shared memory between steps.
 //  * riccati_soa_kernel<4,1> (cart-pole): 16+4+... values fit one thread's registers, so one
 //    thread per trajectory over the b-fastest SOA layout (every load coalesced).
 #include "qx_async.cuh"
@@ -86,11 +85,11 @@ riccati_soa_kernel(const float* __restrict__ expansion, const float* __restrict_
 #pragma unroll
     for (int i = 0; i < n; ++i)
 #pragma unroll
-      for (int j = 0; j < n; ++j) A[i][j] = ld(R::A + i * n + j);
+      for (int j = 0; j < n; ++j) A[i][j] = ld(R::a(i, j));
 #pragma unroll
     for (int i = 0; i < n; ++i)
 #pragma unroll
-      for (int j = 0; j < m; ++j) Bm[i][j] = ld(R::Bm + i * m + j);
+      for (int j = 0; j < m; ++j) Bm[i][j] = ld(R::b(i, j));
     // W = V [A | B]
     float WA[n][n], WB[n][m];
 #pragma unroll
@@ -218,22 +217,76 @@ riccati_soa_kernel(const float* __restrict__ expansion, const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
-// Warp-per-trajectory, REC layout, n = 12, m = 4.
-constexpr int kRicStages = 3;
+// Half-warp-per-trajectory (two trajectories per warp), REC layout, n = 12, m = 4.
+//
+// Lane roles inside a half-warp (hl = lane & 15, ri = hl >> 2, cj = hl & 3):
+//   phase 1  W = V F (12x16): 3x4 tile (rows 3ri.., cols 4cj..); V is kept in a padded
+//            "p4" layout  Vp[l][4*(i/3) + i%3]  so the three V values are one 16-B load;
+//            every lane also accumulates q[hl] = [l_x|l_u][hl] + sum_l F[l][hl] V_x[l]
+//   phase 2  Q = L + F^T W (16x16): 4x4 tile (rows 4ri.., cols 4cj..), two 16-B loads per 16 FMAs
+//   phase 3  lane hl < 12 solves column hl of K, lane 12 solves k (no-pivot elimination of the
+//            SPD matrix, pivoted fallback if a pivot is not positive)
+//   phase 4  V' = Q_xx + K^T (Q_uu K + Q_ux) + Q_ux^T K on the nine Q_xx tile lanes
+//   phase 5  symmetrise V' and rewrite it in the p4 layout (all 16 lanes, 3 rows of 4 each)
+constexpr int kRicStages = 2;
 constexpr int kRicWarps = 4;
 
-struct RicWarpSmem {
+struct RicSmem {                               // per trajectory
   alignas(128) float rec[kRicStages][416];   // expansion records (bulk-copy destinations)
-  alignas(16) float V[12 * 12];              // V_xx (symmetric)
-  alignas(16) float W[12 * 16];              // V [A|B]; reused as the un-symmetrised V_xx
+  alignas(16) float Vp[12 * 16];             // V_xx, p4 layout
+  alignas(16) float W[12 * 16];              // V F; reused for the un-symmetrised V_xx' (pitch 12)
   alignas(16) float Qb[4 * 16];              // rows 12..15 of Q: [Q_ux | Q_uu]
   alignas(16) float Ks[4 * 12];              // K
   alignas(16) float Ms[4 * 12];              // Q_uu K + Q_ux
-  alignas(16) float Vx[12];
+  alignas(16) float Vx[16];
   alignas(16) float q[16];                   // [Q_x | Q_u]
   alignas(16) float kh[8];                   // [k | Q_uu k + Q_u]
   alignas(8) uint64_t bar[kRicStages];
 };
+
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(r, fmaf(-x, r, 1.f), r);       // one Newton step: <= 1 ulp
+}
+
+// SPD fast path: elimination without pivoting.  Returns false if a pivot is not positive.
+__device__ __forceinline__ bool solve_spd4(const float (&Min)[4][4], float (&r)[4]) {
+  float M[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) M[a][c] = Min[a][c];
+  float inv[4];
+  bool ok = true;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    ok = ok && (M[c][c] > 0.f);
+    inv[c] = fast_rcp(M[c][c]);
+#pragma unroll
+    for (int rr = c + 1; rr < 4; ++rr) {
+      const float f = M[rr][c] * inv[c];
+#pragma unroll
+      for (int j = c + 1; j < 4; ++j) M[rr][j] = fmaf(-f, M[c][j], M[rr][j]);
+      r[rr] = fmaf(-f, r[c], r[rr]);
+    }
+  }
+#pragma unroll
+  for (int c = 3; c >= 0; --c) {
+    float acc = r[c];
+#pragma unroll
+    for (int j = c + 1; j < 4; ++j) acc = fmaf(-M[c][j], r[j], acc);
+    r[c] = acc * inv[c];
+  }
+  return ok;
+}
+
+__device__ __noinline__ void solve_pp4_slow(const float (&Min)[4][4], float (&r)[4]) {
+  float M[4][4];
+  for (int a = 0; a < 4; ++a)
+    for (int c = 0; c < 4; ++c) M[a][c] = Min[a][c];
+  solve_pp<4>(M, r);
+}
 
 __global__ void __launch_bounds__(32 * kRicWarps)
 riccati_warp_kernel(const float* __restrict__ expansion, const float* __restrict__ terminal,
@@ -241,135 +294,134 @@ riccati_warp_kernel(const float* __restrict__ expansion, const float* __restrict
                     float reg) {
   constexpr int n = 12, m = 4;
   using R = Rec<n, m>;
-  static_assert(R::size == 416 && R::gain == 52, "layout");
-  __shared__ RicWarpSmem smem[kRicWarps];
+  static_assert(R::size == 416 && R::gain == 52 && R::pitch == 16, "layout");
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ RicSmem smem[kRicWarps][2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * kRicWarps + warp;
-  if (b >= B) return;
-  if (status != nullptr && status[b] != 0) return;
-  RicWarpSmem& s = smem[warp];
+  const int half = lane >> 4, hl = lane & 15;
+  const int b_mine = (blockIdx.x * kRicWarps + warp) * 2 + half;
+  const bool valid = (b_mine < B) && (status == nullptr || status[b_mine] == 0);
+  const unsigned vmask = __ballot_sync(FULL, valid);
+  if (vmask == 0u) return;
+  // an idle half shadows the other half's trajectory (same loads, no stores) so the warp stays convergent
+  const int b = valid ? b_mine : (blockIdx.x * kRicWarps + warp) * 2 + (1 - half);
+  RicSmem& s = smem[warp][half];
   const int steps = N - t_start;
 
-  if (lane == 0) {
+  if (hl == 0) {
     for (int i = 0; i < kRicStages; ++i) mbar_init(&s.bar[i], 1);
     mbar_fence_init();
   }
   __syncwarp();
-  auto issue = [&](int k) {   // lane 0: sequence k <-> t = N-1-k
+  auto issue = [&](int k) {   // lane hl == 0: sequence k <-> t = N-1-k
     const int t = N - 1 - k;
     mbar_arrive_expect_tx(&s.bar[k % kRicStages], R::size * sizeof(float));
     bulk_g2s(s.rec[k % kRicStages], expansion + ((size_t)t * B + b) * R::size, R::size * sizeof(float),
              &s.bar[k % kRicStages]);
   };
-  if (lane == 0)
+  if (hl == 0)
     for (int k = 0; k < kRicStages && k < steps; ++k) issue(k);
 
-  // terminal condition
+  // terminal condition -> V_x, V_xx (p4 layout)
   {
     const float* tm = terminal + (size_t)b * R::term;
-    for (int e = lane; e < R::term; e += 32) {
+    for (int e = hl; e < R::term; e += 16) {
       const float v = tm[e];
-      if (e < n) s.Vx[e] = v; else s.V[e - n] = v;
+      if (e < n) {
+        s.Vx[e] = v;
+      } else {
+        const int i = (e - n) / n, j = (e - n) % n;
+        s.Vp[i * 16 + 4 * (j / 3) + (j % 3)] = v;
+      }
     }
   }
   __syncwarp();
 
-  const int ri = lane >> 2, cj = lane & 3;   // tile coordinates: rows 2ri, 2ri+1; cols 4cj..4cj+3
+  const int ri = hl >> 2, cj = hl & 3;
 
   for (int k = 0; k < steps; ++k) {
     const int t = N - 1 - k;
     mbar_wait(&s.bar[k % kRicStages], (k / kRicStages) & 1u);
     const float* rec = s.rec[k % kRicStages];
-    const float* A = rec + R::A;
-    const float* Bm = rec + R::Bm;
+    const float* F = rec + R::F;
 
-    // ---- phase 1: W = V F (lanes 0..23), q = l + F^T V_x (lanes 24..31) -------------------
-    if (lane < 24) {
-      float acc[2][4] = {};
-      const float* bsrc = (cj < 3) ? (A + 4 * cj) : Bm;
-      const int bstride = (cj < 3) ? n : m;
+    // ---- phase 1: W = V F on 3x4 tiles; q = l + F^T V_x ------------------------------------------
+    {
+      float acc[3][4] = {};
+      float qv = rec[R::lx + hl];
 #pragma unroll
       for (int l = 0; l < n; ++l) {
-        const float2 a = *reinterpret_cast<const float2*>(&s.V[l * n + 2 * ri]);
-        const float4 bv = *reinterpret_cast<const float4*>(bsrc + l * bstride);
-        acc[0][0] += a.x * bv.x; acc[0][1] += a.x * bv.y; acc[0][2] += a.x * bv.z; acc[0][3] += a.x * bv.w;
-        acc[1][0] += a.y * bv.x; acc[1][1] += a.y * bv.y; acc[1][2] += a.y * bv.z; acc[1][3] += a.y * bv.w;
+        const float4 a = *reinterpret_cast<const float4*>(&s.Vp[l * 16 + 4 * ri]);     // V[l][3ri..3ri+2]
+        const float4 f = *reinterpret_cast<const float4*>(F + l * 16 + 4 * cj);
+        acc[0][0] = fmaf(a.x, f.x, acc[0][0]); acc[0][1] = fmaf(a.x, f.y, acc[0][1]);
+        acc[0][2] = fmaf(a.x, f.z, acc[0][2]); acc[0][3] = fmaf(a.x, f.w, acc[0][3]);
+        acc[1][0] = fmaf(a.y, f.x, acc[1][0]); acc[1][1] = fmaf(a.y, f.y, acc[1][1]);
+        acc[1][2] = fmaf(a.y, f.z, acc[1][2]); acc[1][3] = fmaf(a.y, f.w, acc[1][3]);
+        acc[2][0] = fmaf(a.z, f.x, acc[2][0]); acc[2][1] = fmaf(a.z, f.y, acc[2][1]);
+        acc[2][2] = fmaf(a.z, f.z, acc[2][2]); acc[2][3] = fmaf(a.z, f.w, acc[2][3]);
+        qv = fmaf(F[l * 16 + hl], s.Vx[l], qv);
       }
-      *reinterpret_cast<float4*>(&s.W[(2 * ri) * 16 + 4 * cj]) = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
-      *reinterpret_cast<float4*>(&s.W[(2 * ri + 1) * 16 + 4 * cj]) = make_float4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]);
-    } else {
-      const int j0 = 2 * (lane - 24);        // columns j0, j0+1 of F
-      const float* fsrc = (j0 < n) ? (A + j0) : (Bm + (j0 - n));
-      const int fstride = (j0 < n) ? n : m;
-      float q0 = (j0 < n) ? rec[R::lx + j0] : rec[R::lu + j0 - n];
-      float q1 = (j0 < n) ? rec[R::lx + j0 + 1] : rec[R::lu + j0 + 1 - n];
 #pragma unroll
-      for (int l = 0; l < n; ++l) {
-        const float2 f = *reinterpret_cast<const float2*>(fsrc + l * fstride);
-        const float vx = s.Vx[l];
-        q0 += f.x * vx;
-        q1 += f.y * vx;
-      }
-      *reinterpret_cast<float2*>(&s.q[j0]) = make_float2(q0, q1);
+      for (int r = 0; r < 3; ++r)
+        *reinterpret_cast<float4*>(&s.W[(3 * ri + r) * 16 + 4 * cj]) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      s.q[hl] = qv;
     }
     __syncwarp();
 
-    // ---- phase 2: Q = L + F^T W, 2x4 tile per lane over the 16x16 matrix -------------------
-    float Q[2][4];
+    // ---- phase 2: Q = L + F^T W on 4x4 tiles -------------------------------------------------------
+    float Q[4][4];
     {
-      const int i0 = 2 * ri, j0 = 4 * cj;
-      // initialise with the cost Hessian block
+      // cost Hessian block of this tile (the Q_xu tile, ri < 3 && cj == 3, is never used)
+      const float* lsrc = (ri < 3) ? (rec + R::lxx + (4 * ri) * n + 4 * cj)
+                                   : ((cj < 3) ? (rec + R::lux + 4 * cj) : (rec + R::luu));
+      const int lstride = (ri < 3 || cj < 3) ? n : m;
+      const bool have_l = !(ri < 3 && cj == 3);
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int i = i0 + r;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int j = j0 + c;
-          float v;
-          if (i < n && j < n) v = rec[R::lxx + i * n + j];
-          else if (i < n) v = rec[R::lux + (j - n) * n + i];        // Q_xu = Q_ux^T
-          else if (j < n) v = rec[R::lux + (i - n) * n + j];
-          else v = rec[R::luu + (i - n) * m + (j - n)];
-          Q[r][c] = v;
-        }
+      for (int r = 0; r < 4; ++r) {
+        const float4 v = have_l ? *reinterpret_cast<const float4*>(lsrc + r * lstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+        Q[r][0] = v.x; Q[r][1] = v.y; Q[r][2] = v.z; Q[r][3] = v.w;
       }
-      const float* asrc = (ri < 6) ? (A + i0) : (Bm + (i0 - n));
-      const int astride = (ri < 6) ? n : m;
 #pragma unroll
       for (int l = 0; l < n; ++l) {
-        const float2 a = *reinterpret_cast<const float2*>(asrc + l * astride);
-        const float4 w = *reinterpret_cast<const float4*>(&s.W[l * 16 + j0]);
-        Q[0][0] += a.x * w.x; Q[0][1] += a.x * w.y; Q[0][2] += a.x * w.z; Q[0][3] += a.x * w.w;
-        Q[1][0] += a.y * w.x; Q[1][1] += a.y * w.y; Q[1][2] += a.y * w.z; Q[1][3] += a.y * w.w;
+        const float4 a = *reinterpret_cast<const float4*>(F + l * 16 + 4 * ri);
+        const float4 w = *reinterpret_cast<const float4*>(&s.W[l * 16 + 4 * cj]);
+        Q[0][0] = fmaf(a.x, w.x, Q[0][0]); Q[0][1] = fmaf(a.x, w.y, Q[0][1]); Q[0][2] = fmaf(a.x, w.z, Q[0][2]); Q[0][3] = fmaf(a.x, w.w, Q[0][3]);
+        Q[1][0] = fmaf(a.y, w.x, Q[1][0]); Q[1][1] = fmaf(a.y, w.y, Q[1][1]); Q[1][2] = fmaf(a.y, w.z, Q[1][2]); Q[1][3] = fmaf(a.y, w.w, Q[1][3]);
+        Q[2][0] = fmaf(a.z, w.x, Q[2][0]); Q[2][1] = fmaf(a.z, w.y, Q[2][1]); Q[2][2] = fmaf(a.z, w.z, Q[2][2]); Q[2][3] = fmaf(a.z, w.w, Q[2][3]);
+        Q[3][0] = fmaf(a.w, w.x, Q[3][0]); Q[3][1] = fmaf(a.w, w.y, Q[3][1]); Q[3][2] = fmaf(a.w, w.z, Q[3][2]); Q[3][3] = fmaf(a.w, w.w, Q[3][3]);
       }
-      if (ri >= 6) {
-        *reinterpret_cast<float4*>(&s.Qb[(i0 - n) * 16 + j0]) = make_float4(Q[0][0], Q[0][1], Q[0][2], Q[0][3]);
-        *reinterpret_cast<float4*>(&s.Qb[(i0 + 1 - n) * 16 + j0]) = make_float4(Q[1][0], Q[1][1], Q[1][2], Q[1][3]);
+      if (ri == 3) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          *reinterpret_cast<float4*>(&s.Qb[r * 16 + 4 * cj]) = make_float4(Q[r][0], Q[r][1], Q[r][2], Q[r][3]);
       }
     }
     __syncwarp();
     // the record is consumed: refill its stage with the record of step k + stages
-    if (lane == 0 && k + kRicStages < steps) issue(k + kRicStages);
+    if (hl == 0 && k + kRicStages < steps) issue(k + kRicStages);
 
-    // ---- phase 3: gains.  lane j < 12 solves column j of K, lane 12 solves k -----------------
+    // ---- phase 3: gains.  lane hl < 12 solves column hl of K, lane 12 solves k -------------------
     {
-      float Quu[m][m], Mr[m][m], rhs[m];
+      float Quu[m][m], Mr[m][m], rhs[m], src[m];
 #pragma unroll
       for (int a = 0; a < m; ++a) {
         const float4 v = *reinterpret_cast<const float4*>(&s.Qb[a * 16 + n]);
         Quu[a][0] = v.x; Quu[a][1] = v.y; Quu[a][2] = v.z; Quu[a][3] = v.w;
       }
-      const int col = (lane < n) ? lane : 0;
+      const int col = (hl < n) ? hl : 0;
 #pragma unroll
       for (int a = 0; a < m; ++a) {
 #pragma unroll
         for (int c = 0; c < m; ++c) Mr[a][c] = Quu[a][c] + (a == c ? reg : 0.f);
-        rhs[a] = (lane == n) ? s.q[n + a] : s.Qb[a * 16 + col];
+        src[a] = (hl == n) ? s.q[n + a] : s.Qb[a * 16 + col];
+        rhs[a] = src[a];
       }
-      float src[m];
+      const bool ok = solve_spd4(Mr, rhs);
+      if (__any_sync(FULL, !ok)) {           // indefinite Q_uu: the reference's LU still "works" (a-Q(4))
 #pragma unroll
-      for (int a = 0; a < m; ++a) src[a] = rhs[a];
-      solve_pp<m>(Mr, rhs);
+        for (int a = 0; a < m; ++a) rhs[a] = src[a];
+        solve_pp4_slow(Mr, rhs);
+      }
       float z[m], hm[m];
 #pragma unroll
       for (int a = 0; a < m; ++a) z[a] = -rhs[a];
@@ -377,67 +429,65 @@ riccati_warp_kernel(const float* __restrict__ expansion, const float* __restrict
       for (int a = 0; a < m; ++a) {
         float acc = src[a];
 #pragma unroll
-        for (int c = 0; c < m; ++c) acc += Quu[a][c] * z[c];
+        for (int c = 0; c < m; ++c) acc = fmaf(Quu[a][c], z[c], acc);
         hm[a] = acc;                         // Q_uu K + Q_ux (column), or Q_uu k + Q_u
       }
       float* g = gains + ((size_t)t * B + b) * R::gain;
-      if (lane < n) {
+      if (hl < n) {
 #pragma unroll
         for (int a = 0; a < m; ++a) {
-          s.Ks[a * n + lane] = z[a];
-          s.Ms[a * n + lane] = hm[a];
-          g[m + a * n + lane] = z[a];
+          s.Ks[a * n + hl] = z[a];
+          s.Ms[a * n + hl] = hm[a];
+          if (valid) g[m + a * n + hl] = z[a];
         }
-      } else if (lane == n) {
+      } else if (hl == n) {
 #pragma unroll
         for (int a = 0; a < m; ++a) {
           s.kh[a] = z[a];
           s.kh[m + a] = hm[a];
-          g[a] = z[a];
+          if (valid) g[a] = z[a];
         }
       }
     }
     __syncwarp();
 
-    // ---- phase 4: V_xx' = Q_xx + K^T (Q_uu K + Q_ux) + Q_ux^T K ;  V_x' ------------------------
-    if (ri < 6 && cj < 3) {
-      const int i0 = 2 * ri, j0 = 4 * cj;
+    // ---- phase 4: V_xx' = Q_xx + K^T (Q_uu K + Q_ux) + Q_ux^T K ;  V_x' ----------------------------
+    if (ri < 3 && cj < 3) {
 #pragma unroll
       for (int a = 0; a < m; ++a) {
-        const float2 ka = *reinterpret_cast<const float2*>(&s.Ks[a * n + i0]);
-        const float4 mb = *reinterpret_cast<const float4*>(&s.Ms[a * n + j0]);
-        const float2 qa = *reinterpret_cast<const float2*>(&s.Qb[a * 16 + i0]);
-        const float4 kb = *reinterpret_cast<const float4*>(&s.Ks[a * n + j0]);
-        Q[0][0] += ka.x * mb.x + qa.x * kb.x; Q[0][1] += ka.x * mb.y + qa.x * kb.y;
-        Q[0][2] += ka.x * mb.z + qa.x * kb.z; Q[0][3] += ka.x * mb.w + qa.x * kb.w;
-        Q[1][0] += ka.y * mb.x + qa.y * kb.x; Q[1][1] += ka.y * mb.y + qa.y * kb.y;
-        Q[1][2] += ka.y * mb.z + qa.y * kb.z; Q[1][3] += ka.y * mb.w + qa.y * kb.w;
+        const float4 ka = *reinterpret_cast<const float4*>(&s.Ks[a * n + 4 * ri]);
+        const float4 mb = *reinterpret_cast<const float4*>(&s.Ms[a * n + 4 * cj]);
+        const float4 qa = *reinterpret_cast<const float4*>(&s.Qb[a * 16 + 4 * ri]);
+        const float4 kb = *reinterpret_cast<const float4*>(&s.Ks[a * n + 4 * cj]);
+        const float kar[4] = {ka.x, ka.y, ka.z, ka.w}, qar[4] = {qa.x, qa.y, qa.z, qa.w};
+        const float mbc[4] = {mb.x, mb.y, mb.z, mb.w}, kbc[4] = {kb.x, kb.y, kb.z, kb.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) Q[r][c] = fmaf(kar[r], mbc[c], fmaf(qar[r], kbc[c], Q[r][c]));
       }
-      // un-symmetrised V_xx' goes to the W buffer (pitch 12)
-      *reinterpret_cast<float4*>(&s.W[i0 * n + j0]) = make_float4(Q[0][0], Q[0][1], Q[0][2], Q[0][3]);
-      *reinterpret_cast<float4*>(&s.W[(i0 + 1) * n + j0]) = make_float4(Q[1][0], Q[1][1], Q[1][2], Q[1][3]);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)    // un-symmetrised V_xx' -> W buffer, pitch 12
+        *reinterpret_cast<float4*>(&s.W[(4 * ri + r) * n + 4 * cj]) = make_float4(Q[r][0], Q[r][1], Q[r][2], Q[r][3]);
     }
     float vx_new = 0.f;
-    if (lane < n) {
-      vx_new = s.q[lane];
+    if (hl < n) {
+      vx_new = s.q[hl];
 #pragma unroll
-      for (int a = 0; a < m; ++a) vx_new += s.Ks[a * n + lane] * s.kh[m + a] + s.Qb[a * 16 + lane] * s.kh[a];
+      for (int a = 0; a < m; ++a) vx_new += s.Ks[a * n + hl] * s.kh[m + a] + s.Qb[a * 16 + hl] * s.kh[a];
     }
     __syncwarp();
-    if (lane < n) s.Vx[lane] = vx_new;
+    if (hl < n) s.Vx[hl] = vx_new;
 
-    // ---- phase 5: symmetrise ---------------------------------------------------------------------
-    if (ri < 6 && cj < 3) {
-      const int i0 = 2 * ri, j0 = 4 * cj;
-      float o[2][4];
+    // ---- phase 5: V = (V' + V'^T) / 2 into the p4 layout: item (i, g) = V[i][3g..3g+2] -----------------
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float2 tr = *reinterpret_cast<const float2*>(&s.W[(j0 + c) * n + i0]);   // V'[j][i0..i0+1]
-        o[0][c] = 0.5f * (Q[0][c] + tr.x);
-        o[1][c] = 0.5f * (Q[1][c] + tr.y);
-      }
-      *reinterpret_cast<float4*>(&s.V[i0 * n + j0]) = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
-      *reinterpret_cast<float4*>(&s.V[(i0 + 1) * n + j0]) = make_float4(o[1][0], o[1][1], o[1][2], o[1][3]);
+    for (int it = 0; it < 3; ++it) {
+      const int item = hl + 16 * it;           // 48 items
+      const int i = item >> 2, g = item & 3;
+      const float* vr = &s.W[i * n + 3 * g];
+      const float* vc = &s.W[(3 * g) * n + i];
+      const float4 o = make_float4(0.5f * (vr[0] + vc[0]), 0.5f * (vr[1] + vc[n]), 0.5f * (vr[2] + vc[2 * n]), 0.f);
+      *reinterpret_cast<float4*>(&s.Vp[i * 16 + 4 * g]) = o;
     }
     __syncwarp();
   }
@@ -458,7 +508,7 @@ extern "C" int qx_riccati(int model_id, const float* expansion, const float* ter
       return QX_OK;
     case QX_MODEL_QUADROTOR:
       QX_CHECK_ARG((reinterpret_cast<uintptr_t>(expansion) & 15u) == 0, "expansion must be 16-byte aligned");
-      qx::riccati_warp_kernel<<<qx::ceil_div(B, qx::kRicWarps), 32 * qx::kRicWarps, 0, st>>>(
+      qx::riccati_warp_kernel<<<qx::ceil_div(B, 2 * qx::kRicWarps), 32 * qx::kRicWarps, 0, st>>>(
           expansion, terminal, gains, status, B, N, t_start, reg);
       QX_CHECK_LAUNCH("riccati_warp_kernel");
       return QX_OK;

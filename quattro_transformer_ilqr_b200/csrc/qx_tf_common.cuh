@@ -9,6 +9,7 @@
 //              linear1.weight[ff][d] linear1.bias[ff] linear2.weight[d][ff] linear2.bias[d]
 //              norm1.weight[d] norm1.bias[d] norm2.weight[d] norm2.bias[d]
 //   output_linear.{weight[c][d], bias[c]}
+// Every tensor starts on a 32-float (128-B) boundary so kernels may use vector / bulk loads.
 #pragma once
 #include "qx_common.cuh"
 
@@ -24,21 +25,22 @@ struct TfLayout {
     n = g.state_dim; c = g.control_dim; d = g.d_model; ff = g.dim_ff; T = g.target_len; P = g.prompt_len;
     L = g.horizon + 1 + P + T; layers = g.num_layers;
     size_t o = 0;
-    x_mean = o; o += n; x_std = o; o += n; u_mean = o; o += c; u_std = o; o += c;
-    ws = o; o += (size_t)d * n; bs = o; o += d;
-    wc = o; o += (size_t)d * c; bc = o; o += d;
-    tgt = o; o += (size_t)T * d;
-    pe = o; o += (size_t)L * d;
+    auto take = [&o](size_t count) { const size_t at = o; o = (o + count + 31) / 32 * 32; return at; };
+    x_mean = take(n); x_std = take(n); u_mean = take(c); u_std = take(c);
+    ws = take((size_t)d * n); bs = take(d);
+    wc = take((size_t)d * c); bc = take(d);
+    tgt = take((size_t)T * d);
+    pe = take((size_t)L * d);
     layer0 = o;
-    size_t q = 0;
-    l_inw = q; q += (size_t)3 * d * d; l_inb = q; q += 3 * d;
-    l_outw = q; q += (size_t)d * d; l_outb = q; q += d;
-    l_w1 = q; q += (size_t)ff * d; l_b1 = q; q += ff;
-    l_w2 = q; q += (size_t)d * ff; l_b2 = q; q += d;
-    l_n1w = q; q += d; l_n1b = q; q += d; l_n2w = q; q += d; l_n2b = q; q += d;
-    layer_stride = q;
-    o += q * layers;
-    wo = o; o += (size_t)c * d; bo = o; o += c;
+    o = 0;
+    l_inw = take((size_t)3 * d * d); l_inb = take(3 * d);
+    l_outw = take((size_t)d * d); l_outb = take(d);
+    l_w1 = take((size_t)ff * d); l_b1 = take(ff);
+    l_w2 = take((size_t)d * ff); l_b2 = take(d);
+    l_n1w = take(d); l_n1b = take(d); l_n2w = take(d); l_n2b = take(d);
+    layer_stride = o;
+    o = layer0 + layer_stride * layers;
+    wo = take((size_t)c * d); bo = take(c);
     total = o;
   }
 };

@@ -177,9 +177,10 @@ class BatchedILQR:
         else:
             e = self.expansion.view(N, R, B).permute(2, 0, 1)
             t = self.terminal.view(n + n * n, B).t()
-        o, out = 0, {}
-        for name, shape in (("A", (n, n)), ("B", (n, m)), ("lx", (n,)), ("lu", (m,)), ("lxx", (n, n)),
-                            ("luu", (m, m)), ("lux", (m, n))):
+        F = e[..., : n * (n + m)].reshape(B, N, n, n + m)      # [A | B] interleaved row by row
+        out = {"A": F[..., :n], "B": F[..., n:]}
+        o = n * (n + m)
+        for name, shape in (("lx", (n,)), ("lu", (m,)), ("lxx", (n, n)), ("luu", (m, m)), ("lux", (m, n))):
             sz = int(np.prod(shape))
             out[name] = e[..., o:o + sz].reshape((B, N) + shape)
             o += sz

@@ -116,7 +116,10 @@ class TransformerILQR:
                                           "self_attn.out_proj.bias", "linear1.weight", "linear1.bias", "linear2.weight",
                                           "linear2.bias", "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias")]
         parts += [sd["output_linear.weight"], sd["output_linear.bias"]]
-        flat = torch.cat([p.reshape(-1) for p in parts]).contiguous()
+        def pad32(t):                      # every tensor starts on a 32-float boundary (qx_tf_common.cuh)
+            t = t.reshape(-1)
+            return torch.cat([t, t.new_zeros((-t.numel()) % 32)])
+        flat = torch.cat([pad32(p) for p in parts]).contiguous()
         cfg = self.config()
         expect = _lib.load().qx_tf_weight_floats(C.byref(cfg))
         if flat.numel() != expect:
