@@ -137,8 +137,15 @@ int qx_linesearch(const QxParams* p, double* x_in, double* u_in, const float* ga
  * last prompt_len gain records, writes gain records for t in [0, target_len). */
 size_t qx_tf_weight_floats(const QxTfConfig* cfg);
 size_t qx_tf_workspace_bytes(const QxTfConfig* cfg, int B);
-int qx_tf_forward(const QxTfConfig* cfg, const float* weights, const double* x, const double* x_shift,
-                  float* gains, int model_id, const int32_t* status, void* workspace, int B, void* stream);
+/* Tensor-core path: the four dense weights of every layer split once into (hi, lo) TF32 halves
+ * (3xTF32, fp32-accurate products).  wsplit has qx_tf_split_floats() floats. */
+size_t qx_tf_split_floats(const QxTfConfig* cfg);
+int qx_tf_prepare(const QxTfConfig* cfg, const float* weights, float* wsplit, void* stream);
+/* wsplit == NULL selects the exact-fp32 CUDA-core GEMMs; otherwise the dense layers run on
+ * tcgen05 (kind::tf32, TMEM accumulators, TMA-staged operands). */
+int qx_tf_forward(const QxTfConfig* cfg, const float* weights, const float* wsplit, const double* x,
+                  const double* x_shift, float* gains, int model_id, const int32_t* status, void* workspace, int B,
+                  void* stream);
 
 #ifdef __cplusplus
 }

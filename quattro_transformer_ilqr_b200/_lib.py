@@ -52,7 +52,9 @@ SIGNATURES = {
                                 C.c_int, C.c_int, _P]),
     "qx_tf_weight_floats": (C.c_size_t, [C.POINTER(QxTfConfig)]),
     "qx_tf_workspace_bytes": (C.c_size_t, [C.POINTER(QxTfConfig), C.c_int]),
-    "qx_tf_forward": (C.c_int, [C.POINTER(QxTfConfig), _P, _P, _P, _P, C.c_int, _P, _P, C.c_int, _P]),
+    "qx_tf_split_floats": (C.c_size_t, [C.POINTER(QxTfConfig)]),
+    "qx_tf_prepare": (C.c_int, [C.POINTER(QxTfConfig), _P, _P, _P]),
+    "qx_tf_forward": (C.c_int, [C.POINTER(QxTfConfig), _P, _P, _P, _P, _P, C.c_int, _P, _P, C.c_int, _P]),
 }
 
 _lib = None

@@ -203,8 +203,27 @@ static int gemm(const float* A, const float* W, const float* bias, float* C, int
   return QX_OK;
 }
 
-int tf_forward_simt(const QxTfConfig* cfg, const float* w, const double* x, const double* x_shift, float* gains,
-                    int layout, const int32_t* status, float* ws, int B, cudaStream_t st) {
+// tensor-core GEMM (qx_tf_tc.cu)
+int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* bias, float* C, int M, int N, int K,
+               bool relu, cudaStream_t st);
+int tf_split_weights(const float* w, float* hi, float* lo, size_t count, cudaStream_t st);
+
+// offsets of the (hi, lo) copies of the four GEMM weights of one layer inside the split buffer
+struct SplitLayout {
+  size_t in_hi, in_lo, out_hi, out_lo, w1_hi, w1_lo, w2_hi, w2_lo, stride;
+  explicit SplitLayout(const TfLayout& l) {
+    const size_t d = l.d, ff = l.ff;
+    size_t o = 0;
+    in_hi = o; o += 3 * d * d; in_lo = o; o += 3 * d * d;
+    out_hi = o; o += d * d; out_lo = o; o += d * d;
+    w1_hi = o; o += ff * d; w1_lo = o; o += ff * d;
+    w2_hi = o; o += d * ff; w2_lo = o; o += d * ff;
+    stride = o;
+  }
+};
+
+int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, const double* x, const double* x_shift,
+                    float* gains, int layout, const int32_t* status, float* ws, int B, cudaStream_t st) {
   const TfLayout lay(*cfg);
   const int d = lay.d, L = lay.L, ff = lay.ff, rows = B * L;
   float* h = ws;
@@ -218,17 +237,27 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const double* x, cons
   QX_CHECK_LAUNCH("tf_embed_kernel");
   const int hd = d / cfg->nhead;
   const size_t att_smem = (size_t)2 * L * (hd + 1) * sizeof(float);
+  const SplitLayout sp(lay);
+  // dense contraction: tcgen05 3xTF32 when split weights are supplied, exact-fp32 CUDA cores otherwise
+  auto dense = [&](const float* A, const float* lw, size_t w_off, size_t b_off, size_t hi_off, size_t lo_off, int l,
+                   float* C, int N, int K, bool relu) -> int {
+    if (wsplit != nullptr) {
+      const float* sw = wsplit + (size_t)l * sp.stride;
+      return tf_gemm_tc(A, sw + hi_off, sw + lo_off, lw + b_off, C, rows, N, K, relu, st);
+    }
+    return gemm(A, lw + w_off, lw + b_off, C, rows, N, K, relu, st);
+  };
   for (int l = 0; l < lay.layers; ++l) {
     const float* lw = w + lay.layer0 + (size_t)l * lay.layer_stride;
-    int rc = gemm(h, lw + lay.l_inw, lw + lay.l_inb, qkv, rows, 3 * d, d, false, st);
+    int rc = dense(h, lw, lay.l_inw, lay.l_inb, sp.in_hi, sp.in_lo, l, qkv, 3 * d, d, false);
     if (rc) return rc;
     tf_attention_kernel<32><<<dim3(cfg->nhead, B), 128, att_smem, st>>>(qkv, att, L, d);
     QX_CHECK_LAUNCH("tf_attention_kernel");
-    if ((rc = gemm(att, lw + lay.l_outw, lw + lay.l_outb, y, rows, d, d, false, st))) return rc;
+    if ((rc = dense(att, lw, lay.l_outw, lay.l_outb, sp.out_hi, sp.out_lo, l, y, d, d, false))) return rc;
     tf_add_ln_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(h, y, lw + lay.l_n1w, lw + lay.l_n1b, rows);
     QX_CHECK_LAUNCH("tf_add_ln_kernel");
-    if ((rc = gemm(h, lw + lay.l_w1, lw + lay.l_b1, ffh, rows, ff, d, true, st))) return rc;
-    if ((rc = gemm(ffh, lw + lay.l_w2, lw + lay.l_b2, y, rows, d, ff, false, st))) return rc;
+    if ((rc = dense(h, lw, lay.l_w1, lay.l_b1, sp.w1_hi, sp.w1_lo, l, ffh, ff, d, true))) return rc;
+    if ((rc = dense(ffh, lw, lay.l_w2, lay.l_b2, sp.w2_hi, sp.w2_lo, l, y, d, ff, false))) return rc;
     tf_add_ln_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(h, y, lw + lay.l_n2w, lw + lay.l_n2b, rows);
     QX_CHECK_LAUNCH("tf_add_ln_kernel");
   }
@@ -252,18 +281,42 @@ extern "C" size_t qx_tf_workspace_bytes(const QxTfConfig* cfg, int B) {
   return (size_t)B * lay.L * (6 * (size_t)lay.d + lay.ff) * sizeof(float);
 }
 
-extern "C" int qx_tf_forward(const QxTfConfig* cfg, const float* weights, const double* x, const double* x_shift,
-                             float* gains, int model_id, const int32_t* status, void* workspace, int B,
-                             void* stream) {
+extern "C" size_t qx_tf_split_floats(const QxTfConfig* cfg) {
+  if (!cfg) return 0;
+  const qx::TfLayout lay(*cfg);
+  return qx::SplitLayout(lay).stride * lay.layers;
+}
+
+extern "C" int qx_tf_prepare(const QxTfConfig* cfg, const float* weights, float* wsplit, void* stream) {
+  QX_CHECK_ARG(cfg && weights && wsplit, "null pointer");
+  const qx::TfLayout lay(*cfg);
+  const qx::SplitLayout sp(lay);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t d = lay.d, ff = lay.ff;
+  for (int l = 0; l < lay.layers; ++l) {
+    const float* lw = weights + lay.layer0 + (size_t)l * lay.layer_stride;
+    float* sw = wsplit + (size_t)l * sp.stride;
+    int rc;
+    if ((rc = qx::tf_split_weights(lw + lay.l_inw, sw + sp.in_hi, sw + sp.in_lo, 3 * d * d, st))) return rc;
+    if ((rc = qx::tf_split_weights(lw + lay.l_outw, sw + sp.out_hi, sw + sp.out_lo, d * d, st))) return rc;
+    if ((rc = qx::tf_split_weights(lw + lay.l_w1, sw + sp.w1_hi, sw + sp.w1_lo, ff * d, st))) return rc;
+    if ((rc = qx::tf_split_weights(lw + lay.l_w2, sw + sp.w2_hi, sw + sp.w2_lo, d * ff, st))) return rc;
+  }
+  return QX_OK;
+}
+
+extern "C" int qx_tf_forward(const QxTfConfig* cfg, const float* weights, const float* wsplit, const double* x,
+                             const double* x_shift, float* gains, int model_id, const int32_t* status, void* workspace,
+                             int B, void* stream) {
   QX_CHECK_ARG(cfg && weights && x && x_shift && gains && workspace, "null pointer");
   QX_CHECK_ARG(B > 0, "B must be positive");
   QX_CHECK_ARG(cfg->d_model == 128 && cfg->d_model / cfg->nhead == 32, "kernels are built for d_model 128, head_dim 32");
   QX_CHECK_ARG(cfg->control_dim <= 64 && cfg->state_dim <= 64, "state/control dims must be <= 64");
-  QX_CHECK_ARG(cfg->dim_ff % 64 == 0, "dim_feedforward must be a multiple of 64");
+  QX_CHECK_ARG(cfg->dim_ff % 128 == 0, "dim_feedforward must be a multiple of 128");
   QX_CHECK_ARG(cfg->control_dim == cfg->m * (1 + cfg->state_dim), "control_dim must equal m (1 + n)");
   QX_CHECK_ARG(cfg->horizon == cfg->target_len + cfg->prompt_len, "horizon must equal target_len + prompt_len");
   const int layout = qx_layout(model_id);
   if (layout < 0) return layout;
-  return qx::tf_forward_simt(cfg, weights, x, x_shift, gains, layout, status, static_cast<float*>(workspace), B,
+  return qx::tf_forward_simt(cfg, weights, wsplit, x, x_shift, gains, layout, status, static_cast<float*>(workspace), B,
                              static_cast<cudaStream_t>(stream));
 }

@@ -35,7 +35,8 @@ class TransformerILQR:
         self.device = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
         self.model = None
         self.normalizer = DataNormalizer()
-        self._packed = None          # (device, float32 tensor) cache of the packed weights
+        self._packed = None          # (device, packed weights, TF32 hi/lo split of the dense weights)
+        self.tensor_cores = True     # dense layers on tcgen05 (3xTF32); False = exact-fp32 CUDA cores
         self._shift = None
         self._ws = None
         self._solo = None            # 1-trajectory scratch engine state for predict()
@@ -127,9 +128,16 @@ class TransformerILQR:
         return flat
 
     def _device_weights(self, device):
+        """(packed weights, hi/lo split of the dense weights) resident on `device`."""
         if self._packed is None or self._packed[0] != device:
-            self._packed = (device, self.pack_weights().to(device))
-        return self._packed[1]
+            lib = _lib.load()
+            cfg = self.config()
+            w = self.pack_weights().to(device)
+            split = torch.empty(lib.qx_tf_split_floats(C.byref(cfg)), dtype=torch.float32, device=device)
+            _lib.check(lib.qx_tf_prepare(C.byref(cfg), C.c_void_p(w.data_ptr()), C.c_void_p(split.data_ptr()),
+                                         C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "qx_tf_prepare")
+            self._packed = (device, w, split)
+        return self._packed[1], self._packed[2]
 
     def invalidate(self):
         """Call after mutating ``model`` / ``normalizer`` in place (e.g. after training)."""
@@ -145,14 +153,16 @@ class TransformerILQR:
         lib = _lib.load()
         cfg = self.config()
         dev = engine.device
-        w = self._device_weights(dev)
+        w, split = self._device_weights(dev)
         need = lib.qx_tf_workspace_bytes(C.byref(cfg), engine.B)
         if self._ws is None or self._ws.device != dev or self._ws.numel() * 4 < need:
             self._ws = torch.empty(need // 4, dtype=torch.float32, device=dev)
         if self._shift is None or self._shift.device != dev:
             self.set_shift(np.zeros(self.state_dim), dev)
         c = engine.cur
-        _lib.check(lib.qx_tf_forward(C.byref(cfg), C.c_void_p(w.data_ptr()), C.c_void_p(engine.x[c].data_ptr()),
+        _lib.check(lib.qx_tf_forward(C.byref(cfg), C.c_void_p(w.data_ptr()),
+                                     C.c_void_p(split.data_ptr() if self.tensor_cores else 0),
+                                     C.c_void_p(engine.x[c].data_ptr()),
                                      C.c_void_p(self._shift.data_ptr()), C.c_void_p(engine.gains.data_ptr()),
                                      engine.model.model_id, C.c_void_p(engine.status.data_ptr()),
                                      C.c_void_p(self._ws.data_ptr()), engine.B, engine.stream), "qx_tf_forward")

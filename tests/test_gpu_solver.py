@@ -187,9 +187,25 @@ def test_transformer_predict_matches_reference(system, mode, golden_dir):
     assert relmax(batch, g[f"pred_{mode}"]) < tol
     from tests.test_oracle import oracle_from_wrapper
     exact = oracle_from_wrapper(w, dtype=np.float64).predict_batch(g["x_err"], g["kK"])
-    assert relmax(batch, exact) < 2e-5
+    # the reference's own fp32 prediction sits 2.3e-5 (quadrotor checkpoint) / 1e-7 from this oracle
+    assert relmax(batch, exact) < (5e-5 if mode == "fp32" else 5e-6)
     if mode == "fp32":      # shipped fp16 checkpoint run by the reference in fp16: its own quantisation gap
         assert relmax(batch, g["pred_fp16"]) < 5e-2
+
+
+@pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
+def test_tensor_core_path_matches_exact_fp32_path(system, golden_dir):
+    """tcgen05 3xTF32 dense layers vs the exact-fp32 CUDA-core GEMMs on the same inputs, at a batch
+    that is not a multiple of the 128-row tile (B*L = 16*61 / 8*101 rows)."""
+    g = np.load(f"{golden_dir}/tf_forward_{system}.npz")
+    w = _wrapper(system, "rand")
+    w.tensor_cores = False
+    exact = w.predict(g["x_err"], g["kK"])
+    w.tensor_cores = True
+    tc = w.predict(g["x_err"], g["kK"])
+    err = relmax(tc, exact)
+    print(f"{system}: tensor-core vs exact fp32 path max-norm relative error {err:.2e}")
+    assert err < 5e-6
 
 
 @pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
