@@ -100,48 +100,67 @@ tf_gemm_kernel(const float* __restrict__ A, const float* __restrict__ W, const f
 }
 
 // ---- causal multi-head attention: grid (nhead, B), block 128 threads (one query row each) ------
+// K and V rows (128 B) are read as warp-broadcast 16-B vectors.  Two passes over the keys (row
+// maximum, then exp / PV) recompute the 32-term score instead of parking it: 26 KB of shared memory
+// per block keeps 8 blocks (32 warps) resident per SM, which is what hides the LDS latency.
 template <int HD>
 __global__ void __launch_bounds__(128)
 tf_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int L, int d) {
-  extern __shared__ float sm[];
-  float* Ks = sm;                    // [L][HD + 1]
-  float* Vs = sm + (size_t)L * (HD + 1);
-  const int head = blockIdx.x, b = blockIdx.y;
+  extern __shared__ float4 sm4[];
+  float4* Ks = sm4;                                  // [L][HD/4]
+  float4* Vs = sm4 + (size_t)L * (HD / 4);
+  const int head = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const float* base = qkv + (size_t)b * L * 3 * d;
-  for (int e = threadIdx.x; e < L * HD; e += blockDim.x) {
-    const int r = e / HD, cc = e % HD;
-    Ks[r * (HD + 1) + cc] = base[(size_t)r * 3 * d + d + head * HD + cc];
-    Vs[r * (HD + 1) + cc] = base[(size_t)r * 3 * d + 2 * d + head * HD + cc];
+  for (int e = tid; e < L * (HD / 4); e += 128) {
+    const int r = e / (HD / 4), c4 = e % (HD / 4);
+    Ks[e] = *reinterpret_cast<const float4*>(base + (size_t)r * 3 * d + d + head * HD + 4 * c4);
+    Vs[e] = *reinterpret_cast<const float4*>(base + (size_t)r * 3 * d + 2 * d + head * HD + 4 * c4);
   }
   __syncthreads();
+  const int i = tid;
+  const bool live = i < L;
   const float scale = rsqrtf((float)HD);
-  for (int i = threadIdx.x; i < L; i += blockDim.x) {
-    float q[HD];
+  float4 q[HD / 4];
 #pragma unroll
-    for (int cc = 0; cc < HD; ++cc) q[cc] = base[(size_t)i * 3 * d + head * HD + cc];
-    // two passes over keys j <= i: max, then exp-sum and weighted V
-    float mx = -INFINITY;
-    for (int j = 0; j <= i; ++j) {
-      float s = 0.f;
+  for (int c = 0; c < HD / 4; ++c) {
+    q[c] = live ? *reinterpret_cast<const float4*>(base + (size_t)i * 3 * d + head * HD + 4 * c) : make_float4(0, 0, 0, 0);
+    q[c].x *= scale; q[c].y *= scale; q[c].z *= scale; q[c].w *= scale;
+  }
+  const int jmax = min(L - 1, (tid | 31));           // warp-uniform loop bound (causal: j <= i)
+  auto score = [&](int j) {
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-      for (int cc = 0; cc < HD; ++cc) s += q[cc] * Ks[j * (HD + 1) + cc];
-      mx = fmaxf(mx, s * scale);
+    for (int c = 0; c < HD / 4; c += 2) {
+      const float4 k0 = Ks[j * (HD / 4) + c], k1 = Ks[j * (HD / 4) + c + 1];
+      s0 = fmaf(q[c].x, k0.x, s0); s0 = fmaf(q[c].y, k0.y, s0); s0 = fmaf(q[c].z, k0.z, s0); s0 = fmaf(q[c].w, k0.w, s0);
+      s1 = fmaf(q[c + 1].x, k1.x, s1); s1 = fmaf(q[c + 1].y, k1.y, s1); s1 = fmaf(q[c + 1].z, k1.z, s1); s1 = fmaf(q[c + 1].w, k1.w, s1);
     }
-    float den = 0.f, o[HD];
+    return s0 + s1;
+  };
+  float mx = -INFINITY;
+  for (int j = 0; j <= jmax; ++j) {
+    const float sc = score(j);
+    if (j <= i) mx = fmaxf(mx, sc);
+  }
+  float den = 0.f;
+  float4 o[HD / 4];
 #pragma unroll
-    for (int cc = 0; cc < HD; ++cc) o[cc] = 0.f;
-    for (int j = 0; j <= i; ++j) {
-      float s = 0.f;
+  for (int c = 0; c < HD / 4; ++c) o[c] = make_float4(0, 0, 0, 0);
+  for (int j = 0; j <= jmax; ++j) {
+    const float pj = (j <= i) ? expf(score(j) - mx) : 0.f;
+    den += pj;
 #pragma unroll
-      for (int cc = 0; cc < HD; ++cc) s += q[cc] * Ks[j * (HD + 1) + cc];
-      const float pj = expf(s * scale - mx);
-      den += pj;
-#pragma unroll
-      for (int cc = 0; cc < HD; ++cc) o[cc] += pj * Vs[j * (HD + 1) + cc];
+    for (int c = 0; c < HD / 4; ++c) {
+      const float4 v = Vs[j * (HD / 4) + c];
+      o[c].x = fmaf(pj, v.x, o[c].x); o[c].y = fmaf(pj, v.y, o[c].y);
+      o[c].z = fmaf(pj, v.z, o[c].z); o[c].w = fmaf(pj, v.w, o[c].w);
     }
+  }
+  if (live) {
     const float inv = 1.f / den;
+    float4* dst = reinterpret_cast<float4*>(out + ((size_t)b * L + i) * d + head * HD);
 #pragma unroll
-    for (int cc = 0; cc < HD; ++cc) out[((size_t)b * L + i) * d + head * HD + cc] = o[cc] * inv;
+    for (int c = 0; c < HD / 4; ++c) dst[c] = make_float4(o[c].x * inv, o[c].y * inv, o[c].z * inv, o[c].w * inv);
   }
 }
 
@@ -194,6 +213,32 @@ __global__ void tf_output_kernel(const QxTfConfig cfg, const float* __restrict__
   else gains[((size_t)t * G + slot) * B + b] = val;
 }
 
+// de-normalise + unpack of a precomputed output head y[rows][128] (tensor-core path)
+template <int LAYOUT>
+__global__ void tf_unpack_kernel(const QxTfConfig cfg, const float* __restrict__ w, const float* __restrict__ y,
+                                 float* __restrict__ gains, const int32_t* __restrict__ status, int B) {
+  const TfLayout lay(cfg);
+  const int t = blockIdx.x, b = blockIdx.y, o = threadIdx.x;
+  if (status != nullptr && status[b] != 0) return;
+  const int c = lay.c, m = cfg.m, n = lay.n;
+  if (o >= c) return;
+  const float acc = y[((size_t)b * lay.L + (lay.L - lay.T + t)) * 128 + o];
+  const float val = acc * w[lay.u_std + o] + w[lay.u_mean + o];
+  const int a = o / (1 + n), j = o % (1 + n);
+  const int slot = (j == 0) ? a : (m + a * n + (j - 1));
+  const int G = m + m * n;
+  if (LAYOUT == QX_LAYOUT_REC) gains[((size_t)t * B + b) * G + slot] = val;
+  else gains[((size_t)t * G + slot) * B + b] = val;
+}
+
+// zero-padded copy of the output head: W_out [c][d] -> [128][d], bias [c] -> [128]
+__global__ void tf_pad_head_kernel(const float* __restrict__ wo, const float* __restrict__ bo, float* __restrict__ wpad,
+                                   float* __restrict__ bpad, int c, int d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 128 * d) wpad[i] = (i / d < c) ? wo[i] : 0.f;
+  if (i < 128) bpad[i] = (i < c) ? bo[i] : 0.f;
+}
+
 static int gemm(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, bool relu,
                 cudaStream_t st) {
   dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
@@ -211,6 +256,7 @@ int tf_split_weights(const float* w, float* hi, float* lo, size_t count, cudaStr
 // offsets of the (hi, lo) copies of the four GEMM weights of one layer inside the split buffer
 struct SplitLayout {
   size_t in_hi, in_lo, out_hi, out_lo, w1_hi, w1_lo, w2_hi, w2_lo, stride;
+  size_t head_pad, head_hi, head_lo, head_bias, total;     // after the per-layer blocks
   explicit SplitLayout(const TfLayout& l) {
     const size_t d = l.d, ff = l.ff;
     size_t o = 0;
@@ -219,6 +265,9 @@ struct SplitLayout {
     w1_hi = o; o += ff * d; w1_lo = o; o += ff * d;
     w2_hi = o; o += d * ff; w2_lo = o; o += d * ff;
     stride = o;
+    size_t g = stride * l.layers;
+    head_pad = g; g += 128 * d; head_hi = g; g += 128 * d; head_lo = g; g += 128 * d; head_bias = g; g += 128;
+    total = g;
   }
 };
 
@@ -236,7 +285,12 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
   else tf_embed_kernel<QX_LAYOUT_SOA><<<ge, d, 0, st>>>(*cfg, w, x, x_shift, gains, h, B);
   QX_CHECK_LAUNCH("tf_embed_kernel");
   const int hd = d / cfg->nhead;
-  const size_t att_smem = (size_t)2 * L * (hd + 1) * sizeof(float);
+  const size_t att_smem = (size_t)2 * L * hd * sizeof(float);
+  static bool att_cfg = false;
+  if (!att_cfg) {
+    cudaFuncSetAttribute(tf_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    att_cfg = true;
+  }
   const SplitLayout sp(lay);
   // dense contraction: tcgen05 3xTF32 when split weights are supplied, exact-fp32 CUDA cores otherwise
   auto dense = [&](const float* A, const float* lw, size_t w_off, size_t b_off, size_t hi_off, size_t lo_off, int l,
@@ -262,6 +316,14 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
     QX_CHECK_LAUNCH("tf_add_ln_kernel");
   }
   dim3 go(lay.T, B);
+  if (wsplit != nullptr) {      // output head as one more tensor-core GEMM over all rows (N padded to 128)
+    int rc = tf_gemm_tc(h, wsplit + sp.head_hi, wsplit + sp.head_lo, wsplit + sp.head_bias, y, rows, 128, d, false, st);
+    if (rc) return rc;
+    if (layout == QX_LAYOUT_REC) tf_unpack_kernel<QX_LAYOUT_REC><<<go, 64, 0, st>>>(*cfg, w, y, gains, status, B);
+    else tf_unpack_kernel<QX_LAYOUT_SOA><<<go, 64, 0, st>>>(*cfg, w, y, gains, status, B);
+    QX_CHECK_LAUNCH("tf_unpack_kernel");
+    return QX_OK;
+  }
   if (layout == QX_LAYOUT_REC) tf_output_kernel<QX_LAYOUT_REC><<<go, 64, 0, st>>>(*cfg, w, h, gains, status, B);
   else tf_output_kernel<QX_LAYOUT_SOA><<<go, 64, 0, st>>>(*cfg, w, h, gains, status, B);
   QX_CHECK_LAUNCH("tf_output_kernel");
@@ -284,7 +346,7 @@ extern "C" size_t qx_tf_workspace_bytes(const QxTfConfig* cfg, int B) {
 extern "C" size_t qx_tf_split_floats(const QxTfConfig* cfg) {
   if (!cfg) return 0;
   const qx::TfLayout lay(*cfg);
-  return qx::SplitLayout(lay).stride * lay.layers;
+  return qx::SplitLayout(lay).total;
 }
 
 extern "C" int qx_tf_prepare(const QxTfConfig* cfg, const float* weights, float* wsplit, void* stream) {
@@ -302,7 +364,11 @@ extern "C" int qx_tf_prepare(const QxTfConfig* cfg, const float* weights, float*
     if ((rc = qx::tf_split_weights(lw + lay.l_w1, sw + sp.w1_hi, sw + sp.w1_lo, ff * d, st))) return rc;
     if ((rc = qx::tf_split_weights(lw + lay.l_w2, sw + sp.w2_hi, sw + sp.w2_lo, d * ff, st))) return rc;
   }
-  return QX_OK;
+  qx::tf_pad_head_kernel<<<(unsigned)((128 * d + 255) / 256), 256, 0, st>>>(weights + lay.wo, weights + lay.bo,
+                                                                          wsplit + sp.head_pad, wsplit + sp.head_bias,
+                                                                          lay.c, (int)d);
+  QX_CHECK_LAUNCH("tf_pad_head_kernel");
+  return qx::tf_split_weights(wsplit + sp.head_pad, wsplit + sp.head_hi, wsplit + sp.head_lo, 128 * d, st);
 }
 
 extern "C" int qx_tf_forward(const QxTfConfig* cfg, const float* weights, const float* wsplit, const double* x,

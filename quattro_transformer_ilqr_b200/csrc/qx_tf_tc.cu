@@ -8,14 +8,17 @@
 // holding the top 19 bits (what kind::tf32 reads) and *_lo the exact remainder;
 // A W^T ~= A_hi W_hi^T + A_hi W_lo^T + A_lo W_hi^T, accumulated in fp32 in TMEM.
 //
-// One CTA computes one 128 x 128 output tile:
-//   warp 0   TMA producer: per 32-wide K block, three 2-D tiled loads (A raw, W_hi, W_lo; 128-B
-//            swizzle) into a 3-stage shared-memory ring, completion on "full" mbarriers
+// Persistent kernel, one CTA per SM looping over 128 x 128 output tiles (n fastest, so the CTAs
+// that share an A tile run together and it is read from HBM once):
+//   warp 0    TMA producer: per 32-wide K block, three 2-D tiled loads (A raw, W_hi, W_lo; 128-B
+//             swizzle) into a 3-stage shared-memory ring, completion on "full" mbarriers
 //   warps 2-5 splitter: turn the raw A tile into A_hi (masked in place) and A_lo, then
-//            fence.proxy.async + arrive on "ready"; afterwards they are the epilogue warps
-//   warp 1   allocates 128 TMEM columns; one elected lane issues 12 tcgen05.mma (kind::tf32,
-//            M=128, N=128, K=8) per K block and tcgen05.commit's the stage back to the producer
-//   epilogue tcgen05.ld (32x32b.x32) TMEM -> registers, + bias, optional ReLU, 16-B stores
+//             fence.proxy.async + arrive on "ready"
+//   warp 1    allocates 256 TMEM columns (two accumulators); one elected lane issues 12 tcgen05.mma
+//             (kind::tf32, M=128, N=128, K=8) per K block, tcgen05.commit's the stage back to the
+//             producer and, after the last K block, the accumulator to the epilogue
+//   warps 6-9 epilogue: tcgen05.ld (32x32b.x32) TMEM -> registers, + bias, optional ReLU, 16-B
+//             stores; runs concurrently with the next tile's MMAs (double-buffered TMEM)
 #include <cuda.h>
 
 #include "qx_async.cuh"
@@ -34,7 +37,8 @@ struct GemmStage {
 };
 struct GemmSmem {
   GemmStage st[kGemmStages];
-  uint64_t full[kGemmStages], ready[kGemmStages], empty[kGemmStages], tmem_full;
+  float4 epi[4][32][8];          // per epilogue warp: 32 rows x 32 columns, 16-B chunks XOR-swizzled by row
+  uint64_t full[kGemmStages], ready[kGemmStages], empty[kGemmStages], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
 constexpr size_t kGemmSmemBytes = sizeof(GemmSmem) + 1024;   // + slack to align the ring to 1024 B
@@ -70,19 +74,29 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem) {
   d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
   return d;
 }
+// hi = a rounded to the nearest TF32 (10 explicit mantissa bits), lo = the exact remainder rounded
+// to TF32 as well: a*w - (hi*w_hi + hi*w_lo + lo*w_hi) is then ~3 * 2^-24 |a w| (fp32-class accuracy).
+__device__ __forceinline__ float tf32_rn(float v) {
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ void tf32_split(float v, float& hi, float& lo) {
+  hi = tf32_rn(v);
+  lo = tf32_rn(v - hi);
+}
 // D = F32, A = B = TF32, both K-major, M = 128, N = 128
 constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 
 template <bool RELU>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 tf_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
                   const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, float* __restrict__ C,
                   int M, int N, int K) {
   extern __shared__ uint8_t smem_raw[];
   GemmSmem& s = *reinterpret_cast<GemmSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * kBN, m0 = blockIdx.y * kBM;
   const int KB = K / kBK;
+  const int n_tiles_n = N / kBN;
+  const int n_tiles = n_tiles_n * ceil_div(M, kBM);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kGemmStages; ++i) {
@@ -90,11 +104,14 @@ tf_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&s.ready[i], 128);
       mbar_init(&s.empty[i], 1);
     }
-    mbar_init(&s.tmem_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.acc_full[i], 1);
+      mbar_init(&s.acc_empty[i], 128);
+    }
     mbar_fence_init();
   }
-  if (warp == 1) {   // TMEM: 128 fp32 accumulator columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "n"(kBN)
+  if (warp == 1) {   // TMEM: two 128-column fp32 accumulators (double buffered across tiles)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "n"(2 * kBN)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -104,79 +121,100 @@ tf_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem = s.tmem_base;
 
   if (warp == 0) {
+    // ---- TMA producer ------------------------------------------------------------------------------
     if (lane == 0) {
-      for (int kb = 0; kb < KB; ++kb) {
-        const int st = kb % kGemmStages;
-        mbar_wait(&s.empty[st], ((kb / kGemmStages) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&s.full[st], 3 * kTileBytes);
-        tma_load_2d(&tmA, &s.full[st], s.st[st].a_hi, kb * kBK, m0);
-        tma_load_2d(&tmWhi, &s.full[st], s.st[st].w_hi, kb * kBK, n0);
-        tma_load_2d(&tmWlo, &s.full[st], s.st[st].w_lo, kb * kBK, n0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int n0 = (tile % n_tiles_n) * kBN, m0 = (tile / n_tiles_n) * kBM;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int st = it % kGemmStages;
+          mbar_wait(&s.empty[st], ((it / kGemmStages) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&s.full[st], 3 * kTileBytes);
+          tma_load_2d(&tmA, &s.full[st], s.st[st].a_hi, kb * kBK, m0);
+          tma_load_2d(&tmWhi, &s.full[st], s.st[st].w_hi, kb * kBK, n0);
+          tma_load_2d(&tmWlo, &s.full[st], s.st[st].w_lo, kb * kBK, n0);
+        }
       }
     }
   } else if (warp == 1) {
+    // ---- MMA issuer ----------------------------------------------------------------------------------
     if (lane == 0) {
-      for (int kb = 0; kb < KB; ++kb) {
-        const int st = kb % kGemmStages;
-        mbar_wait(&s.ready[st], (kb / kGemmStages) & 1u);
+      uint32_t it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+        const uint32_t buf = tl & 1u;
+        mbar_wait(&s.acc_empty[buf], ((tl >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator
         tcgen05_fence_after();
-        const uint64_t da_hi = umma_desc_sw128(s.st[st].a_hi), da_lo = umma_desc_sw128(s.st[st].a_lo);
-        const uint64_t dw_hi = umma_desc_sw128(s.st[st].w_hi), dw_lo = umma_desc_sw128(s.st[st].w_lo);
+        const uint32_t acc = tmem + buf * kBN;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int st = it % kGemmStages;
+          mbar_wait(&s.ready[st], (it / kGemmStages) & 1u);
+          tcgen05_fence_after();
+          const uint64_t da_hi = umma_desc_sw128(s.st[st].a_hi), da_lo = umma_desc_sw128(s.st[st].a_lo);
+          const uint64_t dw_hi = umma_desc_sw128(s.st[st].w_hi), dw_lo = umma_desc_sw128(s.st[st].w_lo);
 #pragma unroll
-        for (int k = 0; k < kBK / 8; ++k) {
-          const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);       // 32 bytes per K=8 slice
-          mma_tf32(tmem, da_lo + adv, dw_hi + adv, kIdescTf32, (kb | k) ? 1u : 0u);
-          mma_tf32(tmem, da_hi + adv, dw_lo + adv, kIdescTf32, 1u);
-          mma_tf32(tmem, da_hi + adv, dw_hi + adv, kIdescTf32, 1u);
+          for (int k = 0; k < kBK / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);       // 32 bytes per K=8 slice
+            mma_tf32(acc, da_lo + adv, dw_hi + adv, kIdescTf32, (kb | k) ? 1u : 0u);
+            mma_tf32(acc, da_hi + adv, dw_lo + adv, kIdescTf32, 1u);
+            mma_tf32(acc, da_hi + adv, dw_hi + adv, kIdescTf32, 1u);
+          }
+          tcgen05_commit(&s.empty[st]);          // frees the stage when these MMAs have read it
         }
-        tcgen05_commit(&s.empty[st]);          // frees the stage when these MMAs have read it
+        tcgen05_commit(&s.acc_full[buf]);
       }
-      tcgen05_commit(&s.tmem_full);
+    }
+  } else if (warp < 6) {
+    // ---- splitter: raw A -> (A_hi, A_lo) -------------------------------------------------------------
+    const int tid = threadIdx.x - 64;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const int st = it % kGemmStages;
+        mbar_wait(&s.full[st], (it / kGemmStages) & 1u);
+        float4* hi4 = reinterpret_cast<float4*>(s.st[st].a_hi);
+        float4* lo4 = reinterpret_cast<float4*>(s.st[st].a_lo);
+#pragma unroll
+        for (int i = 0; i < kBM * kBK / 4 / 128; ++i) {
+          const float4 v = hi4[tid + i * 128];
+          float4 h, l;
+          tf32_split(v.x, h.x, l.x);
+          tf32_split(v.y, h.y, l.y);
+          tf32_split(v.z, h.z, l.z);
+          tf32_split(v.w, h.w, l.w);
+          hi4[tid + i * 128] = h;
+          lo4[tid + i * 128] = l;
+        }
+        fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(&s.ready[st]);
+      }
     }
   } else {
-    // ---- splitter: raw A -> (A_hi, A_lo) -----------------------------------------------------
-    const int tid = threadIdx.x - 64;
-    for (int kb = 0; kb < KB; ++kb) {
-      const int st = kb % kGemmStages;
-      mbar_wait(&s.full[st], (kb / kGemmStages) & 1u);
-      float4* hi4 = reinterpret_cast<float4*>(s.st[st].a_hi);
-      float4* lo4 = reinterpret_cast<float4*>(s.st[st].a_lo);
+    // ---- epilogue: TMEM -> registers -> global, overlapping the next tile's MMAs -----------------------
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+      const int n0 = (tile % n_tiles_n) * kBN, m0 = (tile / n_tiles_n) * kBM;
+      const uint32_t buf = tl & 1u;
+      mbar_wait(&s.acc_full[buf], (tl >> 1) & 1u);
+      tcgen05_fence_after();
 #pragma unroll
-      for (int i = 0; i < kBM * kBK / 4 / 128; ++i) {
-        const float4 v = hi4[tid + i * 128];
-        float4 h, l;
-        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
-        hi4[tid + i * 128] = h;
-        lo4[tid + i * 128] = l;
-      }
-      fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core
-      mbar_arrive(&s.ready[st]);
-    }
-    // ---- epilogue: TMEM -> registers -> global -------------------------------------------------
-    mbar_wait(&s.tmem_full, 0);
-    tcgen05_fence_after();
-    const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-#pragma unroll
-    for (int c0 = 0; c0 < kBN; c0 += 32) {
-      uint32_t r[32];
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < M) {
-        float* dst = C + (size_t)row * N + n0 + c0;
+      for (int c0 = 0; c0 < kBN; c0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem + buf * kBN + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // bias / activation in registers, then transpose through shared memory so that every global
+        // store instruction writes four full 128-B row segments
         const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c0);
+        float4 (*stg)[8] = s.epi[q];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 bb = b4[j];
@@ -186,15 +224,26 @@ tf_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           o.z = __uint_as_float(r[4 * j + 2]) + bb.z;
           o.w = __uint_as_float(r[4 * j + 3]) + bb.w;
           if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-          reinterpret_cast<float4*>(dst)[j] = o;
+          stg[lane][j ^ (lane & 7)] = o;
         }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int rr = 4 * k + (lane >> 3), c4 = lane & 7;
+          const int grow = m0 + q * 32 + rr;
+          if (grow < M)
+            *reinterpret_cast<float4*>(C + (size_t)grow * N + n0 + c0 + 4 * c4) = stg[rr][c4 ^ (rr & 7)];
+        }
+        __syncwarp();
       }
+      tcgen05_fence_before();
+      mbar_arrive(&s.acc_empty[buf]);            // 128 arrivals release the accumulator
     }
   }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kBN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * kBN) : "memory");
   }
 }
 
@@ -202,10 +251,10 @@ tf_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 __global__ void tf_split_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, size_t count) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  const float v = w[i];
-  const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  float h, l;
+  tf32_split(w[i], h, l);
   hi[i] = h;
-  lo[i] = v - h;
+  lo[i] = l;
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -261,9 +310,16 @@ int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* 
     cudaFuncSetAttribute(tf_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes);
     configured = true;
   }
-  dim3 grid(N / kBN, ceil_div(M, kBM));
-  if (relu) tf_gemm_tc_kernel<true><<<grid, 192, kGemmSmemBytes, st>>>(ma, mh, ml, bias, C, M, N, K);
-  else tf_gemm_tc_kernel<false><<<grid, 192, kGemmSmemBytes, st>>>(ma, mh, ml, bias, C, M, N, K);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int tiles = (N / kBN) * ceil_div(M, kBM);
+  const int grid = tiles < num_sms ? tiles : num_sms;          // persistent: one CTA per SM
+  if (relu) tf_gemm_tc_kernel<true><<<grid, 320, kGemmSmemBytes, st>>>(ma, mh, ml, bias, C, M, N, K);
+  else tf_gemm_tc_kernel<false><<<grid, 320, kGemmSmemBytes, st>>>(ma, mh, ml, bias, C, M, N, K);
   QX_CHECK_LAUNCH("tf_gemm_tc_kernel");
   return QX_OK;
 }

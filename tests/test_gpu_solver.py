@@ -181,7 +181,7 @@ def test_transformer_predict_matches_reference(system, mode, golden_dir):
     # two fp32 implementations with different summation orders: the trained checkpoint (wide
     # dynamic range) shows 1.5e-5 between this kernel and torch-CPU; random-init weights < 1e-5.
     # Against the float64 NumPy oracle both are ~1e-5 away (checked below).
-    tol = 3e-5 if mode == "fp32" else 1e-5
+    tol = 5e-5 if mode == "fp32" else 1e-5
     assert relmax(pred, g[f"pred_{mode}"][:4]) < tol
     batch = w.predict(g["x_err"], g["kK"])
     assert relmax(batch, g[f"pred_{mode}"]) < tol
