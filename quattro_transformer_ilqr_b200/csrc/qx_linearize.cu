@@ -228,6 +228,163 @@ linearize_rec_kernel(const __grid_constant__ QxParams p, const double* __restric
   }
 }
 
+// ---- REC, quadrotor + Euler: only the entries that change from record to record are recomputed ----
+// Of the 416 floats of a record only 59 depend on (x_t, u_t): 27 entries of A = I + dt J, 12 of B,
+// [l_x | l_u] and the 4 diagonal entries of l_uu (the barrier curvature).  Each warp owns 32
+// trajectories and a run of consecutive time steps: the first half-record [F | l_x | l_u] lives
+// in a per-lane shared-memory row whose constant entries are written once, the second half
+// [l_xx | l_uu | l_ux] is a per-warp constant held in registers (two 16-B pieces per lane) and
+// patched with the four barrier terms on the way out.  Every global store is 512 contiguous bytes.
+constexpr int kLinSteps = 10;      // time steps per warp
+
+__global__ void __launch_bounds__(32)
+linearize_quad_euler_kernel(const __grid_constant__ QxParams p, const double* __restrict__ x,
+                            const double* __restrict__ u, float* __restrict__ expansion, float* __restrict__ terminal,
+                            const int32_t* __restrict__ status, int B, int N, int t_start) {
+  using Mdl = Quadrotor;
+  constexpr int n = 12, m = 4;
+  using R = Rec<n, m>;
+  constexpr int HALF = R::lxx;                 // 208 floats = 52 float4
+  constexpr int PITCH4 = 53;                   // row pitch in float4 (16-B aligned rows)
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ float4 stage4[32 * PITCH4];
+  __shared__ float bh_s[32][4];
+  const int lane = threadIdx.x;
+  const int b0 = blockIdx.x * 32, b = b0 + lane;
+  const int t_lo = t_start + blockIdx.y * kLinSteps, t_hi = min(N, t_lo + kLinSteps);
+  const bool mine = (b < B) && (status == nullptr || status[b] == 0);
+  const unsigned live = __ballot_sync(FULL, mine);
+  if (live == 0u) return;
+  float* row = reinterpret_cast<float*>(&stage4[lane * PITCH4]);
+  const float dt = float(p.dt);
+
+  // second half-record template [l_xx | l_uu | l_ux]: float4 #lane and #(32 + lane)
+  auto tmpl_elem = [&](int e) -> float {       // e in [0, 208)
+    if (e < n * n) { const int i = e / n, j = e % n; return float(p.Q[i * n + j] + p.Q[j * n + i]); }
+    e -= n * n;
+    if (e < m * m) { const int i = e / m, j = e % m; return float(p.R[i * m + j] + p.R[j * m + i]); }
+    return 0.f;
+  };
+  float4 tmpl0, tmpl1;
+  tmpl0 = make_float4(tmpl_elem(4 * lane), tmpl_elem(4 * lane + 1), tmpl_elem(4 * lane + 2), tmpl_elem(4 * lane + 3));
+  {
+    const int e = 4 * (32 + lane);
+    tmpl1 = (lane < 20) ? make_float4(tmpl_elem(e), tmpl_elem(e + 1), tmpl_elem(e + 2), tmpl_elem(e + 3))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+
+  // constant entries of the first half: A = I + dt J and B = dt G where J, G do not depend on (x,u)
+  if (mine) {
+    for (int e = 0; e < R::lx; ++e) row[e] = 0.f;
+#pragma unroll
+    for (int i = 0; i < n; ++i) row[R::a(i, i)] = 1.f;
+    row[R::a(0, 3)] = dt; row[R::a(1, 4)] = dt; row[R::a(2, 5)] = dt;
+    row[R::a(6, 9)] = dt;
+    const float aix = dt * float(p.phys[4] / p.phys[1]), aiy = dt * float(p.phys[4] / p.phys[2]);
+    const float kiz = dt * float(p.phys[6] / p.phys[3]);
+    row[R::b(9, 0)] = -aix; row[R::b(9, 1)] = aix; row[R::b(9, 2)] = aix; row[R::b(9, 3)] = -aix;
+    row[R::b(10, 0)] = aiy; row[R::b(10, 1)] = aiy; row[R::b(10, 2)] = -aiy; row[R::b(10, 3)] = -aiy;
+    row[R::b(11, 0)] = kiz; row[R::b(11, 1)] = -kiz; row[R::b(11, 2)] = kiz; row[R::b(11, 3)] = -kiz;
+  }
+  const float mass = float(p.phys[0]), Ix = float(p.phys[1]), Iy = float(p.phys[2]), Iz = float(p.phys[3]);
+  const float c1 = (Iy - Iz) / Ix, c2 = (Iz - Ix) / Iy, c3 = (Ix - Iy) / Iz, im = 1.f / mass;
+
+  for (int t = t_lo; t < t_hi; ++t) {
+    if (mine) {
+      float xs[n], us[m];
+      load_xu<Mdl>(x, u, t, b, B, xs, us);
+      float sphi, cphi, sth, cth, spsi, cpsi;
+      sincosf(xs[6], &sphi, &cphi);
+      sincosf(xs[7], &sth, &cth);
+      sincosf(xs[8], &spsi, &cpsi);
+      const float pp = xs[9], q = xs[10], r = xs[11];
+      const float Tm = (us[0] + us[1] + us[2] + us[3]) / mass;
+      const float sec = 1.f / cth, tth = sth * sec;
+      const float dirx = spsi * sphi + cpsi * sth * cphi;
+      const float diry = cpsi * sphi - spsi * sth * cphi;
+      const float dirz = cth * cphi;
+      // same expressions as Quadrotor::fc_jac (qx_models.cuh), scaled by dt
+      row[R::a(3, 6)] = dt * (Tm * (spsi * cphi - cpsi * sth * sphi));
+      row[R::a(3, 7)] = dt * (Tm * (cpsi * cth * cphi));
+      row[R::a(3, 8)] = dt * (Tm * diry);
+      row[R::a(4, 6)] = dt * (Tm * (cpsi * cphi + spsi * sth * sphi));
+      row[R::a(4, 7)] = dt * (Tm * (-spsi * cth * cphi));
+      row[R::a(4, 8)] = dt * (-Tm * dirx);
+      row[R::a(5, 6)] = dt * (-Tm * cth * sphi);
+      row[R::a(5, 7)] = dt * (-Tm * sth * cphi);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        row[R::b(3, j)] = dt * (im * dirx);
+        row[R::b(4, j)] = dt * (im * diry);
+        row[R::b(5, j)] = dt * (im * dirz);
+      }
+      const float w = q * sphi + r * cphi, v = q * cphi - r * sphi;
+      row[R::a(6, 6)] = 1.f + dt * (v * tth);
+      row[R::a(6, 7)] = dt * (w * sec * sec);
+      row[R::a(6, 10)] = dt * (sphi * tth);
+      row[R::a(6, 11)] = dt * (cphi * tth);
+      row[R::a(7, 6)] = dt * (-w);
+      row[R::a(7, 10)] = dt * cphi;
+      row[R::a(7, 11)] = dt * (-sphi);
+      row[R::a(8, 6)] = dt * (v * sec);
+      row[R::a(8, 7)] = dt * (w * sth * sec * sec);
+      row[R::a(8, 10)] = dt * (sphi * sec);
+      row[R::a(8, 11)] = dt * (cphi * sec);
+      row[R::a(9, 10)] = dt * (c1 * r);
+      row[R::a(9, 11)] = dt * (c1 * q);
+      row[R::a(10, 9)] = dt * (c2 * r);
+      row[R::a(10, 11)] = dt * (c2 * pp);
+      row[R::a(11, 9)] = dt * (c3 * q);
+      row[R::a(11, 10)] = dt * (c3 * pp);
+      float dx[n], gx[n], gu[m], bg[m], bh[m];
+#pragma unroll
+      for (int i = 0; i < n; ++i) dx[i] = xs[i] - float(p.x_ref[i]);
+      quad_grad<float, n>(p.Q, dx, p.diag_cost, gx);
+      quad_grad<float, m>(p.R, us, p.diag_cost, gu);
+      Mdl::barrier_d<float>(us, p, bg, bh);
+#pragma unroll
+      for (int i = 0; i < n; ++i) row[R::lx + i] = gx[i];
+#pragma unroll
+      for (int j = 0; j < m; ++j) row[R::lu + j] = gu[j] + bg[j];
+      *reinterpret_cast<float4*>(bh_s[lane]) = make_float4(bh[0], bh[1], bh[2], bh[3]);
+    }
+    __syncwarp();
+    float4* out4 = reinterpret_cast<float4*>(expansion + ((size_t)t * B + b0) * R::size);
+    for (int rr = 0; rr < 32; ++rr) {
+      if (!((live >> rr) & 1u)) continue;
+      const float4* src = &stage4[rr * PITCH4];
+      float4* dst = out4 + (size_t)rr * (R::size / 4);
+      dst[lane] = src[lane];
+      if (lane < 20) dst[32 + lane] = src[32 + lane];
+      // second half: template + this record's barrier curvature on the l_uu diagonal
+      float4 v1 = tmpl1;
+      if (lane >= 4 && lane < 8) {             // float4 #(36 + a) holds l_uu[a][0..3]
+        const int a = lane - 4;
+        const float add = bh_s[rr][a];
+        if (a == 0) v1.x += add; else if (a == 1) v1.y += add; else if (a == 2) v1.z += add; else v1.w += add;
+      }
+      dst[HALF / 4 + lane] = tmpl0;
+      if (lane < 20) dst[HALF / 4 + 32 + lane] = v1;
+    }
+    __syncwarp();
+  }
+  if (t_hi == N) {   // terminal V_x, V_xx at x_N
+    if (mine) {
+      float xs[n];
+#pragma unroll
+      for (int i = 0; i < n; ++i) xs[i] = float(x[((size_t)N * n + i) * B + b]);
+      emit_terminal<Mdl>(xs, p, StageSink{row});
+    }
+    __syncwarp();
+    for (int rr = 0; rr < 32; ++rr) {
+      if (!((live >> rr) & 1u)) continue;
+      const float* src = reinterpret_cast<const float*>(&stage4[rr * PITCH4]);
+      float* dst = terminal + (size_t)(b0 + rr) * R::term;
+      for (int e = lane; e < R::term; e += 32) dst[e] = src[e];
+    }
+  }
+}
+
 }  // namespace qx
 
 extern "C" int qx_linearize(const QxParams* p, const double* x, const double* u, float* expansion, float* terminal,
@@ -249,10 +406,10 @@ extern "C" int qx_linearize(const QxParams* p, const double* x, const double* u,
     }
     case QX_MODEL_QUADROTOR: {
       dim3 grid(qx::ceil_div(B, 32 * qx::kLinWarps), T);
-      if (p->integrator == QX_EULER)
-        qx::linearize_rec_kernel<qx::Quadrotor, QX_EULER><<<grid, 32 * qx::kLinWarps, 0, st>>>(*p, x, u, expansion, terminal,
-                                                                                             status, B, N, t_start);
-      else
+      if (p->integrator == QX_EULER) {
+        dim3 g2(qx::ceil_div(B, 32), qx::ceil_div(T, qx::kLinSteps));
+        qx::linearize_quad_euler_kernel<<<g2, 32, 0, st>>>(*p, x, u, expansion, terminal, status, B, N, t_start);
+      } else
         qx::linearize_rec_kernel<qx::Quadrotor, QX_RK4><<<grid, 32 * qx::kLinWarps, 0, st>>>(*p, x, u, expansion, terminal,
                                                                                            status, B, N, t_start);
       QX_CHECK_LAUNCH("linearize_rec_kernel");
