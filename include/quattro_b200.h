@@ -130,6 +130,11 @@ int qx_linesearch(const QxParams* p, double* x_in, double* u_in, const float* ga
                   int32_t* status, int32_t* iters, int32_t* alpha, double* x_out, double* u_out,
                   int32_t* n_active, double tol, uint32_t flags, int B, int N, void* stream);
 
+/* forward_pass with a caller-chosen alpha (quattro_ilqr_tf.py:377-390): candidate trajectory and its
+ * total cost for every trajectory, no accept test.  (x_in,u_in) is the nominal, gains as above. */
+int qx_forward_pass(const QxParams* p, const double* x_in, const double* u_in, const float* gains, double alpha,
+                    double* x_out, double* u_out, double* cost_out, int B, int N, void* stream);
+
 /* ---- Quattro transformer: TransformerILQR.predict for a batch (transformer_ilqr.py:311-325,
  * transformer_model.py:122-138) fused with the prompt pack / prediction unpack of optimize
  * (quattro_ilqr_tf.py:496-518).  Weights are one packed float buffer laid out by

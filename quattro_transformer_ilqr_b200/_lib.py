@@ -50,6 +50,7 @@ SIGNATURES = {
     "qx_riccati": (C.c_int, [C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "qx_linesearch": (C.c_int, [C.POINTER(QxParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_uint32,
                                 C.c_int, C.c_int, _P]),
+    "qx_forward_pass": (C.c_int, [C.POINTER(QxParams), _P, _P, _P, C.c_double, _P, _P, _P, C.c_int, C.c_int, _P]),
     "qx_tf_weight_floats": (C.c_size_t, [C.POINTER(QxTfConfig)]),
     "qx_tf_workspace_bytes": (C.c_size_t, [C.POINTER(QxTfConfig), C.c_int]),
     "qx_tf_split_floats": (C.c_size_t, [C.POINTER(QxTfConfig)]),

@@ -221,9 +221,10 @@ riccati_soa_kernel(const float* __restrict__ expansion, const float* __restrict_
 //
 // Lane roles inside a half-warp (hl = lane & 15, ri = hl >> 2, cj = hl & 3):
 //   phase 1  W = V F (12x16): 3x4 tile (rows 3ri.., cols 4cj..); V is kept in a padded
-//            "p4" layout  Vp[l][4*(i/3) + i%3]  so the three V values are one 16-B load;
-//            every lane also accumulates q[hl] = [l_x|l_u][hl] + sum_l F[l][hl] V_x[l]
-//   phase 2  Q = L + F^T W (16x16): 4x4 tile (rows 4ri.., cols 4cj..), two 16-B loads per 16 FMAs
+//            "p4" layout  Vp[l][4*(i/3) + i%3]  so the three V values are one 16-B load; the spare
+//            slot of row group 3 carries V_x, which yields q = [l_x|l_u] + F^T V_x for free
+//   phase 2  Q = L + F^T W (16x16) on the TRANSPOSED 4x4 tile (rows 4cj.., cols 4ri..): its F
+//            operand is the one phase 1 already holds in registers
 //   phase 3  lane hl < 12 solves column hl of K, lane 12 solves k (no-pivot elimination of the
 //            SPD matrix, pivoted fallback if a pivot is not positive)
 //   phase 4  V' = Q_xx + K^T (Q_uu K + Q_ux) + Q_ux^T K on the nine Q_xx tile lanes
@@ -232,7 +233,7 @@ constexpr int kRicStages = 2;
 constexpr int kRicWarps = 4;
 
 struct RicSmem {                               // per trajectory
-  alignas(128) float rec[kRicStages][416];   // expansion records (bulk-copy destinations)
+  alignas(64) float rec[kRicStages][416];    // expansion records (bulk-copy destinations)
   alignas(16) float Vp[12 * 16];             // V_xx, p4 layout
   alignas(16) float W[12 * 16];              // V F; reused for the un-symmetrised V_xx' (pitch 12)
   alignas(16) float Qb[4 * 16];              // rows 12..15 of Q: [Q_ux | Q_uu]
@@ -242,7 +243,9 @@ struct RicSmem {                               // per trajectory
   alignas(16) float q[16];                   // [Q_x | Q_u]
   alignas(16) float kh[8];                   // [k | Q_uu k + Q_u]
   alignas(8) uint64_t bar[kRicStages];
-};
+  float pad_[29];                            // sizeof == 64 (mod 128): the two half-warps of a warp work on
+};                                           // structs 16 banks apart, so their 32-bit accesses never collide
+static_assert(sizeof(RicSmem) % 128 == 64, "half-warp bank de-aliasing");
 
 __device__ __forceinline__ float fast_rcp(float x) {
   float r;
@@ -288,7 +291,7 @@ __device__ __noinline__ void solve_pp4_slow(const float (&Min)[4][4], float (&r)
   solve_pp<4>(M, r);
 }
 
-__global__ void __launch_bounds__(32 * kRicWarps)
+__global__ void __launch_bounds__(32 * kRicWarps, 4)
 riccati_warp_kernel(const float* __restrict__ expansion, const float* __restrict__ terminal,
                     float* __restrict__ gains, const int32_t* __restrict__ status, int B, int N, int t_start,
                     float reg) {
@@ -328,7 +331,7 @@ riccati_warp_kernel(const float* __restrict__ expansion, const float* __restrict
     for (int e = hl; e < R::term; e += 16) {
       const float v = tm[e];
       if (e < n) {
-        s.Vx[e] = v;
+        s.Vp[e * 16 + 15] = v;            // V_x rides in the spare slot of row group 3
       } else {
         const int i = (e - n) / n, j = (e - n) % n;
         s.Vp[i * 16 + 4 * (j / 3) + (j % 3)] = v;
@@ -345,55 +348,66 @@ riccati_warp_kernel(const float* __restrict__ expansion, const float* __restrict
     const float* rec = s.rec[k % kRicStages];
     const float* F = rec + R::F;
 
-    // ---- phase 1: W = V F on 3x4 tiles; q = l + F^T V_x ------------------------------------------
+    // ---- phase 1: [W; q^T] = [V; V_x^T] F on 3x4 (+1) tiles -------------------------------------------
+    // The p4 layout has a spare 4th slot per row group; slot 3 of group 3 carries V_x, so the lanes
+    // with ri == 3 get q[4cj..4cj+3] = [l_x|l_u] + F^T V_x for free.  The lane's four F columns are
+    // kept in registers: phase 2 uses the transposed tile (rows 4cj.., cols 4ri..) and needs the same.
+    float4 fc[n];
     {
-      float acc[3][4] = {};
-      float qv = rec[R::lx + hl];
+      float acc[4][4] = {};
 #pragma unroll
       for (int l = 0; l < n; ++l) {
-        const float4 a = *reinterpret_cast<const float4*>(&s.Vp[l * 16 + 4 * ri]);     // V[l][3ri..3ri+2]
+        const float4 a = *reinterpret_cast<const float4*>(&s.Vp[l * 16 + 4 * ri]);     // V[l][3ri..3ri+2], (V_x[l])
         const float4 f = *reinterpret_cast<const float4*>(F + l * 16 + 4 * cj);
+        fc[l] = f;
         acc[0][0] = fmaf(a.x, f.x, acc[0][0]); acc[0][1] = fmaf(a.x, f.y, acc[0][1]);
         acc[0][2] = fmaf(a.x, f.z, acc[0][2]); acc[0][3] = fmaf(a.x, f.w, acc[0][3]);
         acc[1][0] = fmaf(a.y, f.x, acc[1][0]); acc[1][1] = fmaf(a.y, f.y, acc[1][1]);
         acc[1][2] = fmaf(a.y, f.z, acc[1][2]); acc[1][3] = fmaf(a.y, f.w, acc[1][3]);
         acc[2][0] = fmaf(a.z, f.x, acc[2][0]); acc[2][1] = fmaf(a.z, f.y, acc[2][1]);
         acc[2][2] = fmaf(a.z, f.z, acc[2][2]); acc[2][3] = fmaf(a.z, f.w, acc[2][3]);
-        qv = fmaf(F[l * 16 + hl], s.Vx[l], qv);
+        acc[3][0] = fmaf(a.w, f.x, acc[3][0]); acc[3][1] = fmaf(a.w, f.y, acc[3][1]);
+        acc[3][2] = fmaf(a.w, f.z, acc[3][2]); acc[3][3] = fmaf(a.w, f.w, acc[3][3]);
       }
 #pragma unroll
       for (int r = 0; r < 3; ++r)
         *reinterpret_cast<float4*>(&s.W[(3 * ri + r) * 16 + 4 * cj]) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-      s.q[hl] = qv;
+      if (ri == 3) {
+        const float4 lq = *reinterpret_cast<const float4*>(rec + R::lx + 4 * cj);
+        *reinterpret_cast<float4*>(&s.q[4 * cj]) = make_float4(lq.x + acc[3][0], lq.y + acc[3][1], lq.z + acc[3][2], lq.w + acc[3][3]);
+      }
     }
     __syncwarp();
 
-    // ---- phase 2: Q = L + F^T W on 4x4 tiles -------------------------------------------------------
+    // ---- phase 2: Q = L + F^T W on TRANSPOSED 4x4 tiles: rows 4cj.., cols 4ri.. -----------------------------
     float Q[4][4];
     {
-      // cost Hessian block of this tile (the Q_xu tile, ri < 3 && cj == 3, is never used)
-      const float* lsrc = (ri < 3) ? (rec + R::lxx + (4 * ri) * n + 4 * cj)
-                                   : ((cj < 3) ? (rec + R::lux + 4 * cj) : (rec + R::luu));
-      const int lstride = (ri < 3 || cj < 3) ? n : m;
-      const bool have_l = !(ri < 3 && cj == 3);
+      // cost Hessian block of this tile (the Q_xu tile, cj < 3 && ri == 3, is never used)
+      const float* lsrc = (cj < 3) ? (rec + R::lxx + (4 * cj) * n + 4 * ri)
+                                   : ((ri < 3) ? (rec + R::lux + 4 * ri) : (rec + R::luu));
+      const int lstride = (cj < 3 || ri < 3) ? n : m;
+      const bool have_l = !(cj < 3 && ri == 3);
+      // two predicated rounds: row groups cj == 0 and cj == 2 of l_xx are 96 words apart (same banks)
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        const float4 v = have_l ? *reinterpret_cast<const float4*>(lsrc + r * lstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (have_l && cj != 2) v = *reinterpret_cast<const float4*>(lsrc + r * lstride);
+        if (have_l && cj == 2) v = *reinterpret_cast<const float4*>(lsrc + r * lstride);
         Q[r][0] = v.x; Q[r][1] = v.y; Q[r][2] = v.z; Q[r][3] = v.w;
       }
 #pragma unroll
       for (int l = 0; l < n; ++l) {
-        const float4 a = *reinterpret_cast<const float4*>(F + l * 16 + 4 * ri);
-        const float4 w = *reinterpret_cast<const float4*>(&s.W[l * 16 + 4 * cj]);
+        const float4 a = fc[l];
+        const float4 w = *reinterpret_cast<const float4*>(&s.W[l * 16 + 4 * ri]);
         Q[0][0] = fmaf(a.x, w.x, Q[0][0]); Q[0][1] = fmaf(a.x, w.y, Q[0][1]); Q[0][2] = fmaf(a.x, w.z, Q[0][2]); Q[0][3] = fmaf(a.x, w.w, Q[0][3]);
         Q[1][0] = fmaf(a.y, w.x, Q[1][0]); Q[1][1] = fmaf(a.y, w.y, Q[1][1]); Q[1][2] = fmaf(a.y, w.z, Q[1][2]); Q[1][3] = fmaf(a.y, w.w, Q[1][3]);
         Q[2][0] = fmaf(a.z, w.x, Q[2][0]); Q[2][1] = fmaf(a.z, w.y, Q[2][1]); Q[2][2] = fmaf(a.z, w.z, Q[2][2]); Q[2][3] = fmaf(a.z, w.w, Q[2][3]);
         Q[3][0] = fmaf(a.w, w.x, Q[3][0]); Q[3][1] = fmaf(a.w, w.y, Q[3][1]); Q[3][2] = fmaf(a.w, w.z, Q[3][2]); Q[3][3] = fmaf(a.w, w.w, Q[3][3]);
       }
-      if (ri == 3) {
+      if (cj == 3) {
 #pragma unroll
         for (int r = 0; r < 4; ++r)
-          *reinterpret_cast<float4*>(&s.Qb[r * 16 + 4 * cj]) = make_float4(Q[r][0], Q[r][1], Q[r][2], Q[r][3]);
+          *reinterpret_cast<float4*>(&s.Qb[r * 16 + 4 * ri]) = make_float4(Q[r][0], Q[r][1], Q[r][2], Q[r][3]);
       }
     }
     __syncwarp();
@@ -452,13 +466,13 @@ riccati_warp_kernel(const float* __restrict__ expansion, const float* __restrict
     __syncwarp();
 
     // ---- phase 4: V_xx' = Q_xx + K^T (Q_uu K + Q_ux) + Q_ux^T K ;  V_x' ----------------------------
-    if (ri < 3 && cj < 3) {
+    if (ri < 3 && cj < 3) {           // this lane holds Q_xx rows 4cj.., cols 4ri..
 #pragma unroll
       for (int a = 0; a < m; ++a) {
-        const float4 ka = *reinterpret_cast<const float4*>(&s.Ks[a * n + 4 * ri]);
-        const float4 mb = *reinterpret_cast<const float4*>(&s.Ms[a * n + 4 * cj]);
-        const float4 qa = *reinterpret_cast<const float4*>(&s.Qb[a * 16 + 4 * ri]);
-        const float4 kb = *reinterpret_cast<const float4*>(&s.Ks[a * n + 4 * cj]);
+        const float4 ka = *reinterpret_cast<const float4*>(&s.Ks[a * n + 4 * cj]);
+        const float4 mb = *reinterpret_cast<const float4*>(&s.Ms[a * n + 4 * ri]);
+        const float4 qa = *reinterpret_cast<const float4*>(&s.Qb[a * 16 + 4 * cj]);
+        const float4 kb = *reinterpret_cast<const float4*>(&s.Ks[a * n + 4 * ri]);
         const float kar[4] = {ka.x, ka.y, ka.z, ka.w}, qar[4] = {qa.x, qa.y, qa.z, qa.w};
         const float mbc[4] = {mb.x, mb.y, mb.z, mb.w}, kbc[4] = {kb.x, kb.y, kb.z, kb.w};
 #pragma unroll
@@ -468,7 +482,7 @@ riccati_warp_kernel(const float* __restrict__ expansion, const float* __restrict
       }
 #pragma unroll
       for (int r = 0; r < 4; ++r)    // un-symmetrised V_xx' -> W buffer, pitch 12
-        *reinterpret_cast<float4*>(&s.W[(4 * ri + r) * n + 4 * cj]) = make_float4(Q[r][0], Q[r][1], Q[r][2], Q[r][3]);
+        *reinterpret_cast<float4*>(&s.W[(4 * cj + r) * n + 4 * ri]) = make_float4(Q[r][0], Q[r][1], Q[r][2], Q[r][3]);
     }
     float vx_new = 0.f;
     if (hl < n) {
@@ -477,7 +491,7 @@ riccati_warp_kernel(const float* __restrict__ expansion, const float* __restrict
       for (int a = 0; a < m; ++a) vx_new += s.Ks[a * n + hl] * s.kh[m + a] + s.Qb[a * 16 + hl] * s.kh[a];
     }
     __syncwarp();
-    if (hl < n) s.Vx[hl] = vx_new;
+    if (hl < n) s.Vp[hl * 16 + 15] = vx_new;
 
     // ---- phase 5: V = (V' + V'^T) / 2 into the p4 layout: item (i, g) = V[i][3g..3g+2] -----------------
 #pragma unroll
@@ -486,8 +500,10 @@ riccati_warp_kernel(const float* __restrict__ expansion, const float* __restrict
       const int i = item >> 2, g = item & 3;
       const float* vr = &s.W[i * n + 3 * g];
       const float* vc = &s.W[(3 * g) * n + i];
-      const float4 o = make_float4(0.5f * (vr[0] + vc[0]), 0.5f * (vr[1] + vc[n]), 0.5f * (vr[2] + vc[2 * n]), 0.f);
-      *reinterpret_cast<float4*>(&s.Vp[i * 16 + 4 * g]) = o;
+      float* dst = &s.Vp[i * 16 + 4 * g];      // slot 3 of group 3 holds V_x: leave the 4th word alone
+      dst[0] = 0.5f * (vr[0] + vc[0]);
+      dst[1] = 0.5f * (vr[1] + vc[n]);
+      dst[2] = 0.5f * (vr[2] + vc[2 * n]);
     }
     __syncwarp();
   }

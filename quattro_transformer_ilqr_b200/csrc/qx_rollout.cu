@@ -496,6 +496,48 @@ linesearch_quad4_kernel(const __grid_constant__ QxParams p, double* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
+// One candidate rollout with a caller-chosen alpha: iLQR_TF.forward_pass (quattro_ilqr_tf.py:377-390)
+// as a stand-alone entry point (API completeness; the solver itself uses the fused line search).
+template <class Mdl>
+__global__ void __launch_bounds__(128)
+forward_pass_kernel(const __grid_constant__ QxParams p, const double* __restrict__ x_in, const double* __restrict__ u_in,
+                    const float* __restrict__ gains, double alpha, double* __restrict__ x_out,
+                    double* __restrict__ u_out, double* __restrict__ cost_out, int B, int N) {
+  constexpr int n = Mdl::n, m = Mdl::m, G = Rec<n, m>::gain;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double xh[n], xn[n], uh[m], xnext[n];
+#pragma unroll
+  for (int i = 0; i < n; ++i) xh[i] = x_in[(size_t)i * B + b];
+  double c = 0.0;
+  for (int t = 0; t < N; ++t) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) xn[i] = x_in[((size_t)t * n + i) * B + b];
+#pragma unroll
+    for (int j = 0; j < m; ++j) {
+      auto gv = [&](int q) {
+        return (double)((Mdl::layout == QX_LAYOUT_REC) ? gains[((size_t)t * B + b) * G + q]
+                                                       : gains[((size_t)t * G + q) * B + b]);
+      };
+      double kd = 0.0;
+#pragma unroll
+      for (int i = 0; i < n; ++i) kd += gv(m + j * n + i) * (xh[i] - xn[i]);
+      uh[j] = u_in[((size_t)t * m + j) * B + b] + alpha * (gv(j) + kd);
+      u_out[((size_t)t * m + j) * B + b] = uh[j];
+    }
+#pragma unroll
+    for (int i = 0; i < n; ++i) x_out[((size_t)t * n + i) * B + b] = xh[i];
+    c += running_cost<Mdl, double>(xh, uh, p);
+    discrete_step<Mdl, double>(xh, uh, p, xnext);
+#pragma unroll
+    for (int i = 0; i < n; ++i) xh[i] = xnext[i];
+  }
+#pragma unroll
+  for (int i = 0; i < n; ++i) x_out[((size_t)N * n + i) * B + b] = xh[i];
+  cost_out[b] = c + final_cost<Mdl, double>(xh, p);
+}
+
+// ------------------------------------------------------------------------------------------
 template <class Mdl>
 static int launch_rollout(const QxParams* p, const double* x0, const double* u, double* x, double* cost,
                           const int32_t* status, int B, int N, cudaStream_t st) {
@@ -560,4 +602,28 @@ extern "C" int qx_linesearch(const QxParams* p, double* x_in, double* u_in, cons
   }
   qx::set_error("unknown model_id %d", p->model_id);
   return QX_EINVAL;
+}
+
+extern "C" int qx_forward_pass(const QxParams* p, const double* x_in, const double* u_in, const float* gains,
+                               double alpha, double* x_out, double* u_out, double* cost_out, int B, int N,
+                               void* stream) {
+  QX_CHECK_ARG(p && x_in && u_in && gains && x_out && u_out && cost_out, "null pointer");
+  QX_CHECK_ARG(B > 0 && N > 0, "B and N must be positive");
+  QX_CHECK_ARG(x_in != x_out && u_in != u_out, "in and out buffers must differ");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (p->model_id) {
+    case QX_MODEL_CARTPOLE:
+      qx::forward_pass_kernel<qx::CartPole><<<qx::ceil_div(B, 128), 128, 0, st>>>(*p, x_in, u_in, gains, alpha, x_out, u_out,
+                                                                                 cost_out, B, N);
+      break;
+    case QX_MODEL_QUADROTOR:
+      qx::forward_pass_kernel<qx::Quadrotor><<<qx::ceil_div(B, 128), 128, 0, st>>>(*p, x_in, u_in, gains, alpha, x_out, u_out,
+                                                                                  cost_out, B, N);
+      break;
+    default:
+      qx::set_error("unknown model_id %d", p->model_id);
+      return QX_EINVAL;
+  }
+  QX_CHECK_LAUNCH("forward_pass_kernel");
+  return QX_OK;
 }

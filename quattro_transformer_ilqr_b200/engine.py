@@ -111,6 +111,17 @@ class BatchedILQR:
         self.launches += 1
         self.cur = 1 - c
 
+    def forward_pass(self, alpha):
+        """Candidate rollout with step size `alpha` from the current nominal and gains; returns
+        (x (B,N+1,n), u (B,N,m), cost (B,)) tensors without touching the solver state."""
+        c = self.cur
+        cost = torch.empty_like(self.cost)
+        _lib.check(self.lib.qx_forward_pass(C.byref(self.params), _ptr(self.x[c]), _ptr(self.u[c]), _ptr(self.gains),
+                                            float(alpha), _ptr(self.x[1 - c]), _ptr(self.u[1 - c]), _ptr(cost),
+                                            self.B, self.N, self.stream), "qx_forward_pass")
+        self.launches += 1
+        return (self.x[1 - c].permute(2, 0, 1).contiguous(), self.u[1 - c].permute(2, 0, 1).contiguous(), cost)
+
     def backward(self):
         """Gains for the whole horizon: Riccati, or Riccati tail + transformer head."""
         if self.tf is None:

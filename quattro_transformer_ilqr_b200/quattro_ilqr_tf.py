@@ -218,10 +218,20 @@ class iLQR_TF:
         self.logs.append(entry)
 
     def forward_pass(self, x_seq, u_seq, k_seq, K_seq, alpha=1.0):
-        """One candidate rollout with the given gains (reference :377-390); B = 1 or batched."""
-        raise NotImplementedError(
-            "forward_pass with caller-supplied gains is fused into qx_linesearch; use optimize(), or "
-            "BatchedILQR.linesearch() on device-resident gains")
+        """One candidate rollout (reference :377-390): returns (new_x_seq, new_u_seq, total_cost).
+        ``x_seq`` is implied by ``u_seq`` and ``self.x0`` and is recomputed on the device."""
+        t0 = time.time()
+        x0, u = self._problem(u_seq)
+        B = x0.shape[0]
+        e = self._get_engine(B)
+        e.set_problem(x0, u)
+        K = np.asarray(K_seq, dtype=np.float32).reshape(B, self.horizon, e.m, e.n)
+        k = np.asarray(k_seq, dtype=np.float32).reshape(B, self.horizon, e.m)
+        e.load_gains(K, k)
+        xn, un, cost = e.forward_pass(alpha)
+        cost = cost.cpu().numpy()
+        self.forward_pass_time.append(time.time() - t0)
+        return self._out_x(xn), self._out_u(un), (cost if self._batched() else float(cost[0]))
 
     def get_time(self):
         if self.tf is not None:

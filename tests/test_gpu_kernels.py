@@ -136,6 +136,24 @@ def test_linesearch_decisions_and_candidates(system, B, us):
     assert torch.equal(e.u[0][:, :, fin], e.u[1][:, :, fin]) and torch.equal(e.x[0][:, :, fin], e.x[1][:, :, fin])
 
 
+@pytest.mark.parametrize("system,B,us", CASES)
+def test_forward_pass_entry_point(system, B, us):
+    """qx_forward_pass (iLQR_TF.forward_pass) for every alpha of the reference's list vs the oracle."""
+    x0, u = _problem(system, B, 9, 0.5 * us)
+    model = make_model(system)
+    x_ref, _ = ob.rollout(model, x0, u)
+    K, k = ob.riccati(ob.linearize(model, x_ref, u))
+    K, k = K.astype(np.float32), k.astype(np.float32)
+    e = _engine(system, B)
+    e.set_problem(x0, u)
+    e.load_gains(K, k)
+    for alpha in ob.ALPHAS:
+        xn, un, cn = ob.forward_pass(model, x_ref, u, K.astype(np.float64), k.astype(np.float64), alpha)
+        gx, gu, gc = e.forward_pass(alpha)
+        assert relmax(gc.cpu().numpy(), cn) < 1e-12 and relmax(gu.cpu().numpy(), un) < 1e-11
+        assert relmax(gx.cpu().numpy(), xn) < 1e-11
+
+
 def test_inactive_trajectories_are_untouched():
     x0, u = _problem("quadrotor", 70, 6, 0.5)
     e = _engine("quadrotor", 70)
