@@ -125,10 +125,14 @@ int qx_riccati(int model_id, const float* expansion, const float* terminal, floa
  * the reference's stopping rule (:472): finished iff no alpha accepted or |cost - new| < tol.
  * A trajectory that finishes has its final iterate in BOTH (x_in,u_in) and (x_out,u_out), so the
  * caller can ping-pong the buffers.  n_active (device int32, may be NULL) is incremented by the
- * number of trajectories still active afterwards. */
+ * number of trajectories still active afterwards.
+ * workspace (qx_linesearch_workspace_bytes(), may be NULL): with it, models that support it run the
+ * search in two phases - alpha = 1 for every trajectory, then the five remaining alphas of the rejected
+ * ones concurrently (candidates parked in the workspace) - instead of one alpha after the other. */
+size_t qx_linesearch_workspace_bytes(int model_id, int B, int N);
 int qx_linesearch(const QxParams* p, double* x_in, double* u_in, const float* gains, double* cost,
                   int32_t* status, int32_t* iters, int32_t* alpha, double* x_out, double* u_out,
-                  int32_t* n_active, double tol, uint32_t flags, int B, int N, void* stream);
+                  int32_t* n_active, void* workspace, double tol, uint32_t flags, int B, int N, void* stream);
 
 /* forward_pass with a caller-chosen alpha (quattro_ilqr_tf.py:377-390): candidate trajectory and its
  * total cost for every trajectory, no accept test.  (x_in,u_in) is the nominal, gains as above. */

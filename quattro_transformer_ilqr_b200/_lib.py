@@ -48,7 +48,8 @@ SIGNATURES = {
     "qx_rollout_cost": (C.c_int, [C.POINTER(QxParams), _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "qx_linearize": (C.c_int, [C.POINTER(QxParams), _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "qx_riccati": (C.c_int, [C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
-    "qx_linesearch": (C.c_int, [C.POINTER(QxParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_uint32,
+    "qx_linesearch_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "qx_linesearch": (C.c_int, [C.POINTER(QxParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_uint32,
                                 C.c_int, C.c_int, _P]),
     "qx_forward_pass": (C.c_int, [C.POINTER(QxParams), _P, _P, _P, C.c_double, _P, _P, _P, C.c_int, C.c_int, _P]),
     "qx_tf_weight_floats": (C.c_size_t, [C.POINTER(QxTfConfig)]),

@@ -364,132 +364,239 @@ rollout_quad4_kernel(const __grid_constant__ QxParams p, const double* __restric
   if (run && g == 0) cost[b] = c;
 }
 
+// Per-lane constants of the 4-lane scheme: this lane's share of the diagonal cost.
+struct Quad4Lane {
+  QuadConst k;
+  double qd[3], qfd[3], xr[3], rd;
+  int g, base;
+};
+__device__ __forceinline__ void quad4_lane_init(const QxParams& p, int lane, Quad4Lane& c) {
+  constexpr int n = 12, m = 4;
+  c.g = lane & 3;
+  c.base = lane & ~3;
+  quad_consts(p, c.k);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    c.qd[r] = p.Q[(3 * c.g + r) * n + 3 * c.g + r];
+    c.qfd[r] = p.Qf[(3 * c.g + r) * n + 3 * c.g + r];
+    c.xr[r] = p.x_ref[3 * c.g + r];
+  }
+  c.rd = p.R[c.g * m + c.g];
+}
+
+// One candidate rollout (forward_pass :377-390) by a 4-lane group: nominal and gains of trajectory
+// b_src, candidate written at column b_dst of (x_dst, u_dst) (both with row stride B).  All 32 lanes of
+// the warp must call it (shuffles); lanes with run == false only take part in the shuffles.
+// Returns the total cost (identical bits in the four lanes of a group).
+__device__ __forceinline__ double quad4_candidate(const QxParams& p, const Quad4Lane& c, bool run,
+                                                  const double* __restrict__ x_in, const double* __restrict__ u_in,
+                                                  const float* __restrict__ gains, int b_src, double alpha,
+                                                  double* __restrict__ x_dst, double* __restrict__ u_dst, int b_dst,
+                                                  int B, int N) {
+  constexpr int n = 12, m = 4, G = 52;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int g = c.g;
+  double xh[n], xnx[n], xn_nx[n], un_nx = 0.0;
+  float gk_nx = 0.f;
+  float4 gK_nx[3];
+#pragma unroll
+  for (int i = 0; i < n; ++i) xh[i] = run ? x_in[(size_t)i * B + b_src] : 0.0;
+  double cst = 0.0;
+  auto fetch = [&](int t) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) xn_nx[i] = x_in[((size_t)t * n + i) * B + b_src];
+    un_nx = u_in[((size_t)t * m + g) * B + b_src];
+    const float* rec = gains + ((size_t)t * B + b_src) * G;
+    gk_nx = rec[g];
+    const float4* row = reinterpret_cast<const float4*>(rec + m + g * n);
+    gK_nx[0] = row[0]; gK_nx[1] = row[1]; gK_nx[2] = row[2];
+  };
+  if (run) fetch(0);
+  for (int t = 0; t < N; ++t) {
+    double uh = 0.0;
+    if (run) {
+      double xn[n];
+#pragma unroll
+      for (int i = 0; i < n; ++i) xn[i] = xn_nx[i];
+      const double un = un_nx;
+      const float gk = gk_nx;
+      const float kr[12] = {gK_nx[0].x, gK_nx[0].y, gK_nx[0].z, gK_nx[0].w, gK_nx[1].x, gK_nx[1].y,
+                            gK_nx[1].z, gK_nx[1].w, gK_nx[2].x, gK_nx[2].y, gK_nx[2].z, gK_nx[2].w};
+      if (t + 1 < N) fetch(t + 1);
+      double kd = 0.0;
+#pragma unroll
+      for (int i = 0; i < n; ++i) kd += (double)kr[i] * (xh[i] - xn[i]);
+      uh = un + alpha * ((double)gk + kd);                 // alpha scales the feedback term too
+      u_dst[((size_t)t * m + g) * B + b_dst] = uh;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const double xv = (g == 0) ? xh[r] : (g == 1) ? xh[3 + r] : (g == 2) ? xh[6 + r] : xh[9 + r];
+        x_dst[((size_t)t * n + 3 * g + r) * B + b_dst] = xv;
+        const double dxv = xv - c.xr[r];
+        cst += c.qd[r] * dxv * dxv;
+      }
+      cst += c.rd * uh * uh + quad_barrier1(uh, c.k);
+    }
+    quad_step4(xh, uh, c.k, p.integrator, c.base, g, xnx);
+#pragma unroll
+    for (int i = 0; i < n; ++i) xh[i] = xnx[i];
+  }
+  if (run) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double xv = (g == 0) ? xh[r] : (g == 1) ? xh[3 + r] : (g == 2) ? xh[6 + r] : xh[9 + r];
+      x_dst[((size_t)N * n + 3 * g + r) * B + b_dst] = xv;
+      const double dxv = xv - c.xr[r];
+      cst += c.qfd[r] * dxv * dxv;
+    }
+  }
+  // group total (identical bits in the four lanes: the butterfly adds commute)
+  cst += __shfl_xor_sync(FULL, cst, 1);
+  cst += __shfl_xor_sync(FULL, cst, 2);
+  return cst;
+}
+
+// Bookkeeping after the line search of one trajectory (stopping rule :472), executed by its 4-lane group.
+// Leaves the next iterate in (x_out,u_out); a finished trajectory has it in both buffers.
+__device__ __forceinline__ bool quad4_finalize(int g, int b, int idx, double cur, double new_cost, double tol,
+                                               uint32_t flags, double* __restrict__ x_in, double* __restrict__ u_in,
+                                               double* __restrict__ x_out, double* __restrict__ u_out,
+                                               double* __restrict__ cost, int32_t* __restrict__ status,
+                                               int32_t* __restrict__ iters, int32_t* __restrict__ alpha_out, int B, int N) {
+  constexpr int n = 12, m = 4;
+  const bool found = idx >= 0;
+  bool done = (!found) || (fabs(cur - new_cost) < tol);
+  if (flags & QX_LS_FORCE_ACTIVE) done = false;
+  if (!found || done) {
+    // no alpha: (x_out,u_out) <- nominal;  finished with an update: (x_in,u_in) <- final iterate
+    const double* xs = found ? x_out : x_in;
+    const double* us = found ? u_out : u_in;
+    double* xd = found ? x_in : x_out;
+    double* ud = found ? u_in : u_out;
+    for (int t = 0; t <= N; ++t)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) xd[((size_t)t * n + 3 * g + r) * B + b] = xs[((size_t)t * n + 3 * g + r) * B + b];
+    for (int t = 0; t < N; ++t) ud[((size_t)t * m + g) * B + b] = us[((size_t)t * m + g) * B + b];
+  }
+  if (g == 0) {
+    cost[b] = new_cost;
+    alpha_out[b] = idx;
+    iters[b] += 1;
+    if (done) status[b] = 1;
+  }
+  return !done;
+}
+
+// Control block of the two-phase line search (device int32[4], zeroed by the caller before phase A).
+enum { kCtlActive = 0, kCtlQueue = 1 };
+
+// MODE 0: the whole alpha list sequentially with early exit (single launch).
+// MODE 1: phase A of the two-phase search: alpha = 1 only; rejected trajectories are queued.
+template <int MODE>
 __global__ void __launch_bounds__(128)
 linesearch_quad4_kernel(const __grid_constant__ QxParams p, double* __restrict__ x_in, double* __restrict__ u_in,
                         const float* __restrict__ gains, double* __restrict__ cost, int32_t* __restrict__ status,
                         int32_t* __restrict__ iters, int32_t* __restrict__ alpha_out, double* __restrict__ x_out,
-                        double* __restrict__ u_out, int32_t* __restrict__ n_active, double tol, uint32_t flags, int B,
-                        int N) {
-  constexpr int n = 12, m = 4, G = 52;
+                        double* __restrict__ u_out, int32_t* __restrict__ n_active, int32_t* __restrict__ queue,
+                        int32_t* __restrict__ ctl, double tol, uint32_t flags, int B, int N) {
   constexpr unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31, g = lane & 3, base = lane & ~3;
+  const int lane = threadIdx.x & 31;
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
   const bool mine = (b < B) && (status[b] == 0);
   if (!__any_sync(FULL, mine)) return;
-
-  QuadConst k;
-  quad_consts(p, k);
-  // this lane's share of the (diagonal) cost: state rows 3g..3g+2 and control g
-  double qd[3], qfd[3], xr[3];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    qd[r] = p.Q[(3 * g + r) * n + 3 * g + r];
-    qfd[r] = p.Qf[(3 * g + r) * n + 3 * g + r];
-    xr[r] = p.x_ref[3 * g + r];
-  }
-  const double rd = p.R[g * m + g];
-
+  Quad4Lane c;
+  quad4_lane_init(p, lane, c);
   const double cur = mine ? cost[b] : 0.0;
-  double x_first[n];
-#pragma unroll
-  for (int i = 0; i < n; ++i) x_first[i] = mine ? x_in[(size_t)i * B + b] : 0.0;
-
   bool accepted = !mine;
   int idx = -1;
   double new_cost = cur;
-
-  for (int a = 0; a < QX_NUM_ALPHA; ++a) {
+  constexpr int n_alpha = (MODE == 0) ? QX_NUM_ALPHA : 1;
+  for (int a = 0; a < n_alpha; ++a) {
     if (!__any_sync(FULL, !accepted)) break;
     const bool run = !accepted;
-    const double alpha = kAlphas[a];
-    double xh[n], xnx[n], xn_nx[n], un_nx = 0.0;
-    float gk_nx = 0.f;
-    float4 gK_nx[3];
-#pragma unroll
-    for (int i = 0; i < n; ++i) xh[i] = x_first[i];
-    double c = 0.0;
-    auto fetch = [&](int t) {
-#pragma unroll
-      for (int i = 0; i < n; ++i) xn_nx[i] = x_in[((size_t)t * n + i) * B + b];
-      un_nx = u_in[((size_t)t * m + g) * B + b];
-      const float* rec = gains + ((size_t)t * B + b) * G;
-      gk_nx = rec[g];
-      const float4* row = reinterpret_cast<const float4*>(rec + m + g * n);
-      gK_nx[0] = row[0]; gK_nx[1] = row[1]; gK_nx[2] = row[2];
-    };
-    if (run) fetch(0);
-    for (int t = 0; t < N; ++t) {
-      // lanes that are not running still take part in the shuffles of quad_step4 (no-ops on junk)
-      double uh = 0.0;
-      if (run) {
-        double xn[n];
-#pragma unroll
-        for (int i = 0; i < n; ++i) xn[i] = xn_nx[i];
-        const double un = un_nx;
-        const float gk = gk_nx;
-        const float kr[12] = {gK_nx[0].x, gK_nx[0].y, gK_nx[0].z, gK_nx[0].w, gK_nx[1].x, gK_nx[1].y,
-                              gK_nx[1].z, gK_nx[1].w, gK_nx[2].x, gK_nx[2].y, gK_nx[2].z, gK_nx[2].w};
-        if (t + 1 < N) fetch(t + 1);
-        double kd = 0.0;
-#pragma unroll
-        for (int i = 0; i < n; ++i) kd += (double)kr[i] * (xh[i] - xn[i]);
-        uh = un + alpha * ((double)gk + kd);                 // alpha scales the feedback term too
-        u_out[((size_t)t * m + g) * B + b] = uh;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const double xv = (g == 0) ? xh[r] : (g == 1) ? xh[3 + r] : (g == 2) ? xh[6 + r] : xh[9 + r];
-          x_out[((size_t)t * n + 3 * g + r) * B + b] = xv;
-          const double dxv = xv - xr[r];
-          c += qd[r] * dxv * dxv;
-        }
-        c += rd * uh * uh + quad_barrier1(uh, k);
-      }
-      quad_step4(xh, uh, k, p.integrator, base, g, xnx);
-#pragma unroll
-      for (int i = 0; i < n; ++i) xh[i] = xnx[i];
-    }
-    if (run) {
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const double xv = (g == 0) ? xh[r] : (g == 1) ? xh[3 + r] : (g == 2) ? xh[6 + r] : xh[9 + r];
-        x_out[((size_t)N * n + 3 * g + r) * B + b] = xv;
-        const double dxv = xv - xr[r];
-        c += qfd[r] * dxv * dxv;
-      }
-    }
-    // group total (identical bits in the four lanes: the butterfly adds commute)
-    c += __shfl_xor_sync(FULL, c, 1);
-    c += __shfl_xor_sync(FULL, c, 2);
-    if (run && c <= cur) {         // first accepted alpha, "<=" (quattro_ilqr_tf.py:444)
+    const double cst = quad4_candidate(p, c, run, x_in, u_in, gains, b, kAlphas[a], x_out, u_out, b, B, N);
+    if (run && cst <= cur) {       // first accepted alpha, "<=" (quattro_ilqr_tf.py:444)
       accepted = true;
       idx = a;
-      new_cost = c;
+      new_cost = cst;
     }
   }
-
   bool still_active = false;
   if (mine) {
-    const bool found = idx >= 0;
-    bool done = (!found) || (fabs(cur - new_cost) < tol);        // quattro_ilqr_tf.py:472
-    if (flags & QX_LS_FORCE_ACTIVE) done = false;
-    if (!found || done) {
-      // no alpha: (x_out,u_out) <- nominal;  finished with an update: (x_in,u_in) <- final iterate
-      const double* xs = found ? x_out : x_in;
-      const double* us = found ? u_out : u_in;
-      double* xd = found ? x_in : x_out;
-      double* ud = found ? u_in : u_out;
+    if (MODE == 1 && idx < 0) {
+      if (c.g == 0) queue[atomicAdd(&ctl[kCtlQueue], 1)] = b;      // phase B tries the other alphas in parallel
+    } else {
+      still_active = quad4_finalize(c.g, b, idx, cur, new_cost, tol, flags, x_in, u_in, x_out, u_out, cost, status,
+                                    iters, alpha_out, B, N) && c.g == 0;
+    }
+  }
+  const unsigned act = __ballot_sync(FULL, still_active);
+  if (lane == 0 && n_active != nullptr && act != 0u) atomicAdd(n_active, __popc(act));
+}
+
+// Phase B: every queued trajectory x every remaining alpha is one 4-lane work item (alpha-major, so the
+// eight groups of a warp share the alpha and write eight consecutive scratch columns).
+__global__ void __launch_bounds__(128)
+linesearch_quad4_phaseB_kernel(const __grid_constant__ QxParams p, const double* __restrict__ x_in,
+                               const double* __restrict__ u_in, const float* __restrict__ gains,
+                               const int32_t* __restrict__ queue, const int32_t* __restrict__ ctl,
+                               double* __restrict__ xs, double* __restrict__ us, double* __restrict__ cand_cost, int B,
+                               int N) {
+  constexpr int n = 12, m = 4;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int nrej = ctl[kCtlQueue];
+  const long item = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const bool run = item < (long)(QX_NUM_ALPHA - 1) * nrej;
+  if (!__any_sync(FULL, run)) return;
+  Quad4Lane c;
+  quad4_lane_init(p, lane, c);
+  const int a = run ? (int)(item / nrej) : 0;            // 0..4 -> alpha index a + 1
+  const int slot = run ? (int)(item % nrej) : 0;
+  const int b = run ? queue[slot] : 0;
+  double* xd = xs + (size_t)a * (N + 1) * n * B;
+  double* ud = us + (size_t)a * N * m * B;
+  const double cst = quad4_candidate(p, c, run, x_in, u_in, gains, b, kAlphas[a + 1], xd, ud, slot, B, N);
+  if (run && c.g == 0) cand_cost[(size_t)a * B + slot] = cst;
+}
+
+// Phase C: first accepted alpha per queued trajectory, copy its candidate out of the scratch, bookkeeping.
+__global__ void __launch_bounds__(128)
+linesearch_quad4_phaseC_kernel(double* __restrict__ x_in, double* __restrict__ u_in, double* __restrict__ cost,
+                               int32_t* __restrict__ status, int32_t* __restrict__ iters,
+                               int32_t* __restrict__ alpha_out, double* __restrict__ x_out, double* __restrict__ u_out,
+                               int32_t* __restrict__ n_active, const int32_t* __restrict__ queue,
+                               const int32_t* __restrict__ ctl, const double* __restrict__ xs,
+                               const double* __restrict__ us, const double* __restrict__ cand_cost, double tol,
+                               uint32_t flags, int B, int N) {
+  constexpr int n = 12, m = 4;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, g = lane & 3;
+  const int nrej = ctl[kCtlQueue];
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const bool mine = slot < nrej;
+  if (!__any_sync(FULL, mine)) return;
+  bool still_active = false;
+  if (mine) {
+    const int b = queue[slot];
+    const double cur = cost[b];
+    int idx = -1;
+    double new_cost = cur;
+    for (int a = 0; a < QX_NUM_ALPHA - 1; ++a) {
+      const double cc = cand_cost[(size_t)a * B + slot];
+      if (cc <= cur) { idx = a + 1; new_cost = cc; break; }
+    }
+    if (idx > 0) {
+      const double* xsrc = xs + (size_t)(idx - 1) * (N + 1) * n * B;
+      const double* usrc = us + (size_t)(idx - 1) * N * m * B;
       for (int t = 0; t <= N; ++t)
 #pragma unroll
-        for (int r = 0; r < 3; ++r) xd[((size_t)t * n + 3 * g + r) * B + b] = xs[((size_t)t * n + 3 * g + r) * B + b];
-      for (int t = 0; t < N; ++t) ud[((size_t)t * m + g) * B + b] = us[((size_t)t * m + g) * B + b];
+        for (int r = 0; r < 3; ++r)
+          x_out[((size_t)t * n + 3 * g + r) * B + b] = xsrc[((size_t)t * n + 3 * g + r) * B + slot];
+      for (int t = 0; t < N; ++t) u_out[((size_t)t * m + g) * B + b] = usrc[((size_t)t * m + g) * B + slot];
     }
-    if (g == 0) {
-      cost[b] = new_cost;
-      alpha_out[b] = idx;
-      iters[b] += 1;
-      if (done) status[b] = 1;
-    }
-    still_active = !done && g == 0;
+    still_active = quad4_finalize(g, b, idx, cur, new_cost, tol, flags, x_in, u_in, x_out, u_out, cost, status, iters,
+                                  alpha_out, B, N) && g == 0;
   }
   const unsigned act = __ballot_sync(FULL, still_active);
   if (lane == 0 && n_active != nullptr && act != 0u) atomicAdd(n_active, __popc(act));
@@ -578,9 +685,18 @@ extern "C" int qx_rollout_cost(const QxParams* p, const double* x0, const double
   return QX_EINVAL;
 }
 
+extern "C" size_t qx_linesearch_workspace_bytes(int model_id, int B, int N) {
+  if (model_id != QX_MODEL_QUADROTOR || B <= 0 || N <= 0) return 0;
+  constexpr size_t n = 12, m = 4, A = QX_NUM_ALPHA - 1;
+  // [ctl int32[4] | queue int32[B] (padded to 16 B) | cand_cost double[5][B] | xs double[5][N+1][n][B] | us double[5][N][m][B]]
+  const size_t qbytes = ((size_t)B * 4 + 15) / 16 * 16;
+  return 16 + qbytes + A * B * 8 + A * ((size_t)(N + 1) * n + (size_t)N * m) * B * 8;
+}
+
 extern "C" int qx_linesearch(const QxParams* p, double* x_in, double* u_in, const float* gains, double* cost,
                              int32_t* status, int32_t* iters, int32_t* alpha, double* x_out, double* u_out,
-                             int32_t* n_active, double tol, uint32_t flags, int B, int N, void* stream) {
+                             int32_t* n_active, void* workspace, double tol, uint32_t flags, int B, int N,
+                             void* stream) {
   QX_CHECK_ARG(p && x_in && u_in && gains && cost && status && iters && alpha && x_out && u_out, "null pointer");
   QX_CHECK_ARG(B > 0 && N > 0, "B and N must be positive");
   QX_CHECK_ARG(x_in != x_out && u_in != u_out, "in and out buffers must differ");
@@ -590,15 +706,40 @@ extern "C" int qx_linesearch(const QxParams* p, double* x_in, double* u_in, cons
     case QX_MODEL_CARTPOLE:
       return qx::launch_linesearch<qx::CartPole>(p, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out,
                                                  n_active, tol, flags, B, N, st);
-    case QX_MODEL_QUADROTOR:
-      if (p->diag_cost) {
-        qx::linesearch_quad4_kernel<<<qx::ceil_div(4 * B, 128), 128, 0, st>>>(*p, x_in, u_in, gains, cost, status, iters,
-                                                                             alpha, x_out, u_out, n_active, tol, flags, B, N);
+    case QX_MODEL_QUADROTOR: {
+      if (!p->diag_cost)
+        return qx::launch_linesearch<qx::Quadrotor>(p, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out,
+                                                    n_active, tol, flags, B, N, st);
+      const int grid = qx::ceil_div(4 * B, 128);
+      if (workspace == nullptr) {   // single launch, alphas tried one after the other
+        qx::linesearch_quad4_kernel<0><<<grid, 128, 0, st>>>(*p, x_in, u_in, gains, cost, status, iters, alpha, x_out,
+                                                             u_out, n_active, nullptr, nullptr, tol, flags, B, N);
         QX_CHECK_LAUNCH("linesearch_quad4_kernel");
         return QX_OK;
       }
-      return qx::launch_linesearch<qx::Quadrotor>(p, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out,
-                                                  n_active, tol, flags, B, N, st);
+      // two-phase: alpha = 1 for everybody, then the remaining alphas of the rejected ones in parallel
+      QX_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, "workspace must be 16-byte aligned");
+      constexpr size_t n = 12, m = 4, A = QX_NUM_ALPHA - 1;
+      uint8_t* w = static_cast<uint8_t*>(workspace);
+      int32_t* ctl = reinterpret_cast<int32_t*>(w);
+      int32_t* queue = reinterpret_cast<int32_t*>(w + 16);
+      const size_t qbytes = ((size_t)B * 4 + 15) / 16 * 16;
+      double* cand = reinterpret_cast<double*>(w + 16 + qbytes);
+      double* xs = cand + A * B;
+      double* us = xs + A * (size_t)(N + 1) * n * B;
+      cudaError_t e = cudaMemsetAsync(ctl, 0, 16, st);
+      if (e != cudaSuccess) return qx::cuda_fail(e, "cudaMemsetAsync(ctl)");
+      qx::linesearch_quad4_kernel<1><<<grid, 128, 0, st>>>(*p, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out,
+                                                           n_active, queue, ctl, tol, flags, B, N);
+      QX_CHECK_LAUNCH("linesearch_quad4_kernel<phase A>");
+      qx::linesearch_quad4_phaseB_kernel<<<qx::ceil_div((int)(4 * A) * B, 128), 128, 0, st>>>(*p, x_in, u_in, gains, queue, ctl,
+                                                                                             xs, us, cand, B, N);
+      QX_CHECK_LAUNCH("linesearch_quad4_phaseB_kernel");
+      qx::linesearch_quad4_phaseC_kernel<<<grid, 128, 0, st>>>(x_in, u_in, cost, status, iters, alpha, x_out, u_out, n_active,
+                                                               queue, ctl, xs, us, cand, tol, flags, B, N);
+      QX_CHECK_LAUNCH("linesearch_quad4_phaseC_kernel");
+      return QX_OK;
+    }
   }
   qx::set_error("unknown model_id %d", p->model_id);
   return QX_EINVAL;

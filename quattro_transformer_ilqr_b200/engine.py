@@ -29,7 +29,7 @@ def _ptr(t):
 
 
 class BatchedILQR:
-    def __init__(self, model: DeviceModel, B: int, N: int, device=None, tf=None):
+    def __init__(self, model: DeviceModel, B: int, N: int, device=None, tf=None, two_phase_linesearch=True):
         if not torch.cuda.is_available():
             raise RuntimeError("quattro_transformer_ilqr_b200 needs a CUDA device (B200, sm_100a); no CPU fallback")
         self.lib = _lib.load()
@@ -52,6 +52,9 @@ class BatchedILQR:
         self.expansion = torch.zeros(self.lib.qx_expansion_bytes(mid, B, N) // 4, dtype=f32, device=dev)
         self.terminal = torch.zeros(self.lib.qx_terminal_bytes(mid, B) // 4, dtype=f32, device=dev)
         self.gains = torch.zeros(self.lib.qx_gains_bytes(mid, B, N) // 4, dtype=f32, device=dev)
+        # scratch of the two-phase line search (quadrotor): candidates of the 5 smaller alphas
+        ws = self.lib.qx_linesearch_workspace_bytes(mid, B, N)
+        self.ls_workspace = torch.empty(ws, dtype=torch.uint8, device=dev) if (ws and two_phase_linesearch) else None
         self.cur = 0
         self.params = model.params()
         self.launches = 0          # kernels launched through the C ABI (bench.py reports it)
@@ -105,7 +108,8 @@ class BatchedILQR:
         self.n_active.zero_()
         _lib.check(self.lib.qx_linesearch(C.byref(self.params), _ptr(self.x[c]), _ptr(self.u[c]), _ptr(self.gains),
                                           _ptr(self.cost), _ptr(self.status), _ptr(self.iters), _ptr(self.alpha),
-                                          _ptr(self.x[1 - c]), _ptr(self.u[1 - c]), _ptr(self.n_active), float(tol),
+                                          _ptr(self.x[1 - c]), _ptr(self.u[1 - c]), _ptr(self.n_active),
+                                          _ptr(self.ls_workspace), float(tol),
                                           _lib.QX_LS_FORCE_ACTIVE if force else 0, self.B, self.N, self.stream),
                    "qx_linesearch")
         self.launches += 1

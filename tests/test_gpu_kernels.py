@@ -102,10 +102,12 @@ def test_riccati(system, B, us, t_start):
         assert relmax(K[:, t], K_ref[:, t - ts]) < 5e-5, t
 
 
-@pytest.mark.parametrize("system,B,us", CASES)
+@pytest.mark.parametrize("system,B,us", CASES + [("quadrotor-sequential", 97, 1.5)])
 def test_linesearch_decisions_and_candidates(system, B, us):
     """Same gains on both sides (the oracle's, rounded to fp32): identical accepted alpha,
     candidates and costs to fp64 round-off; covers alphas other than 1 and the no-accept case."""
+    two_phase = not system.endswith("-sequential")       # quadrotor: both launch structures
+    system = system.split("-")[0]
     x0, u = _problem(system, B, 4, 0.5 * us)
     model = make_model(system)
     x_ref, c_ref = ob.rollout(model, x0, u)
@@ -116,6 +118,8 @@ def test_linesearch_decisions_and_candidates(system, B, us):
     k = (k * scale[:, None, None]).astype(np.float32)
     K = K.astype(np.float32)
     e = _engine(system, B)
+    if not two_phase:
+        e.ls_workspace = None
     e.set_problem(x0, u)
     e.load_gains(K, k)
     e.linesearch(tol=1e-3)
@@ -191,7 +195,7 @@ def test_abi_rejects_bad_arguments():
     lib = _lib.load()
     rc = lib.qx_linesearch(C.byref(e.params), e.x[0].data_ptr(), e.u[0].data_ptr(), e.gains.data_ptr(),
                            e.cost.data_ptr(), e.status.data_ptr(), e.iters.data_ptr(), e.alpha.data_ptr(),
-                           e.x[0].data_ptr(), e.u[0].data_ptr(), None, 1e-3, 0, 8, 30, None)
+                           e.x[0].data_ptr(), e.u[0].data_ptr(), None, None, 1e-3, 0, 8, 30, None)
     assert rc == -1 and b"must differ" in lib.qx_last_error()
     with pytest.raises(ValueError):
         e.set_problem(np.zeros((8, 5)), np.zeros((8, 30, 1)))
