@@ -52,6 +52,7 @@ extern "C" {
 
 #define QX_LAYOUT_SOA 0
 #define QX_LAYOUT_REC 1
+#define QX_LAYOUT_BLK 2   /* compact block record of the quadrotor/Euler/diagonal-cost fast path, see qx_linearize_blk */
 
 #define QX_MAX_N 12
 #define QX_MAX_M 4
@@ -117,6 +118,26 @@ int qx_linearize(const QxParams* p, const double* x, const double* u, float* exp
  * :327-366): gains for t in [t_start, N) written at their absolute t. reg = 1e-6 in the reference. */
 int qx_riccati(int model_id, const float* expansion, const float* terminal, float* gains,
                const int32_t* status, int B, int N, int t_start, float reg, void* stream);
+
+/* ---- Block fast path of the backward pass: quadrotor + Euler map + diagonal Q, R, Qf (what every driver
+ * of the reference runs: quadrotor_sim.py:100, quadrotor_mpc.py:40-46).  There A_t is block bidiagonal in
+ * x = [p | v | eta | omega], B_t has two non-zero row blocks, l_xx / l_uu are diagonal and l_ux = 0, so
+ * linearise emits 64 floats per (t, b) instead of 416 and the Riccati step works on 3x3 blocks with four
+ * lanes per trajectory (qx_blk.cu).  Same results as qx_linearize + qx_riccati (quattro_ilqr_tf.py:182-366).
+ *   expansion float [N][ceil(B/8)][16 slots][8 trajectories][4]   (QX_LAYOUT_BLK; float4 slots: 0-2 rows of
+ *              G = dt dv'/deta with d = dt/m dir in .w, 3-5 rows of Hp = I + dt deta'/deta with l_u[0..2],
+ *              6-8 rows of E = dt deta'/domega with l_u[3], l_uu[0], l_uu[1], 9-11 rows of
+ *              Sp = I + dt domega'/domega with l_uu[2], l_uu[3], 12-14 l_x, 15 unused)
+ *   terminal  float [B][16]  = [V_x(12) | pad]   (V_xx(N) = 2 Qf comes from the parameters)
+ *   gains     as QX_LAYOUT_REC: float [N][B][52] = [k | K row-major]
+ * qx_blk_supported() tells whether the parameter block qualifies; the generic entry points serve the rest. */
+int qx_blk_supported(const QxParams* p);
+size_t qx_blk_expansion_bytes(int B, int N);
+size_t qx_blk_terminal_bytes(int B);
+int qx_linearize_blk(const QxParams* p, const double* x, const double* u, float* expansion, float* terminal,
+                     const int32_t* status, int B, int N, int t_start, void* stream);
+int qx_riccati_blk(const QxParams* p, const float* expansion, const float* terminal, float* gains,
+                   const int32_t* status, int B, int N, int t_start, float reg, void* stream);
 
 /* The line search of optimize (quattro_ilqr_tf.py:440-451) with forward_pass (:377-390) inside:
  * first alpha in {1,.5,.25,.1,.05,.01} whose candidate cost <= cost[b]; all in one launch.

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libquattro_sm100a.so")
 
 QX_MODEL_CARTPOLE, QX_MODEL_QUADROTOR = 0, 1
 QX_EULER, QX_RK4 = 0, 1
-QX_LAYOUT_SOA, QX_LAYOUT_REC = 0, 1
+QX_LAYOUT_SOA, QX_LAYOUT_REC, QX_LAYOUT_BLK = 0, 1, 2
 QX_MAX_N, QX_MAX_M, QX_NUM_ALPHA = 12, 4, 6
 QX_LS_FORCE_ACTIVE = 1
 ALPHAS = (1.0, 0.5, 0.25, 0.1, 0.05, 0.01)
@@ -48,6 +48,11 @@ SIGNATURES = {
     "qx_rollout_cost": (C.c_int, [C.POINTER(QxParams), _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "qx_linearize": (C.c_int, [C.POINTER(QxParams), _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "qx_riccati": (C.c_int, [C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
+    "qx_blk_supported": (C.c_int, [C.POINTER(QxParams)]),
+    "qx_blk_expansion_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "qx_blk_terminal_bytes": (C.c_size_t, [C.c_int]),
+    "qx_linearize_blk": (C.c_int, [C.POINTER(QxParams), _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "qx_riccati_blk": (C.c_int, [C.POINTER(QxParams), _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "qx_linesearch_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "qx_linesearch": (C.c_int, [C.POINTER(QxParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_uint32,
                                 C.c_int, C.c_int, _P]),

@@ -29,7 +29,8 @@ def _ptr(t):
 
 
 class BatchedILQR:
-    def __init__(self, model: DeviceModel, B: int, N: int, device=None, tf=None, two_phase_linesearch=True):
+    def __init__(self, model: DeviceModel, B: int, N: int, device=None, tf=None, two_phase_linesearch=True,
+                 block_path=True):
         if not torch.cuda.is_available():
             raise RuntimeError("quattro_transformer_ilqr_b200 needs a CUDA device (B200, sm_100a); no CPU fallback")
         self.lib = _lib.load()
@@ -49,14 +50,18 @@ class BatchedILQR:
         self.iters = torch.zeros(B, dtype=i32, device=dev)
         self.alpha = torch.full((B,), -1, dtype=i32, device=dev)
         self.n_active = torch.zeros(1, dtype=i32, device=dev)
-        self.expansion = torch.zeros(self.lib.qx_expansion_bytes(mid, B, N) // 4, dtype=f32, device=dev)
-        self.terminal = torch.zeros(self.lib.qx_terminal_bytes(mid, B) // 4, dtype=f32, device=dev)
+        # expansion / terminal are allocated by _select_path(): compact block records (QX_LAYOUT_BLK) when the
+        # parameters qualify (quadrotor, Euler, diagonal weights), the model's generic layout otherwise
+        self.block_path = bool(block_path)
+        self.exp_layout = None
+        self.expansion = self.terminal = None
         self.gains = torch.zeros(self.lib.qx_gains_bytes(mid, B, N) // 4, dtype=f32, device=dev)
         # scratch of the two-phase line search (quadrotor): candidates of the 5 smaller alphas
         ws = self.lib.qx_linesearch_workspace_bytes(mid, B, N)
         self.ls_workspace = torch.empty(ws, dtype=torch.uint8, device=dev) if (ws and two_phase_linesearch) else None
         self.cur = 0
         self.params = model.params()
+        self._select_path()
         self.launches = 0          # kernels launched through the C ABI (bench.py reports it)
 
     # ------------------------------------------------------------------ plumbing
@@ -66,6 +71,21 @@ class BatchedILQR:
 
     def refresh_params(self):
         self.params = self.model.params()
+        self._select_path()
+
+    def _select_path(self):
+        """Pick the expansion layout for the current parameters and (re)allocate its buffers."""
+        mid, B, N = self.model.model_id, self.B, self.N
+        blk = self.block_path and bool(self.lib.qx_blk_supported(C.byref(self.params)))
+        layout = _lib.QX_LAYOUT_BLK if blk else self.layout
+        if layout == self.exp_layout:
+            return
+        self.exp_layout = layout
+        self.expansion = self.terminal = None           # release before allocating the other layout
+        eb = self.lib.qx_blk_expansion_bytes(B, N) if blk else self.lib.qx_expansion_bytes(mid, B, N)
+        tb = self.lib.qx_blk_terminal_bytes(B) if blk else self.lib.qx_terminal_bytes(mid, B)
+        self.expansion = torch.zeros(eb // 4, dtype=torch.float32, device=self.device)
+        self.terminal = torch.zeros(tb // 4, dtype=torch.float32, device=self.device)
 
     def set_problem(self, x0, u_init, rollout=True):
         """x0 (B, n), u_init (B, N, m): host arrays or tensors (any device); resets the solver state."""
@@ -92,15 +112,20 @@ class BatchedILQR:
 
     def linearize(self, t_start=0):
         c = self.cur
-        _lib.check(self.lib.qx_linearize(C.byref(self.params), _ptr(self.x[c]), _ptr(self.u[c]), _ptr(self.expansion),
-                                         _ptr(self.terminal), _ptr(self.status), self.B, self.N, t_start, self.stream),
-                   "qx_linearize")
+        fn = self.lib.qx_linearize_blk if self.exp_layout == _lib.QX_LAYOUT_BLK else self.lib.qx_linearize
+        _lib.check(fn(C.byref(self.params), _ptr(self.x[c]), _ptr(self.u[c]), _ptr(self.expansion),
+                      _ptr(self.terminal), _ptr(self.status), self.B, self.N, t_start, self.stream), "qx_linearize")
         self.launches += 1
 
     def riccati(self, t_start=0, reg=1e-6):
-        _lib.check(self.lib.qx_riccati(self.model.model_id, _ptr(self.expansion), _ptr(self.terminal), _ptr(self.gains),
-                                       _ptr(self.status), self.B, self.N, t_start, C.c_float(reg), self.stream),
-                   "qx_riccati")
+        if self.exp_layout == _lib.QX_LAYOUT_BLK:
+            _lib.check(self.lib.qx_riccati_blk(C.byref(self.params), _ptr(self.expansion), _ptr(self.terminal),
+                                               _ptr(self.gains), _ptr(self.status), self.B, self.N, t_start,
+                                               C.c_float(reg), self.stream), "qx_riccati_blk")
+        else:
+            _lib.check(self.lib.qx_riccati(self.model.model_id, _ptr(self.expansion), _ptr(self.terminal),
+                                           _ptr(self.gains), _ptr(self.status), self.B, self.N, t_start, C.c_float(reg),
+                                           self.stream), "qx_riccati")
         self.launches += 1
 
     def linesearch(self, tol, force=False):
@@ -186,6 +211,8 @@ class BatchedILQR:
     def expansion_batch(self):
         """dict of (B, N, ...) float32 tensors decoded from the record layout (tests / debugging)."""
         B, N, n, m, R = self.B, self.N, self.n, self.m, self.rec
+        if self.exp_layout == _lib.QX_LAYOUT_BLK:
+            return self._expansion_batch_blk()
         if self.layout == _lib.QX_LAYOUT_REC:
             e = self.expansion.view(N, B, R).permute(1, 0, 2)
             t = self.terminal.view(B, n + n * n)
@@ -202,3 +229,30 @@ class BatchedILQR:
         out["VxN"] = t[:, :n]
         out["VxxN"] = t[:, n:].reshape(B, n, n)
         return out
+
+    def _expansion_batch_blk(self):
+        """Decode the compact block records (include/quattro_b200.h, QX_LAYOUT_BLK) into the dense expansion."""
+        B, N, n, m = self.B, self.N, self.n, self.m
+        p, dev, f32 = self.params, self.device, torch.float32
+        noct = (B + 7) // 8
+        r = self.expansion.view(N, noct, 16, 8, 4).permute(1, 3, 0, 2, 4).reshape(noct * 8, N, 16, 4)[:B]   # (B,N,slot,4)
+        dt = float(p.dt)
+        A = torch.eye(n, dtype=f32, device=dev).repeat(B, N, 1, 1)
+        A[..., 0:3, 3:6] = dt * torch.eye(3, dtype=f32, device=dev)
+        A[..., 3:6, 6:9] = r[..., 0:3, 0:3]
+        A[..., 6:9, 6:9] = r[..., 3:6, 0:3]
+        A[..., 6:9, 9:12] = r[..., 6:9, 0:3]
+        A[..., 9:12, 9:12] = r[..., 9:12, 0:3]
+        Bm = torch.zeros((B, N, n, m), dtype=f32, device=dev)
+        Bm[..., 3:6, :] = r[..., 0:3, 3:4]
+        tr = [dt * p.phys[4] / p.phys[1], dt * p.phys[4] / p.phys[2], dt * p.phys[6] / p.phys[3]]
+        sg = torch.tensor([[-1, 1, 1, -1], [1, 1, -1, -1], [1, -1, 1, -1]], dtype=f32, device=dev)
+        Bm[..., 9:12, :] = sg * torch.tensor(tr, dtype=f32, device=dev)[:, None]
+        lu = torch.stack([r[..., 3, 3], r[..., 4, 3], r[..., 5, 3], r[..., 6, 3]], dim=-1)
+        luu_d = torch.stack([r[..., 7, 3], r[..., 8, 3], r[..., 9, 3], r[..., 10, 3]], dim=-1)
+        Q = torch.tensor(list(p.Q), dtype=torch.float64).view(12, 12).diagonal().to(dev, f32)
+        Qf = torch.tensor(list(p.Qf), dtype=torch.float64).view(12, 12).diagonal().to(dev, f32)
+        return {"A": A, "B": Bm, "lx": r[..., 12:15, :].reshape(B, N, 12), "lu": lu,
+                "lxx": torch.diag(2 * Q).repeat(B, N, 1, 1), "luu": torch.diag_embed(luu_d),
+                "lux": torch.zeros((B, N, m, n), dtype=f32, device=dev),
+                "VxN": self.terminal.view(B, 16)[:, :12], "VxxN": torch.diag(2 * Qf).repeat(B, 1, 1)}

@@ -15,9 +15,9 @@ from tests.util import HORIZON, relmax
 pytestmark = pytest.mark.gpu
 
 
-def _engine(system, B, method="euler", **kw):
+def _engine(system, B, method="euler", block_path=True, **kw):
     from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel
-    return BatchedILQR(DeviceModel(system, integration_method=method, **kw), B, HORIZON[system])
+    return BatchedILQR(DeviceModel(system, integration_method=method, **kw), B, HORIZON[system], block_path=block_path)
 
 
 def _problem(system, B, seed, u_scale):
@@ -31,6 +31,13 @@ def _problem(system, B, seed, u_scale):
 
 
 CASES = [("cartpole", 257, 5.0), ("quadrotor", 97, 1.5)]
+# the quadrotor with the Euler map and diagonal weights takes the block path (qx_blk.cu) by default;
+# "-dense" forces the generic 416-float records + warp-per-trajectory Riccati on the same inputs
+BACKWARD_CASES = CASES + [("quadrotor-dense", 97, 1.5)]
+
+
+def _split(system):
+    return system.split("-")[0], not system.endswith("-dense")
 
 
 @pytest.mark.parametrize("system,B,us", CASES)
@@ -44,11 +51,14 @@ def test_rollout_cost(system, B, us, method):
     assert relmax(e.cost.cpu().numpy(), c_ref) < 1e-12
 
 
-@pytest.mark.parametrize("system,B,us", CASES)
+@pytest.mark.parametrize("system,B,us", BACKWARD_CASES)
 @pytest.mark.parametrize("method", ["euler", "rk4"])
 def test_linearize(system, B, us, method):
+    from quattro_transformer_ilqr_b200 import _lib
+    system, blk = _split(system)
     x0, u = _problem(system, B, 2, us)
-    e = _engine(system, B, method)
+    e = _engine(system, B, method, block_path=blk)
+    assert (e.exp_layout == _lib.QX_LAYOUT_BLK) == (blk and system == "quadrotor" and method == "euler")
     e.set_problem(x0, u)
     e.linearize(0)
     got = {k: v.cpu().numpy() for k, v in e.expansion_batch().items()}
@@ -79,14 +89,15 @@ def test_linearize_dense_cost_matrices():
         assert relmax(got[key], ref[key]) < 2e-6, key
 
 
-@pytest.mark.parametrize("system,B,us", CASES)
+@pytest.mark.parametrize("system,B,us", BACKWARD_CASES)
 @pytest.mark.parametrize("t_start", [0, "segment"])
 def test_riccati(system, B, us, t_start):
     """Full pass and the segment variant (backward_pass_segment) against the fp64 oracle."""
+    system, blk = _split(system)
     x0, u = _problem(system, B, 3, 0.3 * us)
     N = HORIZON[system]
     ts = 0 if t_start == 0 else (N - 5 if system == "cartpole" else N - 1)
-    e = _engine(system, B)
+    e = _engine(system, B, block_path=blk)
     e.set_problem(x0, u)
     e.gains.fill_(float("nan"))
     e.linearize(ts)
@@ -100,6 +111,50 @@ def test_riccati(system, B, us, t_start):
     # per time step too (early steps have much smaller gains than the tail)
     for t in range(ts, N):
         assert relmax(K[:, t], K_ref[:, t - ts]) < 5e-5, t
+
+
+@pytest.mark.parametrize("B", [1, 7, 8, 9, 64, 1000])
+def test_riccati_block_path_sizes_and_status(B):
+    """Block path: ragged octets (B not a multiple of 8), B = 1, and masked (finished) trajectories, whose
+    gain records must stay untouched; compared with the fp64 oracle and with the dense CUDA path."""
+    x0, u = _problem("quadrotor", B, 30 + B, 0.4)
+    model = make_model("quadrotor")
+    x_ref, _ = ob.rollout(model, x0, u)
+    K_ref, k_ref = ob.riccati(ob.linearize(model, x_ref, u))
+    out = {}
+    for blk in (True, False):
+        e = _engine("quadrotor", B, block_path=blk)
+        e.set_problem(x0, u)
+        mask = np.zeros(B, dtype=bool)
+        mask[1::3] = True
+        e.status.copy_(torch.as_tensor(mask.astype(np.int32)))
+        e.gains.fill_(float("nan"))
+        e.linearize(0)
+        e.riccati(0)
+        K, k = (t.cpu().numpy() for t in e.gains_batch())
+        assert np.isnan(K[mask]).all() and np.isnan(k[mask]).all()
+        assert not np.isnan(K[~mask]).any()
+        assert relmax(K[~mask], K_ref[~mask]) < 1e-5 and relmax(k[~mask], k_ref[~mask]) < 1e-5
+        out[blk] = (K[~mask], k[~mask])
+    assert relmax(out[True][0], out[False][0]) < 1e-5 and relmax(out[True][1], out[False][1]) < 1e-5
+
+
+def test_riccati_block_path_indefinite_quu():
+    """An indefinite Q_uu (negative R) must go through the pivoted fallback like the reference's LU inverse
+    (SURVEY a-Q(4)) instead of producing NaN."""
+    B = 16
+    R = np.diag([-900.0, 0.01, 0.01, 0.01])
+    x0, u = _problem("quadrotor", B, 77, 0.2)
+    model = make_model("quadrotor", R=R)
+    x_ref, _ = ob.rollout(model, x0, u)
+    N = HORIZON["quadrotor"]
+    K_ref, k_ref = ob.riccati(ob.linearize(model, x_ref, u), N - 3)
+    e = _engine("quadrotor", B, R=R)
+    e.set_problem(x0, u)
+    e.linearize(N - 3)
+    e.riccati(N - 3)
+    K, k = (t.cpu().numpy() for t in e.gains_batch())
+    assert relmax(K[:, N - 3:], K_ref) < 1e-4 and relmax(k[:, N - 3:], k_ref) < 1e-4
 
 
 @pytest.mark.parametrize("system,B,us", CASES + [("quadrotor-sequential", 97, 1.5)])
