@@ -13,7 +13,7 @@ for s in $SRCS; do
   # rollouts / costs: no FMA contraction, so every kernel that evaluates f and L (nominal rollout,
   # line search, forward_pass) produces the same bits for the same inputs, like the reference's
   # single Python implementation does (the accept test compares such costs with "<=")
-  if [ "$s" = "qx_rollout.cu" ]; then EXTRA="-fmad=false"; fi
+  if [ "$s" = "qx_rollout.cu" ] || [ "$s" = "qx_quadls.cu" ]; then EXTRA="-fmad=false"; fi
   ( $NVCC $FLAGS $EXTRA -c "$s" -o "build/${s%.cu}.o" > "build/${s%.cu}.log" 2>&1 || { cat "build/${s%.cu}.log"; exit 1; } ) &
   pids+=($!)
 done

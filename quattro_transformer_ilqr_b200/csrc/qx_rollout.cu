@@ -664,6 +664,15 @@ static int launch_linesearch(const QxParams* p, double* x_in, double* u_in, cons
   return QX_OK;
 }
 
+// distributed-state 4-lane kernels of qx_quadls.cu (quadrotor, diagonal weights)
+size_t qd_workspace_bytes(int B, int N);
+int qd_launch_rollout(const QxParams* p, const double* x0, const double* u, double* x, double* cost,
+                      const int32_t* status, int B, int N, cudaStream_t st);
+int qd_launch_linesearch(const QxParams* p, double* x_in, double* u_in, const float* gains, double* cost,
+                         int32_t* status, int32_t* iters, int32_t* alpha, double* x_out, double* u_out,
+                         int32_t* n_active, void* workspace, double tol, uint32_t flags, int B, int N,
+                         cudaStream_t st);
+
 }  // namespace qx
 
 extern "C" int qx_rollout_cost(const QxParams* p, const double* x0, const double* u, double* x, double* cost,
@@ -674,11 +683,7 @@ extern "C" int qx_rollout_cost(const QxParams* p, const double* x0, const double
   switch (p->model_id) {
     case QX_MODEL_CARTPOLE: return qx::launch_rollout<qx::CartPole>(p, x0, u, x, cost, status, B, N, st);
     case QX_MODEL_QUADROTOR:
-      if (p->diag_cost) {   // same arithmetic as the 4-lane line search
-        qx::rollout_quad4_kernel<<<qx::ceil_div(4 * B, 128), 128, 0, st>>>(*p, x0, u, x, cost, status, B, N);
-        QX_CHECK_LAUNCH("rollout_quad4_kernel");
-        return QX_OK;
-      }
+      if (p->diag_cost) return qx::qd_launch_rollout(p, x0, u, x, cost, status, B, N, st);   // same arithmetic as the 4-lane line search
       return qx::launch_rollout<qx::Quadrotor>(p, x0, u, x, cost, status, B, N, st);
   }
   qx::set_error("unknown model_id %d", p->model_id);
@@ -687,10 +692,7 @@ extern "C" int qx_rollout_cost(const QxParams* p, const double* x0, const double
 
 extern "C" size_t qx_linesearch_workspace_bytes(int model_id, int B, int N) {
   if (model_id != QX_MODEL_QUADROTOR || B <= 0 || N <= 0) return 0;
-  constexpr size_t n = 12, m = 4, A = QX_NUM_ALPHA - 1;
-  // [ctl int32[4] | queue int32[B] (padded to 16 B) | cand_cost double[5][B] | xs double[5][N+1][n][B] | us double[5][N][m][B]]
-  const size_t qbytes = ((size_t)B * 4 + 15) / 16 * 16;
-  return 16 + qbytes + A * B * 8 + A * ((size_t)(N + 1) * n + (size_t)N * m) * B * 8;
+  return qx::qd_workspace_bytes(B, N);
 }
 
 extern "C" int qx_linesearch(const QxParams* p, double* x_in, double* u_in, const float* gains, double* cost,
@@ -710,35 +712,8 @@ extern "C" int qx_linesearch(const QxParams* p, double* x_in, double* u_in, cons
       if (!p->diag_cost)
         return qx::launch_linesearch<qx::Quadrotor>(p, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out,
                                                     n_active, tol, flags, B, N, st);
-      const int grid = qx::ceil_div(4 * B, 128);
-      if (workspace == nullptr) {   // single launch, alphas tried one after the other
-        qx::linesearch_quad4_kernel<0><<<grid, 128, 0, st>>>(*p, x_in, u_in, gains, cost, status, iters, alpha, x_out,
-                                                             u_out, n_active, nullptr, nullptr, tol, flags, B, N);
-        QX_CHECK_LAUNCH("linesearch_quad4_kernel");
-        return QX_OK;
-      }
-      // two-phase: alpha = 1 for everybody, then the remaining alphas of the rejected ones in parallel
-      QX_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, "workspace must be 16-byte aligned");
-      constexpr size_t n = 12, m = 4, A = QX_NUM_ALPHA - 1;
-      uint8_t* w = static_cast<uint8_t*>(workspace);
-      int32_t* ctl = reinterpret_cast<int32_t*>(w);
-      int32_t* queue = reinterpret_cast<int32_t*>(w + 16);
-      const size_t qbytes = ((size_t)B * 4 + 15) / 16 * 16;
-      double* cand = reinterpret_cast<double*>(w + 16 + qbytes);
-      double* xs = cand + A * B;
-      double* us = xs + A * (size_t)(N + 1) * n * B;
-      cudaError_t e = cudaMemsetAsync(ctl, 0, 16, st);
-      if (e != cudaSuccess) return qx::cuda_fail(e, "cudaMemsetAsync(ctl)");
-      qx::linesearch_quad4_kernel<1><<<grid, 128, 0, st>>>(*p, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out,
-                                                           n_active, queue, ctl, tol, flags, B, N);
-      QX_CHECK_LAUNCH("linesearch_quad4_kernel<phase A>");
-      qx::linesearch_quad4_phaseB_kernel<<<qx::ceil_div((int)(4 * A) * B, 128), 128, 0, st>>>(*p, x_in, u_in, gains, queue, ctl,
-                                                                                             xs, us, cand, B, N);
-      QX_CHECK_LAUNCH("linesearch_quad4_phaseB_kernel");
-      qx::linesearch_quad4_phaseC_kernel<<<grid, 128, 0, st>>>(x_in, u_in, cost, status, iters, alpha, x_out, u_out, n_active,
-                                                               queue, ctl, xs, us, cand, tol, flags, B, N);
-      QX_CHECK_LAUNCH("linesearch_quad4_phaseC_kernel");
-      return QX_OK;
+      return qx::qd_launch_linesearch(p, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out, n_active, workspace,
+                                      tol, flags, B, N, st);
     }
   }
   qx::set_error("unknown model_id %d", p->model_id);
