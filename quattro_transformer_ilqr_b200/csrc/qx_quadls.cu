@@ -28,6 +28,7 @@
 // (coalesced) row loops.  Queues are appended per CTA in trajectory order, so the eight groups of a B warp
 // touch neighbouring columns.
 #include "qx_common.cuh"
+#include "qx_fp64math.cuh"
 
 namespace qx {
 
@@ -37,7 +38,6 @@ constexpr unsigned FULL = 0xffffffffu;
 
 struct QdConst {
   double inv_mass, grav, arm, kyaw, invIx, invIy, invIz, c1, c2, c3, dt, beta, inv_beta, alpha_b;
-  int integrator;
 };
 
 struct QdLane {
@@ -60,7 +60,6 @@ __device__ __forceinline__ void qd_lane_init(const QxParams& p, int lane, QdLane
   k.c2 = (p.phys[3] - p.phys[1]) / p.phys[2];
   k.c3 = (p.phys[1] - p.phys[2]) / p.phys[3];
   k.dt = p.dt; k.beta = p.barrier_beta; k.inv_beta = 1.0 / p.barrier_beta; k.alpha_b = p.barrier_alpha;
-  k.integrator = p.integrator;
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     c.qd[r] = p.Q[(3 * c.g + r) * n + 3 * c.g + r];
@@ -70,87 +69,126 @@ __device__ __forceinline__ void qd_lane_init(const QxParams& p, int lane, QdLane
   c.rd = p.R[c.g * m + c.g];
 }
 
-// continuous dynamics of the lane's own block (quadrotor_dynamics.py:64-164); every lane of the warp must call it
-__device__ __forceinline__ void qd_fc(const double* xg, const double* ua, const QdLane& c, double* dg) {
+// Continuous dynamics of the lane's own block (quadrotor_dynamics.py:64-164) for NA independent states at once;
+// every lane of the warp must call it.  Straight-line code: the four block formulas are all evaluated and the
+// lane's one selected (divergent branches would cost the same issue slots and stop the compiler from
+// interleaving the NA chains).
+template <int NA>
+__device__ __forceinline__ void qd_fc_n(const double (*xg)[3], const double (*ua)[4], const QdLane& c, double (*dg)[3]) {
   const QdConst& k = c.k;
   const int g = c.g, base = c.base;
-  // the angles live in lane 2; lane g < 3 evaluates angle g (lane 3 repeats psi)
-  const double a0 = shfl_d(xg[0], base + 2), a1 = shfl_d(xg[1], base + 2), a2 = shfl_d(xg[2], base + 2);
-  const double ang = (g == 0) ? a0 : (g == 1) ? a1 : a2;
-  double s, cs;
-  ::sincos(ang, &s, &cs);
-  const double sec_own = 1.0 / cs;
-  // right neighbour's block: v for lane 0, omega for lane 2
-  const int nb = base + ((g + 1) & 3);
-  const double n0 = shfl_d(xg[0], nb), n1 = shfl_d(xg[1], nb), n2 = shfl_d(xg[2], nb);
-  const double sphi = shfl_d(s, base), cphi = shfl_d(cs, base);
-  const double sth = shfl_d(s, base + 1), cth = shfl_d(cs, base + 1), sec = shfl_d(sec_own, base + 1);
-  const double spsi = shfl_d(s, base + 2), cpsi = shfl_d(cs, base + 2);
-  if (g == 0) {
-    dg[0] = n0; dg[1] = n1; dg[2] = n2;
-  } else if (g == 1) {
-    const double Tm = ((ua[0] + ua[1]) + (ua[2] + ua[3])) * k.inv_mass;
+  double ang[NA], s[NA], cs[NA];
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+    // the angles live in lane 2; lane g < 3 evaluates angle g (lane 3 repeats psi)
+    const double a0 = shfl_d(xg[a][0], base + 2), a1 = shfl_d(xg[a][1], base + 2), a2 = shfl_d(xg[a][2], base + 2);
+    ang[a] = (g == 0) ? a0 : (g == 1) ? a1 : a2;
+  }
+  fast_sincos_n<NA>(ang, s, cs);
+  const int nb = base + ((g + 1) & 3);       // right neighbour's block: v for lane 0, omega for lane 2
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+    const double sec_own = fast_rcp(cs[a]);
+    const double n0 = shfl_d(xg[a][0], nb), n1 = shfl_d(xg[a][1], nb), n2 = shfl_d(xg[a][2], nb);
+    const double sphi = shfl_d(s[a], base), cphi = shfl_d(cs[a], base);
+    const double sth = shfl_d(s[a], base + 1), cth = shfl_d(cs[a], base + 1), sec = shfl_d(sec_own, base + 1);
+    const double spsi = shfl_d(s[a], base + 2), cpsi = shfl_d(cs[a], base + 2);
+    const double* u = ua[a];
+    // block 1: v' = T/m * R e3 - g e3
+    const double Tm = ((u[0] + u[1]) + (u[2] + u[3])) * k.inv_mass;
     const double sc = sth * cphi;
-    dg[0] = Tm * fma(cpsi, sc, spsi * sphi);
-    dg[1] = Tm * fma(-spsi, sc, cpsi * sphi);
-    dg[2] = fma(Tm, cth * cphi, -k.grav);
-  } else if (g == 2) {
+    const double v0 = Tm * fma(cpsi, sc, spsi * sphi);
+    const double v1 = Tm * fma(-spsi, sc, cpsi * sphi);
+    const double v2 = fma(Tm, cth * cphi, -k.grav);
+    // block 2: eta' from omega = (n0, n1, n2)
     const double tth = sth * sec;
     const double w = fma(n1, sphi, n2 * cphi);          // q sin(phi) + r cos(phi)
-    dg[0] = fma(w, tth, n0);
-    dg[1] = fma(n1, cphi, -(n2 * sphi));
-    dg[2] = w * sec;
-  } else {
-    const double pp = xg[0], q = xg[1], r = xg[2];
-    dg[0] = fma(k.c1, q * r, k.arm * ((ua[1] + ua[2]) - (ua[0] + ua[3])) * k.invIx);
-    dg[1] = fma(k.c2, pp * r, k.arm * ((ua[0] + ua[1]) - (ua[2] + ua[3])) * k.invIy);
-    dg[2] = fma(k.c3, pp * q, k.kyaw * ((ua[0] - ua[1]) + (ua[2] - ua[3])) * k.invIz);
+    const double e0 = fma(w, tth, n0);
+    const double e1 = fma(n1, cphi, -(n2 * sphi));
+    const double e2 = w * sec;
+    // block 3: omega' from the own block
+    const double pp = xg[a][0], q = xg[a][1], r = xg[a][2];
+    const double o0 = fma(k.c1, q * r, k.arm * ((u[1] + u[2]) - (u[0] + u[3])) * k.invIx);
+    const double o1 = fma(k.c2, pp * r, k.arm * ((u[0] + u[1]) - (u[2] + u[3])) * k.invIy);
+    const double o2 = fma(k.c3, pp * q, k.kyaw * ((u[0] - u[1]) + (u[2] - u[3])) * k.invIz);
+    // block 0: p' = v = (n0, n1, n2)
+    dg[a][0] = (g == 0) ? n0 : (g == 1) ? v0 : (g == 2) ? e0 : o0;
+    dg[a][1] = (g == 0) ? n1 : (g == 1) ? v1 : (g == 2) ? e1 : o1;
+    dg[a][2] = (g == 0) ? n2 : (g == 1) ? v2 : (g == 2) ? e2 : o2;
   }
 }
 
-// discrete map of the own block (quadrotor_dynamics.py:186-195)
-__device__ __forceinline__ void qd_step(double* xg, const double* ua, const QdLane& c) {
+// discrete map of the own block (quadrotor_dynamics.py:186-195); the integrator is a template parameter so
+// that the Euler kernels do not carry the registers of the RK4 stages
+template <int INTEG, int NA>
+__device__ __forceinline__ void qd_step_n(double (*xg)[3], const double (*ua)[4], const QdLane& c) {
   const double dt = c.k.dt;
-  double k1[3];
-  qd_fc(xg, ua, c, k1);
-  if (c.k.integrator == QX_EULER) {
+  double k1[NA][3];
+  qd_fc_n<NA>(xg, ua, c, k1);
+  if (INTEG == QX_EULER) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) xg[i] = fma(dt, k1[i], xg[i]);
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) xg[a][i] = fma(dt, k1[a][i], xg[a][i]);
     return;
   }
-  double k2[3], k3[3], k4[3], xs[3];
+  double k2[NA][3], k3[NA][3], k4[NA][3], xs[NA][3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) xs[i] = fma(0.5 * dt, k1[i], xg[i]);
-  qd_fc(xs, ua, c, k2);
+  for (int a = 0; a < NA; ++a)
 #pragma unroll
-  for (int i = 0; i < 3; ++i) xs[i] = fma(0.5 * dt, k2[i], xg[i]);
-  qd_fc(xs, ua, c, k3);
+    for (int i = 0; i < 3; ++i) xs[a][i] = fma(0.5 * dt, k1[a][i], xg[a][i]);
+  qd_fc_n<NA>(xs, ua, c, k2);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) xs[i] = fma(dt, k3[i], xg[i]);
-  qd_fc(xs, ua, c, k4);
+  for (int a = 0; a < NA; ++a)
 #pragma unroll
-  for (int i = 0; i < 3; ++i) xg[i] = fma(dt / 6.0, (k1[i] + 2.0 * k2[i]) + (2.0 * k3[i] + k4[i]), xg[i]);
+    for (int i = 0; i < 3; ++i) xs[a][i] = fma(0.5 * dt, k2[a][i], xg[a][i]);
+  qd_fc_n<NA>(xs, ua, c, k3);
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) xs[a][i] = fma(dt, k3[a][i], xg[a][i]);
+  qd_fc_n<NA>(xs, ua, c, k4);
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      xg[a][i] = fma(dt / 6.0, (k1[a][i] + 2.0 * k2[a][i]) + (2.0 * k3[a][i] + k4[a][i]), xg[a][i]);
 }
 
-// alpha_b * softplus(-u; beta)^2 (quadrotor_mpc.py:80, :92); log1p(e) by its series when e is tiny
-__device__ __forceinline__ double qd_barrier(double u, const QdConst& k) {
-  const double bz = -k.beta * u;
-  const double e = ::exp(-fabs(bz));
-  const double l1p = (e < 1e-4) ? e * fma(-e, fma(-e, fma(-0.25, e, 1.0 / 3.0), 0.5), 1.0) : ::log1p(e);
-  const double sp = (fmax(bz, 0.0) + l1p) * k.inv_beta;
-  return k.alpha_b * sp * sp;
-}
-
-// the lane's share of L(x, u): its state block and its control (quadrotor_mpc.py:86-93)
-__device__ __forceinline__ double qd_running(const double* xg, double uh, const QdLane& c) {
-  double acc = 0.0;
+// The lane's share of L(x, u) for NA candidates: its state block and its control (quadrotor_mpc.py:86-93) with
+// the barrier alpha_b * softplus(-u; beta)^2 (:80, :92).  log1p(e) by its series when e is tiny (u well on the
+// feasible side), by fast_log1p_unit otherwise - evaluated for all NA only if some lane of the warp needs it.
+template <int NA>
+__device__ __forceinline__ void qd_running_n(const double (*xg)[3], const double* uh, const QdLane& c, double* cst) {
+  const QdConst& k = c.k;
+  double e[NA], bz[NA], l1p[NA];
+  bool need = false;
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const double dxv = xg[r] - c.xr[r];
-    acc = fma(c.qd[r] * dxv, dxv, acc);
+  for (int a = 0; a < NA; ++a) {
+    bz[a] = -k.beta * uh[a];
+    e[a] = fast_exp_neg(-fabs(bz[a]));
+    l1p[a] = e[a] * fma(-e[a], fma(-e[a], fma(-0.25, e[a], 1.0 / 3.0), 0.5), 1.0);
+    need = need || !(e[a] < 1e-4);
   }
-  acc = fma(c.rd * uh, uh, acc);
-  return acc + qd_barrier(uh, c.k);
+  if (__any_sync(FULL, need)) {
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      const double full = fast_log1p_unit(e[a]);
+      l1p[a] = (e[a] < 1e-4) ? l1p[a] : full;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+    double acc = 0.0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double dxv = xg[a][r] - c.xr[r];
+      acc = fma(c.qd[r] * dxv, dxv, acc);
+    }
+    acc = fma(c.rd * uh[a], uh[a], acc);
+    const double sp = (fmax(bz[a], 0.0) + l1p[a]) * k.inv_beta;
+    cst[a] += acc + k.alpha_b * sp * sp;
+  }
 }
 
 __device__ __forceinline__ double qd_final(const double* xg, const QdLane& c) {
@@ -169,65 +207,108 @@ __device__ __forceinline__ double qd_group_sum(double v) {
   return v;
 }
 
-// One candidate rollout (forward_pass :377-390) by a 4-lane group: nominal and gains of trajectory b_src,
-// candidate written at column b_dst of (x_dst, u_dst) (row stride B).  All 32 lanes of the warp must call it;
-// lanes with run == false only take part in the shuffles.  Returns the total cost (same bits in the group).
+// NA candidate rollouts (forward_pass :377-390, step sizes alpha[0..NA)) of ONE trajectory by a 4-lane group,
+// interleaved: the nominal and the gains are loaded once and the NA independent recursions give the scheduler
+// NA-fold instruction-level parallelism (a single rollout is a chain of dependent fp64 operations).
+// Nominal and gains of trajectory b_src; candidate a is written at column b_dst of (x_dst[a], u_dst[a]) (row
+// stride B).  All 32 lanes of the warp must call it; lanes with run == false only take part in the shuffles.
+// cst[a] returns the total cost (same bits in the four lanes of the group).
+template <int INTEG, int NA>
+__device__ __forceinline__ void qd_candidates(const QdLane& c, bool run, const double* __restrict__ x_in,
+                                              const double* __restrict__ u_in, const float* __restrict__ gains,
+                                              int b_src, const double* alpha, double* const* x_dst, double* const* u_dst,
+                                              int b_dst, int B, int N, double* cst) {
+  constexpr int n = 12, m = 4, G = 52;
+  const int g = c.g, base = c.base;
+  // per-lane cursors, advanced by one time step per iteration (no index arithmetic in the loop)
+  const size_t rowB = (size_t)B;
+  const double* xin = x_in + (size_t)(3 * g) * rowB + b_src;
+  const double* uin = u_in + (size_t)g * rowB + b_src;
+  const float* rec = gains + (size_t)b_src * G;
+  size_t xo = (size_t)(3 * g) * rowB + b_dst, uo = (size_t)g * rowB + b_dst;     // offsets into x_dst[a], u_dst[a]
+  double xg[NA][3], xn_nx[3] = {0.0, 0.0, 0.0}, un_nx = 0.0;
+  float gk_nx = 0.f;
+  float4 gK_nx[3] = {};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double v = run ? xin[(size_t)i * rowB] : 0.0;
+#pragma unroll
+    for (int a = 0; a < NA; ++a) xg[a][i] = v;
+  }
+  auto fetch = [&]() {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) xn_nx[i] = xin[(size_t)i * rowB];
+    un_nx = *uin;
+    gk_nx = rec[g];
+    const float4* row = reinterpret_cast<const float4*>(rec + m + g * n);
+    gK_nx[0] = row[0]; gK_nx[1] = row[1]; gK_nx[2] = row[2];
+    xin += n * rowB;
+    uin += m * rowB;
+    rec += rowB * G;
+  };
+  if (run) fetch();
+#pragma unroll
+  for (int a = 0; a < NA; ++a) cst[a] = 0.0;
+  for (int t = 0; t < N; ++t) {
+    const double xn[3] = {xn_nx[0], xn_nx[1], xn_nx[2]};
+    const double un = un_nx;
+    const double gk = (double)gk_nx;
+    const double kr[12] = {(double)gK_nx[0].x, (double)gK_nx[0].y, (double)gK_nx[0].z, (double)gK_nx[0].w,
+                           (double)gK_nx[1].x, (double)gK_nx[1].y, (double)gK_nx[1].z, (double)gK_nx[1].w,
+                           (double)gK_nx[2].x, (double)gK_nx[2].y, (double)gK_nx[2].z, (double)gK_nx[2].w};
+    if (run && t + 1 < N) fetch();
+    double uh[NA], ua[NA][4];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      double dx[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) dx[i] = xg[a][i] - xn[i];
+      // du_g = k_g + K[g,:] (x_hat - x): block q of dx comes from lane q
+      double acc[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) acc[i] = fma(kr[3 * q + i], shfl_d(dx[i], base + q), acc[i]);
+      const double kd = (acc[0] + acc[1]) + acc[2];
+      uh[a] = fma(alpha[a], gk + kd, un);                   // alpha scales the feedback term too (:382-383)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ua[a][q] = shfl_d(uh[a], base + q);
+    }
+    if (run) {
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        u_dst[a][uo] = uh[a];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) x_dst[a][xo + (size_t)i * rowB] = xg[a][i];
+      }
+    }
+    qd_running_n<NA>(xg, uh, c, cst);       // lanes with run == false accumulate a cost nobody reads
+    xo += n * rowB;
+    uo += m * rowB;
+    qd_step_n<INTEG, NA>(xg, ua, c);
+  }
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+    if (run) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) x_dst[a][xo + (size_t)i * rowB] = xg[a][i];
+      cst[a] += qd_final(xg[a], c);
+    }
+    cst[a] = qd_group_sum(cst[a]);
+  }
+}
+
+template <int INTEG>
 __device__ __forceinline__ double qd_candidate(const QdLane& c, bool run, const double* __restrict__ x_in,
                                                const double* __restrict__ u_in, const float* __restrict__ gains,
                                                int b_src, double alpha, double* __restrict__ x_dst,
                                                double* __restrict__ u_dst, int b_dst, int B, int N) {
-  constexpr int n = 12, m = 4, G = 52;
-  const int g = c.g, base = c.base;
-  double xg[3], xn_nx[3] = {0.0, 0.0, 0.0}, un_nx = 0.0;
-  float gk_nx = 0.f;
-  float4 gK_nx[3] = {};
-#pragma unroll
-  for (int i = 0; i < 3; ++i) xg[i] = run ? x_in[(size_t)(3 * g + i) * B + b_src] : 0.0;
-  auto fetch = [&](int t) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i) xn_nx[i] = x_in[((size_t)t * n + 3 * g + i) * B + b_src];
-    un_nx = u_in[((size_t)t * m + g) * B + b_src];
-    const float* rec = gains + ((size_t)t * B + b_src) * G;
-    gk_nx = rec[g];
-    const float4* row = reinterpret_cast<const float4*>(rec + m + g * n);
-    gK_nx[0] = row[0]; gK_nx[1] = row[1]; gK_nx[2] = row[2];
-  };
-  if (run) fetch(0);
-  double cst = 0.0;
-  for (int t = 0; t < N; ++t) {
-    double dx[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) dx[i] = xg[i] - xn_nx[i];
-    const double un = un_nx;
-    const double gk = (double)gk_nx;
-    const float kr[12] = {gK_nx[0].x, gK_nx[0].y, gK_nx[0].z, gK_nx[0].w, gK_nx[1].x, gK_nx[1].y,
-                          gK_nx[1].z, gK_nx[1].w, gK_nx[2].x, gK_nx[2].y, gK_nx[2].z, gK_nx[2].w};
-    if (run && t + 1 < N) fetch(t + 1);
-    // du_g = k_g + K[g,:] (x_hat - x): block q of dx comes from lane q
-    double acc[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-      for (int i = 0; i < 3; ++i) acc[i] = fma((double)kr[3 * q + i], shfl_d(dx[i], base + q), acc[i]);
-    const double kd = (acc[0] + acc[1]) + acc[2];
-    const double uh = fma(alpha, gk + kd, un);              // alpha scales the feedback term too (:382-383)
-    double ua[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) ua[q] = shfl_d(uh, base + q);
-    if (run) {
-      u_dst[((size_t)t * m + g) * B + b_dst] = uh;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) x_dst[((size_t)t * n + 3 * g + i) * B + b_dst] = xg[i];
-      cst += qd_running(xg, uh, c);
-    }
-    qd_step(xg, ua, c);
-  }
-  if (run) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i) x_dst[((size_t)N * n + 3 * g + i) * B + b_dst] = xg[i];
-    cst += qd_final(xg, c);
-  }
-  return qd_group_sum(cst);
+  double cst[1];
+  const double al[1] = {alpha};
+  double* const xd[1] = {x_dst};
+  double* const ud[1] = {u_dst};
+  qd_candidates<INTEG, 1>(c, run, x_in, u_in, gains, b_src, al, xd, ud, b_dst, B, N, cst);
+  return cst[0];
 }
 
 // Append the flagged groups of this CTA to a queue, in trajectory order.  Must be reached by all threads.
@@ -285,6 +366,7 @@ static QdWork qd_carve(void* workspace, int B, int N) {
 }
 
 // ------------------------------------------------------------------------------------------------
+template <int INTEG>
 __global__ void __launch_bounds__(128)
 rollout_qd_kernel(const __grid_constant__ QxParams p, const double* __restrict__ x0, const double* __restrict__ u,
                   double* __restrict__ x, double* __restrict__ cost, const int32_t* __restrict__ status, int B, int N) {
@@ -296,31 +378,30 @@ rollout_qd_kernel(const __grid_constant__ QxParams p, const double* __restrict__
   QdLane c;
   qd_lane_init(p, lane, c);
   const int g = c.g, base = c.base;
-  double xg[3];
+  double xg[1][3], cst[1] = {0.0};
 #pragma unroll
-  for (int i = 0; i < 3; ++i) xg[i] = run ? x0[(size_t)(3 * g + i) * B + b] : 0.0;
-  double cst = 0.0;
+  for (int i = 0; i < 3; ++i) xg[0][i] = run ? x0[(size_t)(3 * g + i) * B + b] : 0.0;
   double u_nx = run ? u[(size_t)g * B + b] : 0.0;
   for (int t = 0; t < N; ++t) {
-    const double uh = u_nx;
+    const double uh[1] = {u_nx};
     if (run && t + 1 < N) u_nx = u[((size_t)(t + 1) * m + g) * B + b];
-    double ua[4];
+    double ua[1][4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) ua[q] = shfl_d(uh, base + q);
+    for (int q = 0; q < 4; ++q) ua[0][q] = shfl_d(uh[0], base + q);
     if (run) {
 #pragma unroll
-      for (int i = 0; i < 3; ++i) x[((size_t)t * n + 3 * g + i) * B + b] = xg[i];
-      cst += qd_running(xg, uh, c);
+      for (int i = 0; i < 3; ++i) x[((size_t)t * n + 3 * g + i) * B + b] = xg[0][i];
     }
-    qd_step(xg, ua, c);
+    qd_running_n<1>(xg, uh, c, cst);
+    qd_step_n<INTEG, 1>(xg, ua, c);
   }
   if (run) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) x[((size_t)N * n + 3 * g + i) * B + b] = xg[i];
-    cst += qd_final(xg, c);
+    for (int i = 0; i < 3; ++i) x[((size_t)N * n + 3 * g + i) * B + b] = xg[0][i];
+    cst[0] += qd_final(xg[0], c);
   }
-  cst = qd_group_sum(cst);
-  if (run && g == 0) cost[b] = cst;
+  const double tot = qd_group_sum(cst[0]);
+  if (run && g == 0) cost[b] = tot;
 }
 
 // Bookkeeping after the line search of one trajectory (stopping rule :472), executed by its 4-lane group.
@@ -356,7 +437,7 @@ __device__ __forceinline__ bool qd_finalize4(int g, int b, int idx, double cur, 
 
 // MODE 0: the whole alpha list sequentially with early exit (single launch, no workspace).
 // MODE 1: phase A of the staged search: alpha = 1 only; rejected trajectories are queued.
-template <int MODE>
+template <int MODE, int INTEG>
 __global__ void __launch_bounds__(128)
 ls_qd_phaseA_kernel(const __grid_constant__ QxParams p, double* __restrict__ x_in, double* __restrict__ u_in,
                     const float* __restrict__ gains, double* __restrict__ cost, int32_t* __restrict__ status,
@@ -377,7 +458,7 @@ ls_qd_phaseA_kernel(const __grid_constant__ QxParams p, double* __restrict__ x_i
     for (int a = 0; a < n_alpha; ++a) {
       if (!__any_sync(FULL, !accepted)) break;
       const bool run = !accepted;
-      const double cst = qd_candidate(c, run, x_in, u_in, gains, b, kAlphas[a], x_out, u_out, b, B, N);
+      const double cst = qd_candidate<INTEG>(c, run, x_in, u_in, gains, b, kAlphas[a], x_out, u_out, b, B, N);
       if (run && cst <= cur) {       // first accepted alpha, "<=" (quattro_ilqr_tf.py:444)
         accepted = true;
         idx = a;
@@ -401,27 +482,36 @@ ls_qd_phaseA_kernel(const __grid_constant__ QxParams p, double* __restrict__ x_i
   if (lane == 0 && n_active != nullptr && act != 0u) atomicAdd(n_active, __popc(act));
 }
 
-// Phase B: every queued trajectory x every alpha of the stage is one 4-lane work item (alpha-major, so the
-// eight groups of a warp share the alpha and work on neighbouring trajectories).
+// Phase B: one 4-lane work item per queued trajectory; the NA alphas of the stage are rolled out interleaved.
+template <int INTEG, int NA>
 __global__ void __launch_bounds__(128)
 ls_qd_phaseB_kernel(const __grid_constant__ QxParams p, const double* __restrict__ x_in, const double* __restrict__ u_in,
                     const float* __restrict__ gains, const int32_t* __restrict__ queue, const int32_t* __restrict__ nq_ptr,
-                    QdWork ws, int a_first, int n_alpha, int B, int N) {
+                    QdWork ws, int a_first, int B, int N) {
   constexpr int n = 12, m = 4;
   const int lane = threadIdx.x & 31;
   const int nq = *nq_ptr;
-  const long item = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-  const bool run = item < (long)n_alpha * nq;
+  const int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const bool run = item < nq;
   if (!__any_sync(FULL, run)) return;
   QdLane c;
   qd_lane_init(p, lane, c);
-  const int a = run ? (int)(item / nq) : 0;
-  const int b = run ? queue[item % nq] : 0;
-  const int plane = a_first + a - 1;
-  double* xd = ws.xs + (size_t)plane * (N + 1) * n * B;
-  double* ud = ws.us + (size_t)plane * N * m * B;
-  const double cst = qd_candidate(c, run, x_in, u_in, gains, b, kAlphas[a_first + a], xd, ud, b, B, N);
-  if (run && c.g == 0) ws.cand[(size_t)plane * B + b] = cst;
+  const int b = run ? queue[item] : 0;
+  double al[NA], cst[NA];
+  double* xd[NA];
+  double* ud[NA];
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+    const int plane = a_first + a - 1;
+    al[a] = kAlphas[a_first + a];
+    xd[a] = ws.xs + (size_t)plane * (N + 1) * n * B;
+    ud[a] = ws.us + (size_t)plane * N * m * B;
+  }
+  qd_candidates<INTEG, NA>(c, run, x_in, u_in, gains, b, al, xd, ud, b, B, N, cst);
+  if (run && c.g == 0) {
+#pragma unroll
+    for (int a = 0; a < NA; ++a) ws.cand[(size_t)(a_first + a - 1) * B + b] = cst[a];
+  }
 }
 
 // Phase C: one thread per trajectory (coalesced rows).  A pending trajectory takes the first accepted alpha of
@@ -455,24 +545,41 @@ ls_qd_phaseC_kernel(double* __restrict__ x_in, double* __restrict__ u_in, double
     const int xrows = (N + 1) * n, rows = xrows + N * m;
     const int per = (rows + (int)gridDim.y - 1) / (int)gridDim.y;
     const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+    // one source / up to two destinations per row, loads batched eight deep to keep HBM busy
+    const double* xsrc = nullptr;
+    const double* usrc = nullptr;
+    double *xd0 = nullptr, *ud0 = nullptr, *xd1 = nullptr, *ud1 = nullptr;
     if (found) {
-      const double* xsrc = ws.xs + (size_t)(idx - 1) * xrows * B;
-      const double* usrc = ws.us + (size_t)(idx - 1) * (N * m) * B;
-#pragma unroll 4
-      for (int r = r0; r < r1; ++r) {
-        const double v = (r < xrows) ? xsrc[(size_t)r * B + b] : usrc[(size_t)(r - xrows) * B + b];
-        double* d0 = (r < xrows) ? &x_out[(size_t)r * B + b] : &u_out[(size_t)(r - xrows) * B + b];
-        *d0 = v;
-        if (done) {        // finished: the final iterate also goes to the other buffer
-          double* d1 = (r < xrows) ? &x_in[(size_t)r * B + b] : &u_in[(size_t)(r - xrows) * B + b];
-          *d1 = v;
+      xsrc = ws.xs + (size_t)(idx - 1) * xrows * B;
+      usrc = ws.us + (size_t)(idx - 1) * (N * m) * B;
+      xd0 = x_out; ud0 = u_out;
+      if (done) { xd1 = x_in; ud1 = u_in; }     // finished: the final iterate also goes to the other buffer
+    } else if (FINAL) {                          // no alpha accepted: keep the nominal
+      xsrc = x_in; usrc = u_in;
+      xd0 = x_out; ud0 = u_out;
+    }
+    if (xsrc != nullptr) {
+      constexpr int U = 8;
+      for (int r = r0; r < r1; r += U) {
+        double v[U];
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+          const int rr = r + q;
+          if (rr < r1) v[q] = (rr < xrows) ? xsrc[(size_t)rr * B + b] : usrc[(size_t)(rr - xrows) * B + b];
         }
-      }
-    } else if (FINAL) {    // no alpha accepted: keep the nominal
-#pragma unroll 4
-      for (int r = r0; r < r1; ++r) {
-        if (r < xrows) x_out[(size_t)r * B + b] = x_in[(size_t)r * B + b];
-        else u_out[(size_t)(r - xrows) * B + b] = u_in[(size_t)(r - xrows) * B + b];
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+          const int rr = r + q;
+          if (rr < r1) {
+            if (rr < xrows) {
+              xd0[(size_t)rr * B + b] = v[q];
+              if (xd1 != nullptr) xd1[(size_t)rr * B + b] = v[q];
+            } else {
+              ud0[(size_t)(rr - xrows) * B + b] = v[q];
+              if (ud1 != nullptr) ud1[(size_t)(rr - xrows) * B + b] = v[q];
+            }
+          }
+        }
       }
     }
   }
@@ -496,19 +603,23 @@ ls_qd_phaseC_kernel(double* __restrict__ x_in, double* __restrict__ u_in, double
 // ---- host side: called by qx_rollout_cost / qx_linesearch (qx_rollout.cu) for the quadrotor with diagonal weights
 int qd_launch_rollout(const QxParams* p, const double* x0, const double* u, double* x, double* cost,
                       const int32_t* status, int B, int N, cudaStream_t st) {
-  rollout_qd_kernel<<<ceil_div(4 * B, 128), 128, 0, st>>>(*p, x0, u, x, cost, status, B, N);
+  if (p->integrator == QX_EULER)
+    rollout_qd_kernel<QX_EULER><<<ceil_div(4 * B, 128), 128, 0, st>>>(*p, x0, u, x, cost, status, B, N);
+  else
+    rollout_qd_kernel<QX_RK4><<<ceil_div(4 * B, 128), 128, 0, st>>>(*p, x0, u, x, cost, status, B, N);
   QX_CHECK_LAUNCH("rollout_qd_kernel");
   return QX_OK;
 }
 
-int qd_launch_linesearch(const QxParams* p, double* x_in, double* u_in, const float* gains, double* cost,
-                         int32_t* status, int32_t* iters, int32_t* alpha, double* x_out, double* u_out,
-                         int32_t* n_active, void* workspace, double tol, uint32_t flags, int B, int N,
-                         cudaStream_t st) {
+template <int INTEG>
+static int qd_linesearch_t(const QxParams* p, double* x_in, double* u_in, const float* gains, double* cost,
+                           int32_t* status, int32_t* iters, int32_t* alpha, double* x_out, double* u_out,
+                           int32_t* n_active, void* workspace, double tol, uint32_t flags, int B, int N,
+                           cudaStream_t st) {
   const int grid = ceil_div(4 * B, 128);
   if (workspace == nullptr) {   // single launch, alphas tried one after the other
-    ls_qd_phaseA_kernel<0><<<grid, 128, 0, st>>>(*p, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out,
-                                                 n_active, QdWork{}, tol, flags, B, N);
+    ls_qd_phaseA_kernel<0, INTEG><<<grid, 128, 0, st>>>(*p, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out,
+                                                        n_active, QdWork{}, tol, flags, B, N);
     QX_CHECK_LAUNCH("ls_qd_phaseA_kernel<0>");
     return QX_OK;
   }
@@ -516,23 +627,34 @@ int qd_launch_linesearch(const QxParams* p, double* x_in, double* u_in, const fl
   const QdWork ws = qd_carve(workspace, B, N);
   cudaError_t e = cudaMemsetAsync(ws.ctl, 0, 32, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(ctl)");
-  ls_qd_phaseA_kernel<1><<<grid, 128, 0, st>>>(*p, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out, n_active,
-                                               ws, tol, flags, B, N);
+  ls_qd_phaseA_kernel<1, INTEG><<<grid, 128, 0, st>>>(*p, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out,
+                                                      n_active, ws, tol, flags, B, N);
   QX_CHECK_LAUNCH("ls_qd_phaseA_kernel<1>");
-  const dim3 gridC(ceil_div(B, 128), 8);
+  const dim3 gridC(ceil_div(B, 128), 16);
   // stage 1: alpha = .5, .25
-  ls_qd_phaseB_kernel<<<ceil_div(4 * 2 * B, 128), 128, 0, st>>>(*p, x_in, u_in, gains, ws.queue1, &ws.ctl[0], ws, 1, 2, B, N);
+  ls_qd_phaseB_kernel<INTEG, 2><<<grid, 128, 0, st>>>(*p, x_in, u_in, gains, ws.queue1, &ws.ctl[0], ws, 1, B, N);
   QX_CHECK_LAUNCH("ls_qd_phaseB_kernel<1>");
   ls_qd_phaseC_kernel<false><<<gridC, 128, 0, st>>>(x_in, u_in, cost, status, iters, alpha, x_out, u_out, n_active, ws,
                                                     ws.pend1, ws.pend2, ws.queue2, &ws.ctl[1], 1, 2, tol, flags, B, N);
   QX_CHECK_LAUNCH("ls_qd_phaseC_kernel<false>");
   // stage 2: alpha = .1, .05, .01
-  ls_qd_phaseB_kernel<<<ceil_div(4 * 3 * B, 128), 128, 0, st>>>(*p, x_in, u_in, gains, ws.queue2, &ws.ctl[1], ws, 3, 3, B, N);
+  ls_qd_phaseB_kernel<INTEG, 3><<<grid, 128, 0, st>>>(*p, x_in, u_in, gains, ws.queue2, &ws.ctl[1], ws, 3, B, N);
   QX_CHECK_LAUNCH("ls_qd_phaseB_kernel<2>");
   ls_qd_phaseC_kernel<true><<<gridC, 128, 0, st>>>(x_in, u_in, cost, status, iters, alpha, x_out, u_out, n_active, ws,
                                                    ws.pend2, nullptr, nullptr, nullptr, 3, 3, tol, flags, B, N);
   QX_CHECK_LAUNCH("ls_qd_phaseC_kernel<true>");
   return QX_OK;
+}
+
+int qd_launch_linesearch(const QxParams* p, double* x_in, double* u_in, const float* gains, double* cost,
+                         int32_t* status, int32_t* iters, int32_t* alpha, double* x_out, double* u_out,
+                         int32_t* n_active, void* workspace, double tol, uint32_t flags, int B, int N,
+                         cudaStream_t st) {
+  if (p->integrator == QX_EULER)
+    return qd_linesearch_t<QX_EULER>(p, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out, n_active, workspace,
+                                     tol, flags, B, N, st);
+  return qd_linesearch_t<QX_RK4>(p, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out, n_active, workspace, tol,
+                                 flags, B, N, st);
 }
 
 }  // namespace qx
