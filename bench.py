@@ -49,6 +49,11 @@ ALGO_BYTES = {
 # x,u are kept in fp64 on the device: their share of the figures above doubles
 FP64_EXTRA = {"quadrotor": {"linearize": 3248, "riccati": 0, "linesearch": 3248 + 3276, "rollout": 3300},
               "cartpole": {"linearize": 616, "riccati": 0, "linesearch": 616 + 620, "rollout": 636}}
+# Block path (quadrotor, Euler, diagonal weights; include/quattro_b200.h QX_LAYOUT_BLK): the expansion is 64
+# floats per (t, b) instead of 416 and the terminal 16 floats, so the algorithmic traffic of the backward pass is
+#   linearise: read x,u fp64 6 496 B + write 50 x 256 + 64 B            = 19 360 B per trajectory
+#   Riccati  : read 50 x 256 + 64 B      + write gains 50 x 208 B       = 23 264 B per trajectory
+BLK_BYTES = {"linearize": 6496 + 50 * 256 + 64, "riccati": 50 * 256 + 64 + 50 * 208}
 
 
 def peaks():
@@ -80,7 +85,7 @@ def cpu_cores():
 
 def cpu_reference(system, steps, warmup, iters_per_step=1):
     """Each step: every host core runs `iters_per_step` iLQR iterations of one trajectory."""
-    from oracle.models import sample_x0
+    from quattro_transformer_ilqr_b200.sampling import sample_x0
     cores = cpu_cores()
     x0 = sample_x0(system, cores, seed=0)
     with mp.get_context("fork").Pool(cores) as pool:
@@ -135,7 +140,7 @@ def gpu_bench(args):
     import torch
     import torch.distributed as dist
     import __graft_entry__ as graft
-    from oracle.models import sample_x0                      # input distribution only
+    from quattro_transformer_ilqr_b200.sampling import sample_x0
     from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel, TransformerILQR, TransformerPredictor
 
     rank = int(os.environ.get("RANK", 0))
@@ -211,7 +216,7 @@ def gpu_bench(args):
     value = world * B * args.steps / (ms * 1e-3)
     if args.skip_extras:        # profiling runs (ncu): the timed loop only
         if rank == 0:
-            print(json.dumps({"value": value, "ms_per_step": ms / args.steps, "gpu_launches": launches, "clocks": clocks}))
+            args.emit(json.dumps({"value": value, "ms_per_step": ms / args.steps, "gpu_launches": launches, "clocks": clocks}))
         if world > 1:
             dist.destroy_process_group()
         return
@@ -265,12 +270,16 @@ def gpu_bench(args):
                 for q, k in enumerate(names):
                     acc[k].append(evs[q].elapsed_time(evs[q + 1]))
         hbm, how = peaks()
+        from quattro_transformer_ilqr_b200 import _lib as qlib
+        blk = eng.exp_layout == qlib.QX_LAYOUT_BLK
         for k in names:
             ms_k = float(np.mean(acc[k]))
             entry = {"ms": round(ms_k, 4)}
             if k in ALGO_BYTES[system]:
                 frac_T = (N - (0 if tf is None else N - tf.prompt_len)) / N if k in ("linearize", "riccati") and use_tf else 1.0
                 by = (ALGO_BYTES[system][k] + FP64_EXTRA[system][k]) * frac_T
+                if blk and k in BLK_BYTES:
+                    by = BLK_BYTES[k] * frac_T
                 gbs = by * B / (ms_k * 1e-3) / 1e9
                 entry.update({"algo_bytes_per_traj": by, "GBps": round(gbs, 1), "frac_hbm": round(gbs / hbm, 4)})
             kernels[k] = entry
@@ -294,13 +303,15 @@ def gpu_bench(args):
         "config": {"workload": f"{args.workload}: {system} n={n} m={m} horizon={N}, {B} trajectories per GPU, "
                                f"fixed-iteration mode, problem reset every {RESET_EVERY} steps",
                    "global_batch": world * B, "parallelism": f"dp{world} (independent trajectory shards)",
-                   "l2": "inputs larger than L2 (1.36 GB expansion buffer per pass)"},
+                   "backward_pass": "block records (64 floats per step)" if eng.exp_layout == 2 else "dense records",
+                   "l2": "working set per iteration (x, u ping-pong 0.21 GB + expansion 0.21 GB + gains 0.17 GB + "
+                         "line-search scratch up to 0.53 GB at 16 384 trajectories) larger than the 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "trajectory-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
         "cpu_baseline": {"value": cpu_val, "unit": "trajectory-iterations/s", "cores": cores, "kind": "port", "sample": sample},
     }
-    print(json.dumps(out))
+    args.emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -313,7 +324,7 @@ def reference_arm(args):
     t0 = time.perf_counter()
     val, cores, step_s, sample = cpu_reference(system, args.steps, args.warmup)
     n, m = (12, 4) if system == "quadrotor" else (4, 1)
-    print(json.dumps({
+    args.emit(json.dumps({
         "impl": "reference",
         "metric": "batched iLQR trajectory-iterations/sec (quadrotor, horizon 50)" if system == "quadrotor"
         else "batched iLQR trajectory-iterations/sec (cart-pole, horizon 30)",
@@ -328,6 +339,19 @@ def reference_arm(args):
     }))
 
 
+def _json_only_stdout():
+    """Route everything libraries print on fd 1 (NCCL's version banner, ...) to stderr; return a writer for
+    the one JSON line the driver reads from stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(line):
+        real.write(line + "\n")
+        real.flush()
+    return emit
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -338,6 +362,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--skip-extras", action="store_true", help="timed loop only (for ncu): no e2e / per-kernel / CPU legs")
     args = ap.parse_args()
+    args.emit = _json_only_stdout()
     if args.impl == "reference":
         reference_arm(args)
     else:

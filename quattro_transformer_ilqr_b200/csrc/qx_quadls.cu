@@ -483,8 +483,10 @@ ls_qd_phaseA_kernel(const __grid_constant__ QxParams p, double* __restrict__ x_i
 }
 
 // Phase B: one 4-lane work item per queued trajectory; the NA alphas of the stage are rolled out interleaved.
+// One-warp CTAs: the kernel needs ~170-220 registers and no CTA-level cooperation, and registers are
+// allocated per CTA - small CTAs waste the fewest.
 template <int INTEG, int NA>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32)
 ls_qd_phaseB_kernel(const __grid_constant__ QxParams p, const double* __restrict__ x_in, const double* __restrict__ u_in,
                     const float* __restrict__ gains, const int32_t* __restrict__ queue, const int32_t* __restrict__ nq_ptr,
                     QdWork ws, int a_first, int B, int N) {
@@ -632,13 +634,13 @@ static int qd_linesearch_t(const QxParams* p, double* x_in, double* u_in, const 
   QX_CHECK_LAUNCH("ls_qd_phaseA_kernel<1>");
   const dim3 gridC(ceil_div(B, 128), 16);
   // stage 1: alpha = .5, .25
-  ls_qd_phaseB_kernel<INTEG, 2><<<grid, 128, 0, st>>>(*p, x_in, u_in, gains, ws.queue1, &ws.ctl[0], ws, 1, B, N);
+  ls_qd_phaseB_kernel<INTEG, 2><<<ceil_div(4 * B, 32), 32, 0, st>>>(*p, x_in, u_in, gains, ws.queue1, &ws.ctl[0], ws, 1, B, N);
   QX_CHECK_LAUNCH("ls_qd_phaseB_kernel<1>");
   ls_qd_phaseC_kernel<false><<<gridC, 128, 0, st>>>(x_in, u_in, cost, status, iters, alpha, x_out, u_out, n_active, ws,
                                                     ws.pend1, ws.pend2, ws.queue2, &ws.ctl[1], 1, 2, tol, flags, B, N);
   QX_CHECK_LAUNCH("ls_qd_phaseC_kernel<false>");
   // stage 2: alpha = .1, .05, .01
-  ls_qd_phaseB_kernel<INTEG, 3><<<grid, 128, 0, st>>>(*p, x_in, u_in, gains, ws.queue2, &ws.ctl[1], ws, 3, B, N);
+  ls_qd_phaseB_kernel<INTEG, 3><<<ceil_div(4 * B, 32), 32, 0, st>>>(*p, x_in, u_in, gains, ws.queue2, &ws.ctl[1], ws, 3, B, N);
   QX_CHECK_LAUNCH("ls_qd_phaseB_kernel<2>");
   ls_qd_phaseC_kernel<true><<<gridC, 128, 0, st>>>(x_in, u_in, cost, status, iters, alpha, x_out, u_out, n_active, ws,
                                                    ws.pend2, nullptr, nullptr, nullptr, 3, 3, tol, flags, B, N);
