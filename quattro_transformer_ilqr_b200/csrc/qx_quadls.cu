@@ -483,10 +483,10 @@ ls_qd_phaseA_kernel(const __grid_constant__ QxParams p, double* __restrict__ x_i
 }
 
 // Phase B: one 4-lane work item per queued trajectory; the NA alphas of the stage are rolled out interleaved.
-// One-warp CTAs: the kernel needs ~170-220 registers and no CTA-level cooperation, and registers are
-// allocated per CTA - small CTAs waste the fewest.
+// One-warp CTAs, at most 168 registers: the register file is 4 x 16 K per SM (one slice per scheduler), so 168
+// registers x 32 lanes lets three warps share a scheduler where 178 would leave two.
 template <int INTEG, int NA>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, 12)
 ls_qd_phaseB_kernel(const __grid_constant__ QxParams p, const double* __restrict__ x_in, const double* __restrict__ u_in,
                     const float* __restrict__ gains, const int32_t* __restrict__ queue, const int32_t* __restrict__ nq_ptr,
                     QdWork ws, int a_first, int B, int N) {

@@ -1,0 +1,42 @@
+#!/usr/bin/env python3
+"""Summarise an .ncu-rep (raw page) into the text kept under profiles/: one block per captured launch.
+
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep "<command line that was profiled>" > profiles/rN_....txt
+"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+    "launch__block_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "lts__t_sector_hit_rate.pct",
+]
+
+
+def main():
+    rep, cmd = sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else ""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    print(cmd)
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        print("-----")
+        print(d["Kernel Name"][:150])
+        for k in KEYS:
+            if k in d and d[k] != "":
+                print(f"  {k:72s} {d[k]} {units[hdr.index(k)]}")
+
+
+if __name__ == "__main__":
+    main()
