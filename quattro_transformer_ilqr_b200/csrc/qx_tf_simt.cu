@@ -249,6 +249,7 @@ static int gemm(const float* A, const float* W, const float* bias, float* C, int
 }
 
 // tensor-core GEMM (qx_tf_tc.cu)
+int tf_attention_tc(const float* qkv, float* out, int B, int L, int d, int nhead, cudaStream_t st);   // qx_tf_attn.cu
 int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* bias, float* C, int M, int N, int K,
                bool relu, cudaStream_t st);
 int tf_split_weights(const float* w, float* hi, float* lo, size_t count, cudaStream_t st);
@@ -305,8 +306,14 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
     const float* lw = w + lay.layer0 + (size_t)l * lay.layer_stride;
     int rc = dense(h, lw, lay.l_inw, lay.l_inb, sp.in_hi, sp.in_lo, l, qkv, 3 * d, d, false);
     if (rc) return rc;
-    tf_attention_kernel<32><<<dim3(cfg->nhead, B), 128, att_smem, st>>>(qkv, att, L, d);
-    QX_CHECK_LAUNCH("tf_attention_kernel");
+    // tensor-core path: attention on mma.sync 3xTF32 tiles (qx_tf_attn.cu) when the shape fits, else SIMT
+    rc = (wsplit != nullptr) ? tf_attention_tc(qkv, att, B, L, d, cfg->nhead, st) : QX_EUNSUPPORTED;
+    if (rc == QX_EUNSUPPORTED) {
+      tf_attention_kernel<32><<<dim3(cfg->nhead, B), 128, att_smem, st>>>(qkv, att, L, d);
+      QX_CHECK_LAUNCH("tf_attention_kernel");
+    } else if (rc) {
+      return rc;
+    }
     if ((rc = dense(att, lw, lay.l_outw, lay.l_outb, sp.out_hi, sp.out_lo, l, y, d, d, false))) return rc;
     tf_add_ln_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(h, y, lw + lay.l_n1w, lw + lay.l_n1b, rows);
     QX_CHECK_LAUNCH("tf_add_ln_kernel");

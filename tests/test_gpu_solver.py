@@ -158,6 +158,30 @@ def test_full_size_properties():
     assert relmax(u_now[idx], ref["u"]) < 1e-3
 
 
+def test_streamed_host_batch_equals_single_engine():
+    """StreamedILQR (slices on their own streams, pinned host buffers in and out) returns bit-identical results to
+    one engine over the whole batch, for ragged slice sizes too."""
+    from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel
+    from quattro_transformer_ilqr_b200.pipeline import StreamedILQR
+    B, N = 1003, 50
+    x0 = torch.as_tensor(sample_x0("quadrotor", B, seed=9)).pin_memory()
+    u0 = torch.zeros((B, N, 4), dtype=torch.float64).pin_memory()
+    u_out = torch.empty((B, N, 4), dtype=torch.float64).pin_memory()
+    x_out = torch.empty((B, N + 1, 12), dtype=torch.float64).pin_memory()
+    c_out = torch.empty(B, dtype=torch.float64).pin_memory()
+    pipe = StreamedILQR(DeviceModel("quadrotor"), B, N, chunks=3)
+    for _ in range(2):                       # second call re-uses the engines
+        pipe.run(x0, u0, u_out, x_out, c_out, iters=5, tol=1e-3, force=True)
+        pipe.synchronize()
+    e = BatchedILQR(DeviceModel("quadrotor"), B, N)
+    e.set_problem(x0, u0)
+    e.solve(fixed_iters=5)
+    assert torch.equal(u_out, e.u_batch().cpu()) and torch.equal(x_out, e.x_batch().cpu())
+    assert torch.equal(c_out, e.cost.cpu())
+    with pytest.raises(ValueError):
+        StreamedILQR(DeviceModel("quadrotor"), 4, N, chunks=5)
+
+
 # ---------------------------------------------------------------------------- transformer mode
 def _wrapper(system, mode):
     from quattro_transformer_ilqr_b200 import TransformerILQR, TransformerPredictor
