@@ -294,6 +294,22 @@ def gpu_bench(args):
                 entry.update({"algo_bytes_per_traj": by, "GBps": round(gbs, 1), "frac_hbm": round(gbs / hbm, 4)})
             kernels[k] = entry
 
+    # ---- run-to-convergence mode: one full solve with the reference's stopping rule, rank 0 ----------
+    converge = None
+    if rank == 0:
+        eng.set_problem(x0_d, u0_d)
+        torch.cuda.synchronize(dev)
+        ev0.record()
+        batch_iters = eng.solve(max_iter=100, tol=tol, check_every=4)
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        ms_c = ev0.elapsed_time(ev1)
+        done = int(eng.iters.sum().item())
+        converge = {"value": done / (ms_c * 1e-3), "unit": "trajectory-iterations/s", "ms": round(ms_c, 3),
+                    "trajectory_iterations": done, "batch_iterations": batch_iters,
+                    "finished": int((eng.status != 0).sum().item()),
+                    "note": "one solve to convergence (tol of the reference driver), active set checked every 4 iterations"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -318,7 +334,7 @@ def gpu_bench(args):
                          "line-search scratch up to 0.53 GB at 16 384 trajectories) larger than the 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "trajectory-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "pipeline": f"{chunks} slices on {chunks} streams" if chunks > 1 else "single stream"},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels, "converge": converge,
         "cpu_baseline": {"value": cpu_val, "unit": "trajectory-iterations/s", "cores": cores, "kind": "port", "sample": sample},
     }
     args.emit(json.dumps(out))
