@@ -181,6 +181,37 @@ class BatchedILQR:
                 break
         return done
 
+    # ------------------------------------------------------------------ receding horizon, device resident
+    def advance_receding_horizon(self, x_next=None):
+        """One MPC shift without leaving the device: what ``control_step`` does on the host after ``optimize``
+        (cartpole_mpc.py:326-332, quadrotor_mpc.py:115-122) - x0 <- the next plant state, u <- u[1:] + [u[-1]] -
+        followed by the nominal rollout of the shifted controls.  ``x_next`` (n, B) device tensor is the measured
+        state; by default the model's own prediction x_1 of the current solution is used (plant == model).
+        Returns the control that was applied, u_0 of the solution, as an (m, B) tensor."""
+        c = self.cur
+        u_applied = self.u[c][0].clone()
+        self.x0.copy_(self.x[c][1] if x_next is None else x_next)
+        self.u[c][:-1] = self.u[c][1:].clone()          # the last row keeps u[-1]
+        self.status.zero_()
+        self.iters.zero_()
+        self.alpha.fill_(-1)
+        self.rollout()
+        return u_applied
+
+    def mpc_sweep(self, x0, u_init, steps, max_iter=100, tol=1e-3, fixed_iters=None, check_every=4):
+        """Closed-loop sweep of B independent MPC instances (BASELINE config 5): ``steps`` control steps, each a
+        solve from the warm start of the previous one, the plant being the model itself.  Only the per-iteration
+        active counter crosses PCIe.  Returns (u_applied (steps, m, B), x_visited (steps + 1, n, B)) on the device."""
+        self.set_problem(x0, u_init)
+        us = torch.empty((steps, self.m, self.B), dtype=torch.float64, device=self.device)
+        xs = torch.empty((steps + 1, self.n, self.B), dtype=torch.float64, device=self.device)
+        xs[0] = self.x0
+        for s in range(steps):
+            self.solve(max_iter=max_iter, tol=tol, fixed_iters=fixed_iters, check_every=check_every)
+            us[s] = self.advance_receding_horizon()
+            xs[s + 1] = self.x0
+        return us, xs
+
     # ------------------------------------------------------------------ views in the user layout
     def u_batch(self):
         return self.u[self.cur].permute(2, 0, 1).contiguous()          # (B, N, m)

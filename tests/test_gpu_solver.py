@@ -158,6 +158,24 @@ def test_full_size_properties():
     assert relmax(u_now[idx], ref["u"]) < 1e-3
 
 
+def test_device_resident_mpc_sweep_equals_host_loop():
+    """mpc_sweep (shift + x0 update on the device) reproduces the host-driven control_step loop bit for bit."""
+    from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel
+    from quattro_transformer_ilqr_b200.mpc import QuadrotorMPC
+    B, N, steps = 6, 50, 3
+    x0 = sample_x0("quadrotor", B, seed=13)
+    eng = BatchedILQR(DeviceModel("quadrotor"), B, N)
+    us, xs = eng.mpc_sweep(x0, np.zeros((B, N, 4)), steps, check_every=1)
+    host = QuadrotorMPC(horizon=N, integration_method="euler", batch=B)
+    host.ilqr.enable_log = False
+    x = x0.copy()
+    for s in range(steps):
+        x_seq, u_seq = host.control_step(x)
+        assert np.array_equal(us[s].t().cpu().numpy(), u_seq[:, 0])
+        x = x_seq[:, 1]                                   # plant == model
+        assert np.array_equal(xs[s + 1].t().cpu().numpy(), x)
+
+
 def test_streamed_host_batch_equals_single_engine():
     """StreamedILQR (slices on their own streams, pinned host buffers in and out) returns bit-identical results to
     one engine over the whole batch, for ragged slice sizes too."""
