@@ -64,6 +64,39 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_reference(kernel, blk, system):
+    """DRAM traffic and pipe utilisation of the dominant kernel from the committed `ncu --set full` summary of the
+    same workload (profiles/): counters cannot be read live, the launch duration is (CUDA events, above)."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_full_classic_summary.txt")
+    sym = {("riccati", True): "riccati_quad_blk_kernel", ("linearize", True): "linearize_quad_blk_kernel"}.get((kernel, blk))
+    if system != "quadrotor" or sym is None or not os.path.exists(path):
+        return None
+    vals, inside = {}, False
+    for line in open(path):
+        if line.startswith("-----"):
+            inside = False
+        elif line.startswith(sym) or (" " + sym) in line[:80]:
+            inside = True
+        elif inside and line.startswith("  "):
+            parts = line.split()
+            if len(parts) >= 2:
+                try:
+                    vals[parts[0]] = (float(parts[1]), parts[2] if len(parts) > 2 else "")
+                except ValueError:
+                    pass
+    if "dram__bytes_read.sum" not in vals:
+        return None
+    scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+
+    def byt(k):
+        v, u = vals[k]
+        return v * scale.get(u, 1.0)
+    return {"source": "profiles/r1_ncu_full_classic_summary.txt", "traffic": byt("dram__bytes_read.sum") + byt("dram__bytes_write.sum"),
+            "fma_pipe_pct": vals.get("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", (None,))[0],
+            "issue_active_pct": vals.get("smsp__issue_active.avg.pct_of_peak_sustained_active", (None,))[0],
+            "dram_pct": vals.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", (None,))[0]}
+
+
 # ------------------------------------------------------------------------------- CPU reference arm
 def _cpu_worker(args):
     system, x0, iters = args
@@ -314,11 +347,20 @@ def gpu_bench(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    dom = max((k for k in kernels if "GBps" in kernels[k]), key=lambda k: kernels[k]["ms"])
+    # dominant KERNEL = the longest single launch: linearise and Riccati are one launch each, the line search is
+    # five (stages A, B1, C1, B2, C2; 0.04-0.2 ms each), so it is reported in `kernels` but is not "a kernel"
+    single = [k for k in kernels if "GBps" in kernels[k] and k != "linesearch"] or [k for k in kernels if "GBps" in kernels[k]]
+    dom = max(single, key=lambda k: kernels[k]["ms"])
     hbm, how = peaks()
+    ncu = ncu_reference(dom, blk, system) if B == WORKLOADS[args.workload][2] else None
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["GBps"], "peak": hbm, "unit": "GB/s",
-                "frac": kernels[dom]["frac_hbm"], "traffic": None, "peak_source": how,
+                "frac": kernels[dom]["frac_hbm"], "traffic": ncu["traffic"] if ncu else None, "peak_source": how,
                 "algo_bytes_per_launch": kernels[dom]["algo_bytes_per_traj"] * B}
+    if ncu:
+        roofline["ncu"] = ncu
+    if dom == "riccati":
+        roofline["note"] = ("the recursion is bound by fp32 instruction issue / the FMA pipe, not by HBM (SURVEY 8d asks for "
+                            "both figures): see ncu.fma_pipe_pct and ncu.issue_active_pct")
     cpu_val, cores, _, sample = cpu_reference(system, steps=2, warmup=1, iters_per_step=2)
     out = {
         "metric": "batched iLQR trajectory-iterations/sec (quadrotor, horizon 50)" if system == "quadrotor"
