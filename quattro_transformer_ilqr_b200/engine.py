@@ -149,7 +149,8 @@ class BatchedILQR:
                                             float(alpha), _ptr(self.x[1 - c]), _ptr(self.u[1 - c]), _ptr(cost),
                                             self.B, self.N, self.stream), "qx_forward_pass")
         self.launches += 1
-        return (self.x[1 - c].permute(2, 0, 1).contiguous(), self.u[1 - c].permute(2, 0, 1).contiguous(), cost)
+        return (self.x[1 - c].permute(2, 0, 1).clone(memory_format=torch.contiguous_format),
+                self.u[1 - c].permute(2, 0, 1).clone(memory_format=torch.contiguous_format), cost)
 
     def backward(self):
         """Gains for the whole horizon: Riccati, or Riccati tail + transformer head."""
@@ -213,11 +214,13 @@ class BatchedILQR:
         return us, xs
 
     # ------------------------------------------------------------------ views in the user layout
+    # (always fresh copies: for B == 1 ``.contiguous()`` on the permuted view would alias the live ping-pong buffer,
+    # which the next line search overwrites)
     def u_batch(self):
-        return self.u[self.cur].permute(2, 0, 1).contiguous()          # (B, N, m)
+        return self.u[self.cur].permute(2, 0, 1).clone(memory_format=torch.contiguous_format)          # (B, N, m)
 
     def x_batch(self):
-        return self.x[self.cur].permute(2, 0, 1).contiguous()          # (B, N+1, n)
+        return self.x[self.cur].permute(2, 0, 1).clone(memory_format=torch.contiguous_format)          # (B, N+1, n)
 
     def gains_batch(self):
         """K (B, N, m, n), k (B, N, m) as float32 tensors."""
@@ -227,7 +230,8 @@ class BatchedILQR:
             g = self.gains.view(N, B, G).permute(1, 0, 2)
         else:
             g = self.gains.view(N, G, B).permute(2, 0, 1)
-        return g[..., m:].reshape(B, N, m, n).contiguous(), g[..., :m].contiguous()
+        return (g[..., m:].reshape(B, N, m, n).clone(memory_format=torch.contiguous_format),
+                g[..., :m].clone(memory_format=torch.contiguous_format))
 
     def load_gains(self, K, k):
         """Upload gains given as K (B, N, m, n), k (B, N, m) into the device record layout."""

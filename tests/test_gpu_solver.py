@@ -176,6 +176,26 @@ def test_device_resident_mpc_sweep_equals_host_loop():
         assert np.array_equal(xs[s + 1].t().cpu().numpy(), x)
 
 
+def test_batched_logs_equal_single_trajectory_logs():
+    """Training-set wire format: the entries cut out of a batched solve's logs equal the logs the B = 1 API
+    (the reference's data-collection path) writes for the same initial state."""
+    from quattro_transformer_ilqr_b200 import datasets
+    from quattro_transformer_ilqr_b200.mpc import CartPoleMPC
+    x0 = sample_x0("cartpole", 4, seed=5)
+    mb = CartPoleMPC(horizon=30, dt=0.01, integration_method="euler", ilqr_only=True, batch=4)
+    mb.control_step(x0)
+    entries = [e for e in datasets.split_batched_logs(mb.ilqr.logs)]
+    ms = CartPoleMPC(horizon=30, dt=0.01, integration_method="euler", ilqr_only=True)
+    ms.control_step(x0[2])
+    mine = entries[sum(int(mb.ilqr.total_iter[b]) + 1 for b in range(2)):][:len(ms.ilqr.logs)]
+    assert len(mine) == len(ms.ilqr.logs) == int(mb.ilqr.total_iter[2]) + 1
+    for a, b in zip(mine, ms.ilqr.logs):
+        assert set(a) == set(b)
+        assert a["iteration"] == b["iteration"] and a["alpha"] == b["alpha"] and a["found_update"] == b["found_update"]
+        assert a["current_cost"] == b["current_cost"] and np.array_equal(a["x_seq"], b["x_seq"])
+        assert np.array_equal(np.array(a["K_seq"]), np.array(b["K_seq"])) and np.array_equal(np.array(a["u_seq"]), np.array(b["u_seq"]))
+
+
 def test_streamed_host_batch_equals_single_engine():
     """StreamedILQR (slices on their own streams, pinned host buffers in and out) returns bit-identical results to
     one engine over the whole batch, for ragged slice sizes too."""

@@ -58,3 +58,36 @@ def test_sharded_solve_equals_unsharded(tmp_path, world, total):
     assert np.array_equal(got["cost"], ref["cost"])          # no cross-trajectory arithmetic: bit-identical
     assert np.array_equal(got["iters"], ref["iters"])
     assert np.array_equal(got["u0"], ref["u"][:, 0])
+
+
+def test_batched_logs_split_into_reference_entries(tmp_path):
+    """datasets.split_batched_logs: one reference-schema entry per (trajectory, active iteration); the pickle
+    stream round-trips and feeds _create_dataset's expectations (x_seq (T, n), k_seq (T, m), K_seq (T, m, n))."""
+    import numpy as np
+    from quattro_transformer_ilqr_b200 import datasets
+    B, N, n, m = 3, 5, 4, 1
+    rng = np.random.default_rng(0)
+    logs = []
+    for it in range(2):
+        found = np.array([True, it == 0, False])
+        logs.append({"iteration": it, "x_seq": rng.normal(size=(B, N + 1, n)), "u_seq": rng.normal(size=(B, N, m)),
+                     "current_cost": rng.uniform(1, 2, B), "k_seq": rng.normal(size=(B, N, m)),
+                     "K_seq": rng.normal(size=(B, N, m, n)), "alpha": np.where(found, 0.5, np.nan),
+                     "new_x_seq": rng.normal(size=(B, N + 1, n)), "new_u_seq": rng.normal(size=(B, N, m)),
+                     "new_cost": np.where(found, 1.0, np.nan), "found_update": found,
+                     "active": np.array([True, True, it == 0])})
+    entries = datasets.split_batched_logs(logs)
+    assert len(entries) == 5                                     # trajectory 2 is inactive in iteration 1
+    e = entries[0]
+    assert e["x_seq"].shape == (N + 1, n) and isinstance(e["k_seq"], list) and e["K_seq"][0].shape == (m, n)
+    assert isinstance(e["current_cost"], float) and e["alpha"] == 0.5 and e["found_update"] is True
+    last = entries[-1]                                           # trajectory 2, iteration 0: no update found
+    assert last["alpha"] is None and last["new_x_seq"] is None and last["new_u_seq"] is None and last["new_cost"] is None
+    path = tmp_path / "logs.pkl"
+    datasets.dump_entries(entries[:2], path)
+    datasets.dump_entries(entries[2:], path, append=True)
+    back = datasets.load_entries(path)
+    assert len(back) == 5 and np.array_equal(back[3]["x_seq"], entries[3]["x_seq"])
+    df = datasets.entries_to_dataframe(back)
+    assert {"x_seq", "k_seq", "K_seq", "iteration"} <= set(df.columns)
+    assert np.array(df.iloc[0]["K_seq"], dtype=np.float32).shape == (N, m, n)
