@@ -6,9 +6,10 @@
 // The sequences are short (L = 101 / 61 tokens) and the head dimension is 32, so a (trajectory, head) pair is a
 // 101x32 . 32x101 . 101x32 problem: far below a tcgen05 tile (M = 128 rows of ONE operand pair) but a good fit for
 // warp-level mma.sync.m16n8k8 TF32 tiles.  One CTA per (trajectory, head):
-//   * K and V rows are staged in shared memory already split into TF32 (hi, lo) halves (3xTF32: hi*hi + lo*hi +
-//     hi*lo, fp32-accurate products - the 1e-5 parity bar rules plain TF32 out); row pitch 36 floats makes both
-//     B-fragment access patterns bank-conflict free;
+//   * K and V rows are staged in shared memory as fp32 (30 KB for L = 101, so seven CTAs share an SM) and every
+//     fragment is split into TF32 (hi, lo) halves on the fly (3xTF32: hi*hi + lo*hi + hi*lo, fp32-accurate
+//     products - the 1e-5 parity bar rules plain TF32 out); row pitch 36 floats makes both B-fragment access
+//     patterns bank-conflict free;
 //   * a warp owns 16 query rows at a time; causality means query tile q needs key tiles 0..2q+1 only, and warp w
 //     takes the tile pair (w, nq-1-w) so that the warps carry equal work;
 //   * all score tiles of a query tile stay in registers (<= 14 tiles x 4), so the softmax is the exact
@@ -40,20 +41,18 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const float (&a)[4], flo
 
 }  // namespace
 
-// grid (nhead, B); block 32 * ceil(nq / 2) threads, nq = ceil(L / 16); dynamic shared memory 4 * Lp * 36 floats
+// grid (nhead, B); block 32 * ceil(nq / 2) threads, nq = ceil(L / 16); dynamic shared memory 2 * Lp * 36 floats
 __global__ void __launch_bounds__(128)
 tf_attention_mma_kernel(const float* __restrict__ qkv, float* __restrict__ out, int L, int d) {
   extern __shared__ float smf[];
   const int Lp = (L + 7) & ~7;                       // keys padded to whole tiles
-  float* Khi = smf;
-  float* Klo = Khi + (size_t)Lp * kPitch;
-  float* Vhi = Klo + (size_t)Lp * kPitch;
-  float* Vlo = Vhi + (size_t)Lp * kPitch;
+  float* Ks = smf;                                   // fp32 rows; the TF32 (hi, lo) split is done per fragment
+  float* Vs = Ks + (size_t)Lp * kPitch;
   const int head = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const float* base = qkv + (size_t)b * L * 3 * d + head * kHd;
 
-  // stage K, V (rows beyond L are zero) with the TF32 split done once for the whole CTA
+  // stage K, V (rows beyond L are zero)
   for (int e = tid; e < Lp * (kHd / 4); e += blockDim.x) {
     const int r = e >> 3, c4 = e & 7;
     float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
@@ -61,14 +60,8 @@ tf_attention_mma_kernel(const float* __restrict__ qkv, float* __restrict__ out, 
       kv = *reinterpret_cast<const float4*>(base + (size_t)r * 3 * d + d + 4 * c4);
       vv = *reinterpret_cast<const float4*>(base + (size_t)r * 3 * d + 2 * d + 4 * c4);
     }
-    const float4 kh = make_float4(to_tf32(kv.x), to_tf32(kv.y), to_tf32(kv.z), to_tf32(kv.w));
-    const float4 vh = make_float4(to_tf32(vv.x), to_tf32(vv.y), to_tf32(vv.z), to_tf32(vv.w));
-    *reinterpret_cast<float4*>(&Khi[r * kPitch + 4 * c4]) = kh;
-    *reinterpret_cast<float4*>(&Klo[r * kPitch + 4 * c4]) =
-        make_float4(to_tf32(kv.x - kh.x), to_tf32(kv.y - kh.y), to_tf32(kv.z - kh.z), to_tf32(kv.w - kh.w));
-    *reinterpret_cast<float4*>(&Vhi[r * kPitch + 4 * c4]) = vh;
-    *reinterpret_cast<float4*>(&Vlo[r * kPitch + 4 * c4]) =
-        make_float4(to_tf32(vv.x - vh.x), to_tf32(vv.y - vh.y), to_tf32(vv.z - vh.z), to_tf32(vv.w - vh.w));
+    *reinterpret_cast<float4*>(&Ks[r * kPitch + 4 * c4]) = kv;
+    *reinterpret_cast<float4*>(&Vs[r * kPitch + 4 * c4]) = vv;
   }
   __syncthreads();
 
@@ -99,11 +92,11 @@ tf_attention_mma_kernel(const float* __restrict__ qkv, float* __restrict__ out, 
     for (int jt = 0; jt < kMaxKt; ++jt) {
       s[jt][0] = s[jt][1] = s[jt][2] = s[jt][3] = 0.f;
       if (jt < nkt) {
-        const float* kh = &Khi[(8 * jt + g) * kPitch + t];
-        const float* kl = &Klo[(8 * jt + g) * kPitch + t];
+        const float* kp = &Ks[(8 * jt + g) * kPitch + t];
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-          const float bh0 = kh[8 * kk], bh1 = kh[8 * kk + 4], bl0 = kl[8 * kk], bl1 = kl[8 * kk + 4];
+          const float k0 = kp[8 * kk], k1 = kp[8 * kk + 4];
+          const float bh0 = to_tf32(k0), bh1 = to_tf32(k1), bl0 = to_tf32(k0 - bh0), bl1 = to_tf32(k1 - bh1);
           mma_tf32(s[jt], ql[kk], bh0, bh1);
           mma_tf32(s[jt], qh[kk], bl0, bl1);
           mma_tf32(s[jt], qh[kk], bh0, bh1);
@@ -147,11 +140,11 @@ tf_attention_mma_kernel(const float* __restrict__ qkv, float* __restrict__ out, 
           ph[i] = to_tf32(pf[i]);
           pl[i] = to_tf32(pf[i] - ph[i]);
         }
-        const float* vh = &Vhi[(8 * jt + 2 * t) * kPitch + g];
-        const float* vl = &Vlo[(8 * jt + 2 * t) * kPitch + g];
+        const float* vp = &Vs[(8 * jt + 2 * t) * kPitch + g];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
-          const float bh0 = vh[8 * nt], bh1 = vh[kPitch + 8 * nt], bl0 = vl[8 * nt], bl1 = vl[kPitch + 8 * nt];
+          const float v0 = vp[8 * nt], v1 = vp[kPitch + 8 * nt];
+          const float bh0 = to_tf32(v0), bh1 = to_tf32(v1), bl0 = to_tf32(v0 - bh0), bl1 = to_tf32(v1 - bh1);
           mma_tf32(o[nt], pl, bh0, bh1);
           mma_tf32(o[nt], ph, bl0, bl1);
           mma_tf32(o[nt], ph, bh0, bh1);
@@ -175,10 +168,10 @@ tf_attention_mma_kernel(const float* __restrict__ qkv, float* __restrict__ out, 
 int tf_attention_tc(const float* qkv, float* out, int B, int L, int d, int nhead, cudaStream_t st) {
   if (d != nhead * kHd || L > 8 * kMaxKt || L < 1) return QX_EUNSUPPORTED;
   const int Lp = (L + 7) & ~7, nq = (L + 15) >> 4;
-  const size_t smem = (size_t)4 * Lp * kPitch * sizeof(float);
+  const size_t smem = (size_t)2 * Lp * kPitch * sizeof(float);
   static bool cfg = false;
   if (!cfg) {
-    cudaFuncSetAttribute(tf_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 8 * kMaxKt * kPitch * 4);
+    cudaFuncSetAttribute(tf_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * kMaxKt * kPitch * 4);
     cfg = true;
   }
   tf_attention_mma_kernel<<<dim3(nhead, B), 32 * ((nq + 1) / 2), smem, st>>>(qkv, out, L, d);
