@@ -47,6 +47,25 @@ def test_layout_queries(lib):
     assert lib.qx_layout(7) < 0 and b"unknown model_id" in lib.qx_last_error()
 
 
+def test_block_path_queries(lib):
+    """The compact block records (QX_LAYOUT_BLK): 256 B per (t, b) in octets of trajectories, 64-B terminal; only
+    the quadrotor with the Euler map and diagonal weights qualifies."""
+    from quattro_transformer_ilqr_b200 import DeviceModel
+    assert lib.qx_blk_expansion_bytes(16384, 50) == 16384 * 50 * 256
+    assert lib.qx_blk_expansion_bytes(9, 50) == 16 * 50 * 256          # ragged batch: padded to whole octets
+    assert lib.qx_blk_terminal_bytes(97) == 97 * 64
+    assert lib.qx_blk_expansion_bytes(0, 50) == 0
+    ok = DeviceModel("quadrotor").params()
+    assert lib.qx_blk_supported(ctypes.byref(ok)) == 1
+    assert lib.qx_blk_supported(ctypes.byref(DeviceModel("quadrotor", integration_method="rk4").params())) == 0
+    Q = np.diag([10.0] * 12); Q[0, 1] = Q[1, 0] = 0.5
+    assert lib.qx_blk_supported(ctypes.byref(DeviceModel("quadrotor", Q=Q).params())) == 0
+    assert lib.qx_blk_supported(ctypes.byref(DeviceModel("cartpole").params())) == 0
+    # argument validation needs no GPU: the wrong model is refused before any launch
+    bad = DeviceModel("cartpole").params()
+    assert lib.qx_riccati_blk(ctypes.byref(bad), None, None, None, None, 8, 50, 0, 1e-6, None) == -1
+
+
 def test_params_struct_matches_header():
     from quattro_transformer_ilqr_b200 import _lib
     # 6 int32 + (1 + 8 + 144 + 16 + 144 + 12 + 2) doubles
