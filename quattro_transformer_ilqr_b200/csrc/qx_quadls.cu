@@ -602,6 +602,34 @@ ls_qd_phaseC_kernel(double* __restrict__ x_in, double* __restrict__ u_in, double
   if ((threadIdx.x & 31) == 0 && n_active != nullptr && act != 0u) atomicAdd(n_active, __popc(act));
 }
 
+// forward_pass with a caller-chosen alpha (quattro_ilqr_tf.py:377-390): the same candidate arithmetic as the
+// line search, so qx_forward_pass(alpha) reproduces the candidate the search evaluated bit for bit
+template <int INTEG>
+__global__ void __launch_bounds__(128)
+forward_pass_qd_kernel(const __grid_constant__ QxParams p, const double* __restrict__ x_in, const double* __restrict__ u_in,
+                       const float* __restrict__ gains, double alpha, double* __restrict__ x_out, double* __restrict__ u_out,
+                       double* __restrict__ cost_out, int B, int N) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const bool run = b < B;
+  if (!__any_sync(FULL, run)) return;
+  QdLane c;
+  qd_lane_init(p, lane, c);
+  const double cst = qd_candidate<INTEG>(c, run, x_in, u_in, gains, run ? b : 0, alpha, x_out, u_out, run ? b : 0, B, N);
+  if (run && c.g == 0) cost_out[b] = cst;
+}
+
+int qd_launch_forward_pass(const QxParams* p, const double* x_in, const double* u_in, const float* gains, double alpha,
+                           double* x_out, double* u_out, double* cost_out, int B, int N, cudaStream_t st) {
+  const int grid = ceil_div(4 * B, 128);
+  if (p->integrator == QX_EULER)
+    forward_pass_qd_kernel<QX_EULER><<<grid, 128, 0, st>>>(*p, x_in, u_in, gains, alpha, x_out, u_out, cost_out, B, N);
+  else
+    forward_pass_qd_kernel<QX_RK4><<<grid, 128, 0, st>>>(*p, x_in, u_in, gains, alpha, x_out, u_out, cost_out, B, N);
+  QX_CHECK_LAUNCH("forward_pass_qd_kernel");
+  return QX_OK;
+}
+
 // ---- host side: called by qx_rollout_cost / qx_linesearch (qx_rollout.cu) for the quadrotor with diagonal weights
 int qd_launch_rollout(const QxParams* p, const double* x0, const double* u, double* x, double* cost,
                       const int32_t* status, int B, int N, cudaStream_t st) {

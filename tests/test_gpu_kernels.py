@@ -213,6 +213,25 @@ def test_forward_pass_entry_point(system, B, us):
         assert relmax(gx.cpu().numpy(), xn) < 1e-11
 
 
+def test_forward_pass_reproduces_the_line_search_bitwise():
+    """The accept test is "<=" on costs, so every kernel that evaluates f and L must produce the same bits for the
+    same inputs: forward_pass(alpha) with the alpha the line search accepted returns exactly the cost, controls
+    and states the search kept (quadrotor: staged 4-lane kernels)."""
+    x0, u = _problem("quadrotor", 97, 12, 0.6)
+    e = _engine("quadrotor", 97)
+    e.set_problem(x0, u)
+    e.linearize(0)
+    e.riccati(0)
+    cands = {a: e.forward_pass(alpha) for a, alpha in enumerate(ob.ALPHAS)}
+    e.linesearch(tol=1e-3, force=True)
+    idx = e.alpha.cpu().numpy()
+    assert len(set(idx.tolist())) >= 2
+    xb, ub, cb = e.x_batch(), e.u_batch(), e.cost
+    for a, (gx, gu, gc) in cands.items():
+        sel = torch.as_tensor(idx == a, device=e.device)
+        assert torch.equal(cb[sel], gc[sel]) and torch.equal(ub[sel], gu[sel]) and torch.equal(xb[sel], gx[sel])
+
+
 def test_inactive_trajectories_are_untouched():
     x0, u = _problem("quadrotor", 70, 6, 0.5)
     e = _engine("quadrotor", 70)
