@@ -134,14 +134,47 @@ def cpu_reference(system, steps, warmup, iters_per_step=1):
 
 # ------------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
-    """Polls nvidia-smi from a thread while the timed region runs (the recipe's clocks line)."""
+    """Samples SM clocks and throttle reasons from a thread while the timed region runs (the recipe's clocks
+    line).  NVML (nvidia_ml_py) when importable - a sample costs microseconds, so even a 100 ms region gets
+    dozens - else the nvidia-smi query of the recipe."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.rows, self.index, self._stop, self.thread = [], index, threading.Event(), None
+        self.rows, self.index, self._stop, self.thread, self.max_mhz = [], index, threading.Event(), None, None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical GPUs: honour CUDA_VISIBLE_DEVICES when it is a list of indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                phys = int(vis.split(",")[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
-    def _poll(self):
+    def _poll_nvml(self):
+        n = self.nvml
+        bits = [(getattr(n, "nvmlClocksEventReasonHwSlowdown", getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8))),
+                (getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40))),
+                (getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20))),
+                (getattr(n, "nvmlClocksEventReasonSwPowerCap", getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)))]
+        reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                mhz = int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(reasons_fn(self.handle))
+                self.rows.append([str(mhz), str(self.max_mhz)] + ["Active" if mask & b else "Not Active" for b in bits])
+            except Exception:
+                return
+            self._stop.wait(0.002)
+
+    def _poll_smi(self):
         cmd = ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)]
         while not self._stop.is_set():
             try:
@@ -152,7 +185,7 @@ class ClockSampler:
             self._stop.wait(0.02)
 
     def start(self):
-        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread = threading.Thread(target=self._poll_nvml if self.nvml else self._poll_smi, daemon=True)
         self.thread.start()
 
     def stop(self):
@@ -163,9 +196,9 @@ class ClockSampler:
         if not rows:
             return None
         sm = sorted(int(r[0]) for r in rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i] == "Active" for r in rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[2 + i] == "Active" for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][1]), "reasons": reasons, "samples": len(rows),
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------- GPU arm

@@ -137,7 +137,9 @@ class BatchedILQR:
                                           _ptr(self.ls_workspace), float(tol),
                                           _lib.QX_LS_FORCE_ACTIVE if force else 0, self.B, self.N, self.stream),
                    "qx_linesearch")
-        self.launches += 1
+        # the staged search of the quadrotor (diagonal weights, workspace given) is five kernels: A, B1, C1, B2, C2
+        staged = self.ls_workspace is not None and self.model.model_id == _lib.QX_MODEL_QUADROTOR and self.params.diag_cost
+        self.launches += 5 if staged else 1
         self.cur = 1 - c
 
     def forward_pass(self, alpha):
