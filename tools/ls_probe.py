@@ -2,7 +2,7 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from oracle.models import sample_x0
+from quattro_transformer_ilqr_b200.sampling import sample_x0
 from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel
 
 B, N = int(sys.argv[1]) if len(sys.argv) > 1 else 16384, 50
