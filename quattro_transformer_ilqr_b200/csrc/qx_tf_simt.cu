@@ -75,9 +75,12 @@ tf_embed128_kernel(const QxTfConfig cfg, const float* __restrict__ w, const doub
     const float4 bias = *reinterpret_cast<const float4*>(&w[lay.bs + ch]);
     double mu = 0.0, sd = 1.0, sh = 0.0;
     if (lane < n) { mu = (double)w[lay.x_mean + lane]; sd = (double)w[lay.x_std + lane]; sh = x_shift[lane]; }
+    double xv = (lane < n && warp <= N) ? x[((size_t)warp * n + lane) * B + b] : 0.0;
     for (int tok = warp; tok <= N; tok += 4) {
+      const double xc = xv;
+      if (lane < n && tok + 4 <= N) xv = x[((size_t)(tok + 4) * n + lane) * B + b];           // next row's input in flight
       float in = 0.f;
-      if (lane < n) in = (float)(((x[((size_t)tok * n + lane) * B + b] + sh) - mu) / sd);     // transformer_ilqr.py:312-315
+      if (lane < n) in = (float)(((xc + sh) - mu) / sd);                                      // transformer_ilqr.py:312-315
       float acc[4] = {bias.x, bias.y, bias.z, bias.w};
 #pragma unroll
       for (int i = 0; i < QX_MAX_N; ++i) {
