@@ -158,6 +158,33 @@ def test_full_size_properties():
     assert relmax(u_now[idx], ref["u"]) < 1e-3
 
 
+@pytest.mark.parametrize("system,B", [("quadrotor", 4100), ("cartpole", 3000)])
+def test_active_set_compaction_does_not_change_results(system, B):
+    """solve(compact=True) gathers the still-active trajectories into smaller engines as the batch converges;
+    everything it returns is bit-identical to the uncompacted solve."""
+    from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel
+    N = HORIZON[system]
+    x0 = sample_x0(system, B, seed=31)
+    if system == "cartpole":
+        x0[:, 2] *= 3.0                                  # some hard swing-ups so that iteration counts differ
+    u0 = np.zeros((B, N, make_model(system).m))
+    out = {}
+    for compact in (False, True):
+        e = BatchedILQR(DeviceModel(system), B, N)
+        e.set_problem(x0, u0)
+        n_it = e.solve(max_iter=40, tol=TOL[system], check_every=2, compact=compact, min_compact=256)
+        out[compact] = (n_it, e.u_batch(), e.x_batch(), e.cost.clone(), e.iters.clone(), e.alpha.clone(), e.status.clone(),
+                        int(e.n_active.item()), e.u[1 - e.cur].permute(2, 0, 1).clone())
+        if compact:
+            assert len(e.__dict__.get("_sub_engines", {})) >= 1, "the test should exercise at least one compaction"
+    a, b = out[False], out[True]
+    assert a[0] == b[0] and a[7] == b[7]
+    for p, q in zip(a[1:7], b[1:7]):
+        assert torch.equal(p, q)
+    fin = a[6] != 0
+    assert torch.equal(a[8][fin], b[8][fin])             # finished: same iterate in the other ping-pong buffer too
+
+
 def test_device_resident_mpc_sweep_equals_host_loop():
     """mpc_sweep (shift + x0 update on the device) reproduces the host-driven control_step loop bit for bit."""
     from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel
