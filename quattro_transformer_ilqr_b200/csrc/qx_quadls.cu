@@ -13,8 +13,8 @@
 //   u  (all-gather, 4 values)         for   thrust and torques
 //   the three angles, their sin/cos, 1/cos(theta), and the right neighbour's block (v for p', omega for eta')
 // with warp shuffles; each lane integrates and costs only its own block.  Compared with a full state copy
-// per lane this halves the fp64 work per step and needs ~100 registers instead of ~230, so several warps
-// per scheduler hide the latency of the sequential recursion.
+// per lane this halves the fp64 work per step and needs 128 registers instead of ~230, so four warps per
+// scheduler hide the latency of the sequential recursion.
 //
 // The file is compiled with -fmad=false and every fused multiply-add is written out (fma()), so the nominal
 // rollout, the line search and its retries evaluate f and L with identical bits for identical inputs - like
