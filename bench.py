@@ -468,6 +468,7 @@ def main():
     ap.add_argument("--compact", action="store_true", help="run-to-convergence leg with active-set compaction")
     ap.add_argument("--skip-extras", action="store_true", help="timed loop only (for ncu): no e2e / per-kernel / CPU legs")
     args = ap.parse_args()
+    args.warmup = max(3, args.warmup)        # timing rule: at least three untimed warm-up steps (reported as run)
     args.emit = _json_only_stdout()
     if args.impl == "reference":
         reference_arm(args)

@@ -139,6 +139,43 @@ def test_riccati_block_path_sizes_and_status(B):
     assert relmax(out[True][0], out[False][0]) < 1e-5 and relmax(out[True][1], out[False][1]) < 1e-5
 
 
+def test_block_path_follows_live_parameters():
+    """Non-default physics, weights, reference, dt and horizon (the reference's callers mutate these between calls):
+    linearise, Riccati and one line search of the block path against the oracle built with the same values."""
+    from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel
+    B, N = 41, 37
+    kw = dict(dt=0.02, mass=1.3, Ix=0.03, Iy=0.025, Iz=0.05, arm=0.12, gravity=9.7,
+              Q=np.diag([7.0, 9, 40, 2, 1, 1.5, 12, 8, 30, 1, 2, 0.5]), R=np.diag([0.02, 0.01, 0.03, 0.015]),
+              Qf=np.diag([90.0, 110, 400, 12, 8, 10, 80, 120, 450, 9, 11, 10]),
+              x_ref=np.array([0.1, -0.2, 0.7, 0, 0, 0, 0.05, -0.03, 0.2, 0, 0, 0]), alpha=700.0, beta=8.0)
+    model = make_model("quadrotor", **kw)
+    rng = np.random.default_rng(8)
+    x0 = sample_x0("quadrotor", B, seed=8)
+    u = 0.4 * rng.standard_normal((B, N, 4)) + 3.2
+    e = BatchedILQR(DeviceModel("quadrotor", **kw), B, N)
+    from quattro_transformer_ilqr_b200 import _lib
+    assert e.exp_layout == _lib.QX_LAYOUT_BLK
+    e.set_problem(x0, u)
+    x_ref, c_ref = ob.rollout(model, x0, u)
+    assert relmax(e.x_batch().cpu().numpy(), x_ref) < 1e-12 and relmax(e.cost.cpu().numpy(), c_ref) < 1e-12
+    exp = ob.linearize(model, x_ref, u)
+    e.linearize(0)
+    got = {k: v.cpu().numpy() for k, v in e.expansion_batch().items()}
+    for key in ("A", "B", "lx", "lu", "lxx", "luu", "VxN", "VxxN"):
+        assert relmax(got[key], exp[key]) < 2e-6, key
+    K_ref, k_ref = ob.riccati(exp)
+    e.riccati(0)
+    K, k = (t.cpu().numpy() for t in e.gains_batch())
+    assert relmax(K, K_ref) < 1e-5 and relmax(k, k_ref) < 1e-5
+    # line search on the oracle's gains (rounded to fp32): same decisions and candidates
+    e.load_gains(K_ref.astype(np.float32), k_ref.astype(np.float32))
+    e.linesearch(tol=1e-3)
+    xn, un, cn, idx, _ = ob.line_search(model, x_ref, u, K_ref.astype(np.float32).astype(np.float64),
+                                        k_ref.astype(np.float32).astype(np.float64), c_ref)
+    assert np.array_equal(e.alpha.cpu().numpy(), idx)
+    assert relmax(e.cost.cpu().numpy(), cn) < 1e-12 and relmax(e.u_batch().cpu().numpy(), un) < 1e-11
+
+
 def test_riccati_block_path_indefinite_quu():
     """An indefinite Q_uu (negative R) must go through the pivoted fallback like the reference's LU inverse
     (SURVEY a-Q(4)) instead of producing NaN."""
