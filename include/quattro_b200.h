@@ -177,6 +177,14 @@ int qx_tf_forward(const QxTfConfig* cfg, const float* weights, const float* wspl
                   const double* x_shift, float* gains, int model_id, const int32_t* status, void* workspace, int B,
                   void* stream);
 
+/* One dense layer of the model on the tensor cores (nn.Linear [+ ReLU], transformer_model.py:106-116 and
+ * the in_proj / out_proj / linear1 / linear2 of nn.TransformerEncoderLayer): C[M][N] = act(A[M][K] W[N][K]^T + bias),
+ * row-major fp32, W passed as the (hi, lo) TF32 halves qx_tf_split() produces.  N % 128 == 0, K % 32 == 0,
+ * all pointers 128-B aligned.  K == 128 runs the resident-weight kernel, other K the streaming kernel. */
+int qx_tf_split(const float* w, float* hi, float* lo, size_t count, void* stream);
+int qx_tf_dense(const float* A, const float* w_hi, const float* w_lo, const float* bias, float* C, int M, int N, int K,
+                int relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -504,3 +504,19 @@ extern "C" int qx_tf_forward(const QxTfConfig* cfg, const float* weights, const 
   return qx::tf_forward_simt(cfg, weights, wsplit, x, x_shift, gains, layout, status, static_cast<float*>(workspace), B,
                              static_cast<cudaStream_t>(stream));
 }
+
+// nn.Linear (+ ReLU) as used by the model (transformer_model.py:106-107,116 and the encoder layers) on the
+// tensor cores: C[M][N] = act(A[M][K] W[N][K]^T + bias) with W given as its (hi, lo) TF32 halves.
+extern "C" int qx_tf_split(const float* w, float* hi, float* lo, size_t count, void* stream) {
+  QX_CHECK_ARG(w && hi && lo, "null pointer");
+  if (count == 0) return QX_OK;
+  return qx::tf_split_weights(w, hi, lo, count, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int qx_tf_dense(const float* A, const float* w_hi, const float* w_lo, const float* bias, float* C, int M,
+                           int N, int K, int relu, void* stream) {
+  QX_CHECK_ARG(A && w_hi && w_lo && bias && C, "null pointer");
+  QX_CHECK_ARG(M >= 0 && N > 0 && K > 0, "bad shape");
+  if (M == 0) return QX_OK;
+  return qx::tf_gemm_tc(A, w_hi, w_lo, bias, C, M, N, K, relu != 0, static_cast<cudaStream_t>(stream));
+}

@@ -20,6 +20,7 @@
 //   warps 6-9 epilogue: tcgen05.ld (32x32b.x32) TMEM -> registers, + bias, optional ReLU, 16-B
 //             stores; runs concurrently with the next tile's MMAs (double-buffered TMEM)
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "qx_async.cuh"
 #include "qx_tf_common.cuh"
@@ -247,6 +248,272 @@ tf_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
+
+// ---- main kernel: A operand in TENSOR MEMORY, weights parked in (or ringed through) shared memory ---------------
+// What bounded the streaming kernel above (46 % tensor-pipe activity whatever its ring depth; tools/gemm_probe.py):
+//  * an M128 N128 K8 kind::tf32 MMA with both operands in shared memory reads 4 KB of A and 4 KB of B in its 64
+//    cycles - 128 B/clk, ALL the shared-memory bandwidth of the SM - while the splitter (16 KB read + 32 KB written
+//    per K block) and the epilogue transpose compete for the same banks;
+//  * one diverged lane issuing the MMAs spent ~10 instructions (R2UR round trips) per UTCHMMA, more than the 64
+//    cycles an MMA lasts;
+//  * 64 KB of st.global per tile from the epilogue warps stalled them for longer than the tile's main loop;
+//  * with K = 128 the W tiles (128 KB per output tile) were two thirds of the L2 -> SM traffic.
+// Here:
+//  * the splitter (thread = row) reads its raw A row from the TMA landing block and writes A_hi / A_lo straight
+//    into TMEM (tcgen05.st, lane = row, column = k); the MMAs take A from there (tcgen05.mma [d], [a], b-desc), so
+//    shared memory only carries the landing of raw A, one read of it, and the B operand.  A raw block is free as
+//    soon as the splitter has it in registers: the raw ring is pure latency cover;
+//  * the whole MMA warp walks the issue loop (warp-uniform operands -> uniform registers, UTCHMMAs 1-4 instructions
+//    apart), one elected lane issues;
+//  * the epilogue stages 32 x 32 chunks in the 128-B-swizzle box layout and lets TMA store them
+//    (cp.async.bulk.tensor ... global.shared::cta), double buffered; rows beyond M are clipped by the tensor map;
+//  * the W_hi / W_lo tiles live in a 4-block ring of 32 KB.  K = 128 is exactly 4 blocks: a CTA owns ONE n tile for
+//    its whole life (CTAs b, b+1, .. of a group share the m tile and run in step, so A comes from HBM once), loads
+//    its weights once and never frees them.  K > 128 (linear2) cycles the ring, a block being freed by the
+//    tcgen05.commit of the MMAs that read it.
+// (An L2 prefetch of the next A tile - cp.async.bulk.prefetch.tensor - was measured and removed: it made the
+// linear2 / out-proj shapes 10-17 % SLOWER.)
+// TMEM: columns 0-255 two accumulators (the epilogue of tile i overlaps the MMAs of tile i+1), 256-511 four A stages
+// of (32 hi + 32 lo) columns.  Results are bit-identical to the streaming kernel (same MMAs, same order).
+constexpr int kTaW = 4, kTaRaw = 4, kTaA = 4;
+constexpr int ta_threads(int sets) { return 64 + 128 * sets + 128; }
+
+struct TaSmem {
+  float w_hi[kTaW][kBN * kBK];
+  float w_lo[kTaW][kBN * kBK];
+  float raw[kTaRaw][kBM * kBK];
+  float4 epi[4][2][32][8];       // per epilogue warp: two 32 x 32 fp32 chunks in the TMA 128-B swizzle layout
+  uint64_t w_full[kTaW], w_empty[kTaW], full[kTaRaw], raw_empty[kTaRaw], a_ready[kTaA], a_empty[kTaA], acc_full[2],
+      acc_empty[2];
+  uint32_t tmem_base;
+};
+constexpr size_t kTaSmemBytes = sizeof(TaSmem) + 1024;
+static_assert(kTaSmemBytes <= 227 * 1024, "TMEM-A GEMM exceeds the shared memory of an SM");
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void mma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// kSets sets of four splitter warps take the K blocks in turn.  A set must meet EVERY phase of the barriers it waits
+// on (a parity wait cannot tell phase p from phase p + 2), hence ring depths that are multiples of the set count.
+// STREAM_W: K > 128, the weight ring cycles (K % 128 == 0 keeps block kb in slot kb % 4).
+// dbg (timing experiments only, QX_TF_GEMM_DBG): bit 0 no stores, bit 2 no epilogue work.
+template <bool RELU, bool STREAM_W, int kSets>
+__global__ void __launch_bounds__(ta_threads(kSets), 1)
+tf_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
+                  const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmC,
+                  const float* __restrict__ bias, int M, int N, int K, int dbg) {
+  static_assert(kTaRaw % kSets == 0 && kTaA % kSets == 0, "ring depths must be multiples of the splitter set count");
+  extern __shared__ uint8_t smem_raw[];
+  TaSmem& s = *reinterpret_cast<TaSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = STREAM_W ? K / kBK : kTaW;
+  const int n_tiles_n = N / kBN;
+  const int groups = gridDim.x / n_tiles_n;           // CTAs of a group share the m tile
+  const int n0 = (blockIdx.x % n_tiles_n) * kBN;
+  const int g0 = blockIdx.x / n_tiles_n;
+  const int m_tiles = ceil_div(M, kBM);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kTaW; ++i) {
+      mbar_init(&s.w_full[i], 1);
+      mbar_init(&s.w_empty[i], 1);
+    }
+    for (int i = 0; i < kTaRaw; ++i) {
+      mbar_init(&s.full[i], 1);
+      mbar_init(&s.raw_empty[i], 128);
+    }
+    for (int i = 0; i < kTaA; ++i) {
+      mbar_init(&s.a_ready[i], 128);
+      mbar_init(&s.a_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.acc_full[i], 1);
+      mbar_init(&s.acc_empty[i], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {   // all 512 columns: 2 accumulators + 4 A stages
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = s.tmem_base;
+  const uint32_t tmem_a0 = tmem + 2 * kBN;
+
+  if (warp == 0) {
+    // ---- TMA producer: weight blocks (once, or ringed) and the raw A blocks of this CTA's m tiles ---------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int mt = g0; mt < m_tiles; mt += groups) {
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          if (STREAM_W || it < (uint32_t)kTaW) {
+            const int sw = it % kTaW;
+            mbar_wait(&s.w_empty[sw], ((it / kTaW) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(&s.w_full[sw], 2 * kTileBytes);
+            tma_load_2d(&tmWhi, &s.w_full[sw], s.w_hi[sw], kb * kBK, n0);
+            tma_load_2d(&tmWlo, &s.w_full[sw], s.w_lo[sw], kb * kBK, n0);
+          }
+          const int st = it % kTaRaw;
+          mbar_wait(&s.raw_empty[st], ((it / kTaRaw) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&s.full[st], kTileBytes);
+          tma_load_2d(&tmA, &s.full[st], s.raw[st], kb * kBK, mt * kBM);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: A from TMEM, B from the weight ring -----------------------------------------------------------
+    uint32_t it = 0, tl = 0;
+    for (int mt = g0; mt < m_tiles; mt += groups, ++tl) {
+      const uint32_t buf = tl & 1u;
+      mbar_wait(&s.acc_empty[buf], ((tl >> 1) & 1u) ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t acc = tmem + buf * kBN;
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const uint32_t sa = it % kTaA, sw = it % kTaW;
+        // resident weights: phase 0 of w_full[sw] completes once and the wait stays satisfied
+        mbar_wait(&s.w_full[sw], STREAM_W ? ((it / kTaW) & 1u) : 0u);
+        mbar_wait(&s.a_ready[sa], (it / kTaA) & 1u);
+        tcgen05_fence_after();
+        const uint32_t a_hi = tmem_a0 + sa * (2 * kBK), a_lo = a_hi + kBK;
+        const uint64_t dw_hi = umma_desc_sw128(s.w_hi[sw]), dw_lo = umma_desc_sw128(s.w_lo[sw]);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kBK / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);       // 32 bytes per K = 8 slice
+            mma_tf32_ta(acc, a_lo + 8 * k, dw_hi + adv, kIdescTf32, (kb | k) ? 1u : 0u);
+            mma_tf32_ta(acc, a_hi + 8 * k, dw_lo + adv, kIdescTf32, 1u);
+            mma_tf32_ta(acc, a_hi + 8 * k, dw_hi + adv, kIdescTf32, 1u);
+          }
+          tcgen05_commit(&s.a_empty[sa]);
+          if (STREAM_W) tcgen05_commit(&s.w_empty[sw]);
+          if (kb == KB - 1) tcgen05_commit(&s.acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 2 + 4 * kSets) {
+    // ---- splitter: thread = row; raw A row (128 B, swizzled chunks) -> registers -> A_hi, A_lo in TMEM -----------
+    const int q = warp & 3;                      // TMEM lane quarter of this warp
+    const int row = q * 32 + lane;
+    const int my_tiles = g0 < m_tiles ? (m_tiles - g0 + groups - 1) / groups : 0;
+    for (uint32_t it = (warp - 2) >> 2; it < (uint32_t)(my_tiles * KB); it += kSets) {
+      const int st = it % kTaRaw;
+      const uint32_t sa = it % kTaA;
+      mbar_wait(&s.full[st], (it / kTaRaw) & 1u);
+      const float4* src = reinterpret_cast<const float4*>(s.raw[st]) + row * 8;
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 v = src[j ^ (row & 7)];           // 128-B swizzle: 16-B chunk j of row r sits at j ^ (r % 8)
+        float h, l;
+        tf32_split(v.x, h, l); hi[4 * j + 0] = __float_as_uint(h); lo[4 * j + 0] = __float_as_uint(l);
+        tf32_split(v.y, h, l); hi[4 * j + 1] = __float_as_uint(h); lo[4 * j + 1] = __float_as_uint(l);
+        tf32_split(v.z, h, l); hi[4 * j + 2] = __float_as_uint(h); lo[4 * j + 2] = __float_as_uint(l);
+        tf32_split(v.w, h, l); hi[4 * j + 3] = __float_as_uint(h); lo[4 * j + 3] = __float_as_uint(l);
+      }
+      mbar_arrive(&s.raw_empty[st]);                   // the raw block is in registers: hand it back to the producer
+      mbar_wait(&s.a_empty[sa], ((it / kTaA) & 1u) ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_a0 + sa * (2 * kBK) + ((uint32_t)(q * 32) << 16);
+      tmem_st_32x32b_x32(taddr, hi);
+      tmem_st_32x32b_x32(taddr + kBK, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tcgen05_fence_before();
+      mbar_arrive(&s.a_ready[sa]);
+    }
+  } else {
+    // ---- epilogue: TMEM -> registers (+ bias, ReLU) -> swizzled staging chunk -> TMA store ------------------------
+    const int q = warp & 3;
+    uint32_t tl = 0, chunk = 0;
+    for (int mt = g0; mt < m_tiles; mt += groups, ++tl) {
+      const int m0 = mt * kBM;
+      const uint32_t buf = tl & 1u;
+      mbar_wait(&s.acc_full[buf], (tl >> 1) & 1u);
+      tcgen05_fence_after();
+      if (!(dbg & 4)) {
+#pragma unroll
+        for (int c0 = 0; c0 < kBN; c0 += 32, ++chunk) {
+          uint32_t r[32];
+          const uint32_t taddr = tmem + buf * kBN + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr));
+          if (lane == 0) bulk_wait_read<1>();          // the store that last used this staging chunk has read it
+          __syncwarp();
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c0);
+          float4 (*stg)[8] = s.epi[q][chunk & 1u];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = b4[j];
+            float4 o;
+            o.x = __uint_as_float(r[4 * j + 0]) + bb.x;
+            o.y = __uint_as_float(r[4 * j + 1]) + bb.y;
+            o.z = __uint_as_float(r[4 * j + 2]) + bb.z;
+            o.w = __uint_as_float(r[4 * j + 3]) + bb.w;
+            if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            stg[lane][j ^ (lane & 7)] = o;
+          }
+          fence_proxy_async();                          // generic-proxy writes -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0 && !(dbg & 1)) {
+            tma_store_2d(&tmC, stg, n0 + c0, m0 + q * 32);
+            bulk_commit();
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&s.acc_empty[buf]);
+    }
+    if (lane == 0) bulk_wait_read<0>();              // staging must outlive the last stores' reads
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+  }
+}
+
 // W -> (W_hi, W_lo), elementwise, done once per weight upload
 __global__ void tf_split_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, size_t count) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -275,7 +542,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 // row-major fp32 matrix [rows][cols] -> tiled map with a (32 x 128) box and 128-B swizzle
-static int make_map(CUtensorMap* map, const float* base, int rows, int cols) {
+static int make_map(CUtensorMap* map, const float* base, int rows, int cols, int box_cols = kBK, int box_rows = kBM) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -283,7 +550,7 @@ static int make_map(CUtensorMap* map, const float* base, int rows, int cols) {
   }
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBM};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -315,6 +582,48 @@ int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* 
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  // QX_TF_GEMM_STREAM=1: the first-generation streaming kernel (A/B measurements and the bitwise-equality test; read
+  // per call).  QX_TF_GEMM_VARIANT=1: two splitter warp sets.  QX_TF_GEMM_DBG: timing experiments, see the kernel.
+  const char* env_stream = getenv("QX_TF_GEMM_STREAM");
+  const bool stream_only = env_stream != nullptr && env_stream[0] == '1';
+  if (K % (kTaW * kBK) == 0 && N / kBN <= num_sms && !stream_only) {
+    // groups of N/128 CTAs (one per n tile) walk the m tiles together
+    const int n_tiles_n = N / kBN, m_tiles = ceil_div(M, kBM);
+    int groups = num_sms / n_tiles_n;
+    if (groups > m_tiles) groups = m_tiles;
+    const int grid = groups * n_tiles_n;
+    const char* env_dbg = getenv("QX_TF_GEMM_DBG");
+    const int dbg = env_dbg ? atoi(env_dbg) : 0;
+    const char* env_var = getenv("QX_TF_GEMM_VARIANT");
+    const int variant = env_var ? atoi(env_var) : 0;
+    CUtensorMap mc;
+    if ((rc = make_map(&mc, C, M, N, 32, 32))) return rc;
+#define QX_TA_LAUNCH(RELU_, STREAM_, SETS)                                                                              \
+  do {                                                                                                                  \
+    static bool cfgd = false;                                                                                           \
+    if (!cfgd) {                                                                                                        \
+      cudaFuncSetAttribute(tf_gemm_ta_kernel<RELU_, STREAM_, SETS>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                           (int)kTaSmemBytes);                                                                          \
+      cfgd = true;                                                                                                      \
+    }                                                                                                                   \
+    tf_gemm_ta_kernel<RELU_, STREAM_, SETS><<<grid, ta_threads(SETS), kTaSmemBytes, st>>>(ma, mh, ml, mc, bias, M, N, K, dbg); \
+  } while (0)
+    const bool stream_w = K != kTaW * kBK;
+    if (variant == 1) {
+      if (relu && stream_w) QX_TA_LAUNCH(true, true, 2);
+      else if (relu) QX_TA_LAUNCH(true, false, 2);
+      else if (stream_w) QX_TA_LAUNCH(false, true, 2);
+      else QX_TA_LAUNCH(false, false, 2);
+    } else {
+      if (relu && stream_w) QX_TA_LAUNCH(true, true, 1);
+      else if (relu) QX_TA_LAUNCH(true, false, 1);
+      else if (stream_w) QX_TA_LAUNCH(false, true, 1);
+      else QX_TA_LAUNCH(false, false, 1);
+    }
+#undef QX_TA_LAUNCH
+    QX_CHECK_LAUNCH("tf_gemm_ta_kernel");
+    return QX_OK;
   }
   const int tiles = (N / kBN) * ceil_div(M, kBM);
   const int grid = tiles < num_sms ? tiles : num_sms;          // persistent: one CTA per SM

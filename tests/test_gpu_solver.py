@@ -298,6 +298,29 @@ def test_tensor_core_path_matches_exact_fp32_path(system, golden_dir):
 
 
 @pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
+def test_resident_weight_gemm_equals_streaming_gemm_bitwise(system, golden_dir, monkeypatch):
+    """The K = 128 layers run on the resident-weight tcgen05 kernel (weights parked in shared memory, A streamed
+    through a 3 + 2 block ring); it issues the same MMAs in the same order as the streaming kernel, so the
+    predictions must be bit-identical.  1 200 trajectories = hundreds of m tiles per CTA group: every ring slot,
+    both TMEM accumulators and the ragged last tile are exercised many times over."""
+    g = np.load(f"{golden_dir}/tf_forward_{system}.npz")
+    w = _wrapper(system, "rand")
+    rng = np.random.default_rng(5)
+    reps = 1200 // len(g["x_err"])
+    x = np.concatenate([g["x_err"] * (1.0 + 0.05 * rng.standard_normal(g["x_err"].shape)) for _ in range(reps)])
+    kK = np.concatenate([g["kK"] * (1.0 + 0.05 * rng.standard_normal(g["kK"].shape)) for _ in range(reps)])
+    monkeypatch.setenv("QX_TF_GEMM_STREAM", "1")
+    streamed = w.predict(x, kK)
+    monkeypatch.setenv("QX_TF_GEMM_STREAM", "0")
+    resident = w.predict(x, kK)
+    assert np.isfinite(resident).all()
+    assert np.array_equal(streamed, resident)
+    w.tensor_cores = False
+    exact = w.predict(x, kK)
+    assert relmax(resident, exact) < 5e-6
+
+
+@pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
 @pytest.mark.parametrize("mode", ["fp32", "rand"])
 def test_transformer_mode_matches_golden_runs(system, mode):
     """optimize() with the transformer in the loop vs the reference (same weights, fp32)."""
