@@ -184,6 +184,10 @@ int qx_tf_forward(const QxTfConfig* cfg, const float* weights, const float* wspl
 int qx_tf_split(const float* w, float* hi, float* lo, size_t count, void* stream);
 int qx_tf_dense(const float* A, const float* w_hi, const float* w_lo, const float* bias, float* C, int M, int N, int K,
                 int relu, void* stream);
+/* The causal self-attention core of the encoder layers (nn.MultiheadAttention inside nn.TransformerEncoderLayer,
+ * transformer_model.py:112-113; mask :134-135): qkv [B*L][3d] = packed in_proj output, out [B*L][d], 32-wide heads,
+ * softmax(Q K^T / sqrt(32) + causal mask) V.  impl 0: tcgen05 (L <= 112), 1: mma.sync (L <= 112), 2: exact fp32. */
+int qx_tf_attention(const float* qkv, float* out, int B, int L, int d, int nhead, int impl, void* stream);
 
 #ifdef __cplusplus
 }

@@ -62,6 +62,7 @@ SIGNATURES = {
     "qx_tf_split_floats": (C.c_size_t, [C.POINTER(QxTfConfig)]),
     "qx_tf_prepare": (C.c_int, [C.POINTER(QxTfConfig), _P, _P, _P]),
     "qx_tf_forward": (C.c_int, [C.POINTER(QxTfConfig), _P, _P, _P, _P, _P, C.c_int, _P, _P, C.c_int, _P]),
+    "qx_tf_attention": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "qx_tf_split": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
     "qx_tf_dense": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
 }

@@ -1,0 +1,409 @@
+// Causal multi-head attention of the Quattro transformer on tcgen05 (UMMA + TMEM + TMA), sm_100a.
+//
+//   = the self-attention inside nn.TransformerEncoderLayer (transformer_model.py:112-113, :134-136 of the reference:
+//     bool causal mask triu(ones(L, L), 1), 4 heads x 32, softmax(Q K^T / sqrt(32)) V), for every (trajectory, head).
+//
+// A (trajectory, head) item is a 101x32 . 32x101 . 101x32 problem (61 for cart-pole): ONE M = 128 UMMA tile in the
+// query dimension.  Per item, one 128-thread CTA (thread = query row) runs
+//   1. TMA: the Q, K, V head slices of the packed qkv rows as three [128 tokens x 32 dims] boxes of a
+//      [trajectory][token][feature] tensor map (tokens past L are zero-filled), 128-B swizzle;
+//   2. split: every tile into TF32 (hi, lo) halves in shared memory (3xTF32: hi*hi + lo*hi + hi*lo are
+//      fp32-accurate products - the 1e-5 parity bar rules plain TF32 out);
+//   3. S = Q K^T: 12 tcgen05.mma kind::tf32 (M128, N = keys padded to 16, K8), both operands K-major from shared
+//      memory, accumulator S in TMEM columns [0, NK);
+//   4. softmax, thread = row: two passes over the row's TMEM columns (tcgen05.ld) - exact max-subtracted softmax
+//      like the reference, base 2 - causal chunks only (warp q reads 32 (q+1) keys); P is split and written back
+//      to TMEM (tcgen05.st): P_hi over the S columns, P_lo next to them;
+//   5. O = P V: A = P from TMEM, B = V from shared memory as an MN-major operand: the TMA tile [key][dim], loaded with
+//      the 32-B-atom flavour of the 128-B swizzle (the only MN-major layout kind::tf32 takes), is the canonical atom
+//      sequence - 4 keys of 128 B per atom, two atoms per K = 8 step - so V is never transposed; N = 32;
+//   6. epilogue: O / rowsum -> swizzled staging chunk -> TMA store (rows past L are clipped by the map).
+// The steps of one item are serial inside a CTA (two __syncthreads and four mbarriers), so TWO CTAs share an SM
+// (112 KB of shared memory and 256 TMEM columns each): one does its softmax on the CUDA cores while the other's
+// MMAs run.  The next item's Q/K tiles are requested as soon as S is done, its V tile as soon as O is done.
+#include <stdlib.h>
+
+#include "qx_tc05.cuh"
+
+namespace qx {
+
+namespace {
+
+constexpr int kHd = 32;                    // head dimension = one 128-B row
+constexpr int kRows = 128;                 // UMMA M: query rows (and key rows of a tile)
+constexpr int kMaxKeys = 112;              // TMEM budget: S/P_hi [0,112) | P_lo [112,224) | O [224,256)
+constexpr int kTile = kRows * kHd;         // floats per tile (16 KB)
+constexpr uint32_t kColPlo = kMaxKeys, kColO = 2 * kMaxKeys;
+
+struct AttnSmem {
+  float q_hi[kTile], q_lo[kTile], k_hi[kTile], k_lo[kTile], v_hi[kTile], v_lo[kTile];
+  float4 stage[4][32][8];                  // per warp: 32 rows x 32 dims in the TMA 128-B swizzle layout
+  uint64_t bar_qk, bar_v, bar_s, bar_o;
+  uint32_t tmem_base;
+};
+
+// instruction descriptors: D = F32, A = B = TF32, M = 128; N and the B major differ
+constexpr uint32_t idesc_tf32(int n, bool b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (b_mn_major ? (1u << 16) : 0u) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+}
+
+template <int W>
+struct TmemRow;      // tcgen05.ld / st of W consecutive columns of this thread's lane (32x32b shape)
+template <>
+struct TmemRow<32> {
+  static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+  }
+  static __device__ __forceinline__ void st(uint32_t taddr, const uint32_t (&r)[32]) { tmem_st_32x32b_x32(taddr, r); }
+};
+template <>
+struct TmemRow<16> {
+  static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+  }
+  static __device__ __forceinline__ void st(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+  }
+};
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// hi in place, lo into the second tile; thread = row, its eight 16-B pieces visited in swizzle order
+__device__ __forceinline__ void split_tile_row(float* hi_tile, float* lo_tile, int row) {
+  float4* hi4 = reinterpret_cast<float4*>(hi_tile) + row * 8;
+  float4* lo4 = reinterpret_cast<float4*>(lo_tile) + row * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = j ^ (row & 7);
+    const float4 v = hi4[c];
+    float4 h, l;
+    tf32_split(v.x, h.x, l.x);
+    tf32_split(v.y, h.y, l.y);
+    tf32_split(v.z, h.z, l.z);
+    tf32_split(v.w, h.w, l.w);
+    hi4[c] = h;
+    lo4[c] = l;
+  }
+}
+
+// The Q tile: scaled by log2(e) / sqrt(32) (the scores then are base-2 logits), split, and written to row `dst`
+// (= row, or 127 - row in a flipped CTA) - through registers, with a barrier between the reads and the writes.
+__device__ __forceinline__ void split_q_row(float* hi_tile, float* lo_tile, int row, int dst, float scale) {
+  const float4* src = reinterpret_cast<const float4*>(hi_tile) + row * 8;
+  float4 h[8], l[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {                   // logical 16-B piece j of the row
+    float4 v = src[j ^ (row & 7)];
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    tf32_split(v.x, h[j].x, l[j].x);
+    tf32_split(v.y, h[j].y, l[j].y);
+    tf32_split(v.z, h[j].z, l[j].z);
+    tf32_split(v.w, h[j].w, l[j].w);
+  }
+  __syncthreads();
+  float4* hi4 = reinterpret_cast<float4*>(hi_tile) + dst * 8;
+  float4* lo4 = reinterpret_cast<float4*>(lo_tile) + dst * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    hi4[j ^ (dst & 7)] = h[j];
+    lo4[j ^ (dst & 7)] = l[j];
+  }
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Softmax of one query row whose scores sit in this thread's TMEM lane: Q full chunks of 32 keys, then the chunk
+// that holds the diagonal (WD = 32 or 16 columns, keys 32 Q + t with t <= lrev unmasked).  One sweep: all loads
+// first (their latencies overlap), exact row maximum, P = 2^(s - m), row sum, (hi, lo) halves back into TMEM
+// (P_hi over the scores).  Returns the row sum.
+template <int Q, int WD>
+__device__ __forceinline__ float softmax_row(uint32_t tmem_row, int lrev) {
+  uint32_t r[Q + 1][32];
+#pragma unroll
+  for (int c = 0; c < Q; ++c) TmemRow<32>::ld(tmem_row + 32 * c, r[c]);
+  TmemRow<WD>::ld(tmem_row + 32 * Q, r[Q]);
+  tmem_wait_ld();
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};      // four chains: the reductions are latency-bound
+#pragma unroll
+  for (int c = 0; c < Q; ++c) {
+#pragma unroll
+    for (int t = 0; t < 32; ++t) m4[t & 3] = fmaxf(m4[t & 3], __uint_as_float(r[c][t]));
+  }
+#pragma unroll
+  for (int t = 0; t < WD; ++t) {
+    if (t <= lrev) m4[t & 3] = fmaxf(m4[t & 3], __uint_as_float(r[Q][t]));
+  }
+  const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+  float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c <= Q; ++c) {
+    uint32_t lo[32];
+#pragma unroll
+    for (int t = 0; t < ((c < Q) ? 32 : WD); ++t) {
+      float p = ex2_approx(__uint_as_float(r[c][t]) - m);
+      if (c == Q && t > lrev) p = 0.f;
+      l4[t & 3] += p;
+      float h, lw;
+      tf32_split(p, h, lw);
+      r[c][t] = __float_as_uint(h);
+      lo[t] = __float_as_uint(lw);
+    }
+    if (c < Q) {
+      TmemRow<32>::st(tmem_row + 32 * c, r[c]);
+      TmemRow<32>::st(tmem_row + kColPlo + 32 * c, lo);
+    } else {
+      TmemRow<WD>::st(tmem_row + 32 * c, r[c]);
+      TmemRow<WD>::st(tmem_row + kColPlo + 32 * c, lo);
+    }
+  }
+  return (l4[0] + l4[1]) + (l4[2] + l4[3]);
+}
+template <int W>
+__device__ __forceinline__ void chunk_zero(uint32_t tmem_row, int key0) {
+  uint32_t z[32];
+#pragma unroll
+  for (int t = 0; t < 32; ++t) z[t] = 0u;
+  TmemRow<W>::st(tmem_row + key0, z);
+  TmemRow<W>::st(tmem_row + kColPlo + key0, z);
+}
+
+}  // namespace
+
+// grid: min(B * nhead, 2 * SMs) persistent CTAs of 128 threads; item = trajectory * nhead + head.
+// flip: the CTAs of the upper half of the grid keep their query rows in REVERSED lane order (token 127 - lane), so
+// that of two CTAs sharing an SM one has its long causal rows in warp 3 and the other in warp 0 - warps w of both
+// CTAs sit on the same scheduler, and the softmax work per scheduler evens out (144 : 160 : 160 : 144 keys instead
+// of 64 : 128 : 192 : 224).
+__global__ void __launch_bounds__(128, 2)
+tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmV,
+                         const __grid_constant__ CUtensorMap tmOut, int n_items, int nhead, int L, int d, int dbg) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  AttnSmem& s = *reinterpret_cast<AttnSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NK = (L + 15) & ~15;                    // keys padded to the UMMA N granularity
+  const int nks = (L + 7) >> 3;                     // K = 8 steps of the second product
+  const uint32_t idesc_s = idesc_tf32(NK, false), idesc_o = idesc_tf32(kHd, !(dbg & 8));
+  const bool flip = (gridDim.x > 1) && ((int)blockIdx.x >= (int)(gridDim.x + 1) / 2) && !(dbg & 1);
+  const int qrev = flip ? 3 - warp : warp;          // logical quarter: this thread's token is 32 qrev + lrev
+  const int lrev = flip ? 31 - lane : lane;
+  const int q_dst = flip ? kRows - 1 - tid : tid;   // tile row that holds this thread's loaded Q row
+
+  if (tid == 0) {
+    if (smem_u32(smem_raw) & 1023u) __trap();       // the swizzled tiles need 1 KB alignment
+    mbar_init(&s.bar_qk, 1);
+    mbar_init(&s.bar_v, 1);
+    mbar_init(&s.bar_s, 1);
+    mbar_init(&s.bar_o, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "n"(256)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = s.tmem_base;
+  const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);     // this warp's lane quarter
+  const float scale_log2 = rsqrtf((float)kHd) * 1.4426950408889634f;  // softmax in base 2: exp(x) = 2^(x log2 e)
+
+  auto load_qk = [&](int item) {
+    const int b = item / nhead, h = item - b * nhead;
+    mbar_arrive_expect_tx(&s.bar_qk, 2 * kTile * 4);
+    tma_load_3d(&tmQkv, &s.bar_qk, s.q_hi, h * kHd, 0, b);
+    tma_load_3d(&tmQkv, &s.bar_qk, s.k_hi, d + h * kHd, 0, b);
+  };
+  auto load_v = [&](int item) {
+    const int b = item / nhead, h = item - b * nhead;
+    mbar_arrive_expect_tx(&s.bar_v, kTile * 4);
+    tma_load_3d(&tmV, &s.bar_v, s.v_hi, 2 * d + h * kHd, 0, b);
+  };
+  auto split_qk = [&](uint32_t ph) {
+    mbar_wait(&s.bar_qk, ph);
+    split_tile_row(s.k_hi, s.k_lo, tid);
+    split_q_row(s.q_hi, s.q_lo, tid, q_dst, scale_log2);
+    fence_proxy_async();
+  };
+  if ((int)blockIdx.x < n_items) {
+    if (tid == 0) {
+      load_qk(blockIdx.x);
+      load_v(blockIdx.x);
+    }
+    split_qk(0);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+
+  uint32_t it = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    const uint32_t ph = it & 1u;
+    const int b = item / nhead, h = item - b * nhead;
+    const int next = item + gridDim.x;
+
+    // ---- S = (scaled Q) K^T ---------------------------------------------------------------------------------------
+    if (warp == 0) {
+      tcgen05_fence_after();
+      const uint64_t dq_hi = umma_desc_sw128(s.q_hi), dq_lo = umma_desc_sw128(s.q_lo);
+      const uint64_t dk_hi = umma_desc_sw128(s.k_hi), dk_lo = umma_desc_sw128(s.k_lo);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < kHd / 8; ++k) {
+          const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+          mma_tf32(tmem, dq_lo + adv, dk_hi + adv, idesc_s, k ? 1u : 0u);
+          mma_tf32(tmem, dq_hi + adv, dk_lo + adv, idesc_s, 1u);
+          mma_tf32(tmem, dq_hi + adv, dk_hi + adv, idesc_s, 1u);
+        }
+        tcgen05_commit(&s.bar_s);
+      }
+      __syncwarp();
+    }
+    // V is split while the tensor core works on S
+    mbar_wait(&s.bar_v, ph);
+    split_tile_row(s.v_hi, s.v_lo, tid);
+    fence_proxy_async();
+
+    mbar_wait(&s.bar_s, ph);
+    tcgen05_fence_after();
+    if (tid == 0 && next < n_items) load_qk(next);          // Q, K tiles are free: request the next item's
+    // ---- softmax (thread = row) -----------------------------------------------------------------------------------
+    float l = 1.f;
+    if (qrev * 32 < L && !(dbg & 4)) {
+      const bool wide = NK - 32 * qrev >= 32;
+      switch (qrev * 2 + (wide ? 1 : 0)) {
+        case 0: l = softmax_row<0, 16>(tmem_row, lrev); break;
+        case 1: l = softmax_row<0, 32>(tmem_row, lrev); break;
+        case 2: l = softmax_row<1, 16>(tmem_row, lrev); break;
+        case 3: l = softmax_row<1, 32>(tmem_row, lrev); break;
+        case 4: l = softmax_row<2, 16>(tmem_row, lrev); break;
+        case 5: l = softmax_row<2, 32>(tmem_row, lrev); break;
+        case 6: l = softmax_row<3, 16>(tmem_row, lrev); break;
+        default: l = softmax_row<3, 32>(tmem_row, lrev); break;
+      }
+      for (int c = qrev + 1; 32 * c < NK; ++c) {             // keys beyond the warp's causal range: P = 0
+        if (NK - 32 * c >= 32) chunk_zero<32>(tmem_row, 32 * c);
+        else chunk_zero<16>(tmem_row, 32 * c);
+      }
+      tmem_wait_st();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    // ---- O = P V ----------------------------------------------------------------------------------------------------
+    if (warp == 0) {
+      tcgen05_fence_after();
+      if (elect_one()) {
+        for (int ks = 0; ks < ((dbg & 2) ? 0 : nks); ++ks) {
+          const uint64_t dv_hi = umma_desc_mn_sw128_32b(s.v_hi + ks * 8 * kHd), dv_lo = umma_desc_mn_sw128_32b(s.v_lo + ks * 8 * kHd);
+          const uint32_t a_hi = tmem + 8 * ks, a_lo = tmem + kColPlo + 8 * ks;
+          mma_tf32_ta(tmem + kColO, a_lo, dv_hi, idesc_o, ks ? 1u : 0u);
+          mma_tf32_ta(tmem + kColO, a_hi, dv_lo, idesc_o, 1u);
+          mma_tf32_ta(tmem + kColO, a_hi, dv_hi, idesc_o, 1u);
+        }
+        tcgen05_commit(&s.bar_o);
+      }
+      __syncwarp();
+    }
+    // the next item's Q, K are split while the tensor core works on O
+    if (next < n_items) split_qk(ph ^ 1u);
+    mbar_wait(&s.bar_o, ph);
+    tcgen05_fence_after();
+    if (tid == 0 && next < n_items) load_v(next);
+    // ---- epilogue ---------------------------------------------------------------------------------------------------
+    if (qrev * 32 < L) {
+      uint32_t r[32];
+      TmemRow<32>::ld(tmem_row + kColO, r);
+      if (lane == 0) bulk_wait_read<0>();                    // the previous item's store has read the staging chunk
+      __syncwarp();
+      tmem_wait_ld();
+      const float inv = 1.f / l;
+      float4 (*stg)[8] = s.stage[warp];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 o;
+        o.x = __uint_as_float(r[4 * j + 0]) * inv;
+        o.y = __uint_as_float(r[4 * j + 1]) * inv;
+        o.z = __uint_as_float(r[4 * j + 2]) * inv;
+        o.w = __uint_as_float(r[4 * j + 3]) * inv;
+        stg[lrev][j ^ (lrev & 7)] = o;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&tmOut, stg, h * kHd, qrev * 32, b);
+        bulk_commit();
+      }
+    }
+    tcgen05_fence_before();      // the next item's MMAs overwrite S and O; its Q / K halves must be visible to them
+    __syncthreads();
+  }
+  if (lane == 0) bulk_wait_read<0>();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256) : "memory");
+  }
+}
+
+// Returns QX_EUNSUPPORTED when the shape is outside the kernel's range (the caller then falls back to the mma.sync
+// kernel of qx_tf_attn.cu).  qkv: [B*L][3d] packed rows, out: [B*L][d].
+int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhead, cudaStream_t st) {
+  if (d != nhead * kHd || L > kMaxKeys || L < 1 || B < 1) return QX_EUNSUPPORTED;
+  CUtensorMap mq, mv, mo;
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)(3 * d), (cuuint64_t)L, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)(3 * d) * 4, (cuuint64_t)L * 3 * d * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)kHd, (cuuint32_t)kRows, 1};
+    int rc = make_map_nd(&mq, qkv, 3, dims, strides, box);
+    if (rc) return rc;
+    // V is an MN-major operand of the second product: 32-B swizzle atoms (see umma_desc_mn_sw128_32b)
+    rc = make_map_nd(&mv, qkv, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)L, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)d * 4, (cuuint64_t)L * d * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)kHd, 32, 1};
+    const int rc = make_map_nd(&mo, out, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  static bool cfg = false;
+  static int num_sms = 0;
+  if (!cfg) {
+    cudaFuncSetAttribute(tf_attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmem));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cfg = true;
+  }
+  const int n_items = B * nhead;
+  const char* env_dbg = getenv("QX_TF_ATTN_DBG");
+  const int dbg = env_dbg ? atoi(env_dbg) : 0;
+  const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;
+  tf_attention_umma_kernel<<<grid, 128, sizeof(AttnSmem), st>>>(mq, mv, mo, n_items, nhead, L, d, dbg);
+  QX_CHECK_LAUNCH("tf_attention_umma_kernel");
+  return QX_OK;
+}
+
+}  // namespace qx

@@ -10,6 +10,7 @@
 // anchor of the tensor-core path (qx_tf_tc.cu): embed -> [QKV GEMM -> attention -> out-proj GEMM
 // -> add+LN -> FFN1 GEMM+ReLU -> FFN2 GEMM -> add+LN] x layers -> output head + de-normalise +
 // unpack into gain records.
+#include <stdlib.h>
 #include "qx_tf_common.cuh"
 
 namespace qx {
@@ -350,6 +351,7 @@ static int gemm(const float* A, const float* W, const float* bias, float* C, int
 
 // tensor-core GEMM (qx_tf_tc.cu)
 int tf_attention_tc(const float* qkv, float* out, int B, int L, int d, int nhead, cudaStream_t st);   // qx_tf_attn.cu
+int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhead, cudaStream_t st); // qx_tf_attn05.cu
 int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* bias, float* C, int M, int N, int K,
                bool relu, cudaStream_t st);
 int tf_split_weights(const float* w, float* hi, float* lo, size_t count, cudaStream_t st);
@@ -412,8 +414,14 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
     const float* lw = w + lay.layer0 + (size_t)l * lay.layer_stride;
     int rc = dense(h, lw, lay.l_inw, lay.l_inb, sp.in_hi, sp.in_lo, l, qkv, 3 * d, d, false);
     if (rc) return rc;
-    // tensor-core path: attention on mma.sync 3xTF32 tiles (qx_tf_attn.cu) when the shape fits, else SIMT
-    rc = (wsplit != nullptr) ? tf_attention_tc(qkv, att, B, L, d, cfg->nhead, st) : QX_EUNSUPPORTED;
+    // tensor-core path: attention on tcgen05 (qx_tf_attn05.cu; QX_TF_ATTN_MMA=1 selects the mma.sync kernel of
+    // qx_tf_attn.cu for A/B runs) when the shape fits, else SIMT
+    rc = QX_EUNSUPPORTED;
+    if (wsplit != nullptr) {
+      const char* env_mma = getenv("QX_TF_ATTN_MMA");
+      if (!(env_mma != nullptr && env_mma[0] == '1')) rc = tf_attention_umma(qkv, att, B, L, d, cfg->nhead, st);
+      if (rc == QX_EUNSUPPORTED) rc = tf_attention_tc(qkv, att, B, L, d, cfg->nhead, st);
+    }
     if (rc == QX_EUNSUPPORTED) {
       tf_attention_kernel<32><<<dim3(cfg->nhead, B), 128, att_smem, st>>>(qkv, att, L, d);
       QX_CHECK_LAUNCH("tf_attention_kernel");
@@ -519,4 +527,25 @@ extern "C" int qx_tf_dense(const float* A, const float* w_hi, const float* w_lo,
   QX_CHECK_ARG(M >= 0 && N > 0 && K > 0, "bad shape");
   if (M == 0) return QX_OK;
   return qx::tf_gemm_tc(A, w_hi, w_lo, bias, C, M, N, K, relu != 0, static_cast<cudaStream_t>(stream));
+}
+
+// Causal self-attention core of nn.MultiheadAttention as the model uses it (transformer_model.py:112-113, :134-136):
+// qkv [B*L][3d] packed in_proj output -> out [B*L][d] (heads concatenated), head dimension 32.
+// impl 0: tcgen05 kernel, 1: mma.sync kernel, 2: exact-fp32 CUDA-core kernel.
+extern "C" int qx_tf_attention(const float* qkv, float* out, int B, int L, int d, int nhead, int impl, void* stream) {
+  QX_CHECK_ARG(qkv && out, "null pointer");
+  QX_CHECK_ARG(B >= 0 && L > 0 && d > 0 && nhead > 0 && d == 32 * nhead, "bad shape (head dimension must be 32)");
+  if (B == 0) return QX_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (impl == 0) return qx::tf_attention_umma(qkv, out, B, L, d, nhead, st);
+  if (impl == 1) return qx::tf_attention_tc(qkv, out, B, L, d, nhead, st);
+  QX_CHECK_ARG(impl == 2, "impl must be 0, 1 or 2");
+  static bool att_cfg = false;
+  if (!att_cfg) {
+    cudaFuncSetAttribute(qx::tf_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    att_cfg = true;
+  }
+  qx::tf_attention_kernel<32><<<dim3(nhead, B), 128, (size_t)2 * L * 32 * sizeof(float), st>>>(qkv, out, L, d);
+  QX_CHECK_LAUNCH("tf_attention_kernel");
+  return QX_OK;
 }

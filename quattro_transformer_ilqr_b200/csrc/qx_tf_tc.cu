@@ -22,7 +22,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 
-#include "qx_async.cuh"
+#include "qx_tc05.cuh"
 #include "qx_tf_common.cuh"
 
 namespace qx {
@@ -44,46 +44,6 @@ struct GemmSmem {
 };
 constexpr size_t kGemmSmemBytes = sizeof(GemmSmem) + 1024;   // + slack to align the ring to 1024 B
 
-// ---- PTX wrappers ------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-// K-major, 128-B swizzle: rows at 128-B pitch, 8-row groups 1024 B apart (SBO), version 1 (sm_100)
-__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_u32(smem) >> 4) & 0x3fff);       // start address
-  d |= (uint64_t)1 << 16;                                // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset
-  d |= (uint64_t)1 << 46;                                // descriptor version
-  d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
-  return d;
-}
-// hi = a rounded to the nearest TF32 (10 explicit mantissa bits), lo = the exact remainder rounded
-// to TF32 as well: a*w - (hi*w_hi + hi*w_lo + lo*w_hi) is then ~3 * 2^-24 |a w| (fp32-class accuracy).
-__device__ __forceinline__ float tf32_rn(float v) {
-  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
-}
-__device__ __forceinline__ void tf32_split(float v, float& hi, float& lo) {
-  hi = tf32_rn(v);
-  lo = tf32_rn(v - hi);
-}
 // D = F32, A = B = TF32, both K-major, M = 128, N = 128
 constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 
@@ -290,40 +250,6 @@ struct TaSmem {
 constexpr size_t kTaSmemBytes = sizeof(TaSmem) + 1024;
 static_assert(kTaSmemBytes <= 227 * 1024, "TMEM-A GEMM exceeds the shared memory of an SM");
 
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)),
-               "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void mma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
-        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.b32 %0, 1, 0, P;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
 // kSets sets of four splitter warps take the K blocks in turn.  A set must meet EVERY phase of the barriers it waits
 // on (a parity wait cannot tell phase p from phase p + 2), hence ring depths that are multiples of the set count.
 // STREAM_W: K > 128, the weight ring cycles (K % 128 == 0 keeps block kb in slot kb % 4).
@@ -524,42 +450,12 @@ __global__ void tf_split_kernel(const float* __restrict__ w, float* __restrict__
   lo[i] = l;
 }
 
-// ---- host side ------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
 // row-major fp32 matrix [rows][cols] -> tiled map with a (32 x 128) box and 128-B swizzle
 static int make_map(CUtensorMap* map, const float* base, int rows, int cols, int box_cols = kBK, int box_rows = kBM) {
-  EncodeTiledFn fn = encode_fn();
-  if (fn == nullptr) {
-    set_error("cuTensorMapEncodeTiled is not available from the driver");
-    return QX_ECUDA;
-  }
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
   const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %d cols %d)", (int)r, rows, cols);
-    return QX_ECUDA;
-  }
-  return QX_OK;
+  return make_map_nd(map, base, 2, dims, strides, box);
 }
 
 int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* bias, float* C, int M, int N, int K,

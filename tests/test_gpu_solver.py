@@ -321,6 +321,31 @@ def test_resident_weight_gemm_equals_streaming_gemm_bitwise(system, golden_dir, 
 
 
 @pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
+@pytest.mark.parametrize("mode", ["rand", "fp32"])
+def test_tcgen05_attention_matches_mma_sync_and_exact_attention(system, mode, golden_dir, monkeypatch):
+    """Attention on tcgen05 (S and P V as UMMA tiles, P through tensor memory, V as an MN-major operand) against the
+    mma.sync kernel and the exact-fp32 CUDA-core path: 1 200 trajectories = 4 800 (trajectory, head) items, 16 per
+    persistent CTA, L = 61 (keys padded to 64) and L = 101 (padded to 112, ragged last chunk)."""
+    g = np.load(f"{golden_dir}/tf_forward_{system}.npz")
+    w = _wrapper(system, mode)
+    rng = np.random.default_rng(6)
+    reps = 1200 // len(g["x_err"])
+    x = np.concatenate([g["x_err"] * (1.0 + 0.05 * rng.standard_normal(g["x_err"].shape)) for _ in range(reps)])
+    kK = np.concatenate([g["kK"] * (1.0 + 0.05 * rng.standard_normal(g["kK"].shape)) for _ in range(reps)])
+    monkeypatch.setenv("QX_TF_ATTN_MMA", "1")
+    mma = w.predict(x, kK)
+    monkeypatch.setenv("QX_TF_ATTN_MMA", "0")
+    umma = w.predict(x, kK)
+    w.tensor_cores = False
+    exact = w.predict(x, kK)
+    assert np.isfinite(umma).all()
+    e_mma, e_exact = relmax(umma, mma), relmax(umma, exact)
+    print(f"{system}/{mode}: tcgen05 attention vs mma.sync {e_mma:.2e}, vs exact fp32 {e_exact:.2e}; mma.sync vs exact {relmax(mma, exact):.2e}")
+    tol = 5e-6 if mode == "rand" else 5e-5
+    assert e_mma < tol and e_exact < tol
+
+
+@pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
 @pytest.mark.parametrize("mode", ["fp32", "rand"])
 def test_transformer_mode_matches_golden_runs(system, mode):
     """optimize() with the transformer in the loop vs the reference (same weights, fp32)."""
