@@ -66,7 +66,7 @@ struct TmemRow<32> {
 };
 template <>
 struct TmemRow<16> {
-  static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t (&r)[32]) {
+  static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -74,7 +74,7 @@ struct TmemRow<16> {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
   }
-  static __device__ __forceinline__ void st(uint32_t taddr, const uint32_t (&r)[32]) {
+  static __device__ __forceinline__ void st(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
         "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
@@ -83,16 +83,30 @@ struct TmemRow<16> {
         : "memory");
   }
 };
+template <>
+struct TmemRow<8> {
+  static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+  }
+  static __device__ __forceinline__ void st(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+  }
+};
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// hi in place, lo into the second tile; thread = row, its eight 16-B pieces visited in swizzle order
-__device__ __forceinline__ void split_tile_row(float* hi_tile, float* lo_tile, int row) {
+// Two threads per tile row (half = 0 / 1 takes the 16-B pieces 4 half .. 4 half + 3 of the row's 128 B).
+// hi in place, lo into the second tile; pieces visited in swizzle order (bank-conflict free)
+__device__ __forceinline__ void split_tile_row(float* hi_tile, float* lo_tile, int row, int half) {
   float4* hi4 = reinterpret_cast<float4*>(hi_tile) + row * 8;
   float4* lo4 = reinterpret_cast<float4*>(lo_tile) + row * 8;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = j ^ (row & 7);
+  for (int jj = 0; jj < 4; ++jj) {
+    const int c = (4 * half + jj) ^ (row & 7);
     const float4 v = hi4[c];
     float4 h, l;
     tf32_split(v.x, h.x, l.x);
@@ -104,27 +118,22 @@ __device__ __forceinline__ void split_tile_row(float* hi_tile, float* lo_tile, i
   }
 }
 
-// The Q tile: scaled by log2(e) / sqrt(32) (the scores then are base-2 logits), split, and written to row `dst`
-// (= row, or 127 - row in a flipped CTA) - through registers, with a barrier between the reads and the writes.
-__device__ __forceinline__ void split_q_row(float* hi_tile, float* lo_tile, int row, int dst, float scale) {
-  const float4* src = reinterpret_cast<const float4*>(hi_tile) + row * 8;
-  float4 h[8], l[8];
+// The Q tile is scaled by log2(e) / sqrt(32) on the way (the scores then are base-2 logits)
+__device__ __forceinline__ void split_q_row(float* hi_tile, float* lo_tile, int row, int half, float scale) {
+  float4* hi4 = reinterpret_cast<float4*>(hi_tile) + row * 8;
+  float4* lo4 = reinterpret_cast<float4*>(lo_tile) + row * 8;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {                   // logical 16-B piece j of the row
-    float4 v = src[j ^ (row & 7)];
+  for (int jj = 0; jj < 4; ++jj) {
+    const int c = (4 * half + jj) ^ (row & 7);
+    float4 v = hi4[c];
     v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
-    tf32_split(v.x, h[j].x, l[j].x);
-    tf32_split(v.y, h[j].y, l[j].y);
-    tf32_split(v.z, h[j].z, l[j].z);
-    tf32_split(v.w, h[j].w, l[j].w);
-  }
-  __syncthreads();
-  float4* hi4 = reinterpret_cast<float4*>(hi_tile) + dst * 8;
-  float4* lo4 = reinterpret_cast<float4*>(lo_tile) + dst * 8;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    hi4[j ^ (dst & 7)] = h[j];
-    lo4[j ^ (dst & 7)] = l[j];
+    float4 h, l;
+    tf32_split(v.x, h.x, l.x);
+    tf32_split(v.y, h.y, l.y);
+    tf32_split(v.z, h.z, l.z);
+    tf32_split(v.w, h.w, l.w);
+    hi4[c] = h;
+    lo4[c] = l;
   }
 }
 
@@ -133,37 +142,51 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// the two threads of a row (warps w and w + 4) meet on named barrier 1 + (w % 4)
+__device__ __forceinline__ void pair_sync(int wq) {
+  switch (wq) {      // immediate barrier numbers: the kernel then reserves 5 of the 16 barriers, not all of them
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
+}
 
-// Softmax of one query row whose scores sit in this thread's TMEM lane: Q full chunks of 32 keys, then the chunk
-// that holds the diagonal (WD = 32 or 16 columns, keys 32 Q + t with t <= lrev unmasked).  One sweep: all loads
-// first (their latencies overlap), exact row maximum, P = 2^(s - m), row sum, (hi, lo) halves back into TMEM
-// (P_hi over the scores).  Returns the row sum.
+// Softmax of one query row whose scores sit in this thread's TMEM lane; the row's two threads take the lower / upper
+// half of the columns of every chunk: Q full chunks of 32 keys (16 columns each), then the chunk that holds the
+// diagonal (WD = 32 or 16 columns wide, HW = WD / 2 per thread; key 32 Q + t is unmasked for t <= lrev).  One sweep:
+// all loads first (their latencies overlap), partial maxima exchanged through shared memory, P = 2^(s - m), partial
+// row sum, (hi, lo) halves back into TMEM (P_hi over the scores).  Returns this thread's partial row sum.
 template <int Q, int WD>
-__device__ __forceinline__ float softmax_row(uint32_t tmem_row, int lrev) {
-  uint32_t r[Q + 1][32];
+__device__ __forceinline__ float softmax_half_row(uint32_t tmem_row, int lrev, int half, int wq, float* pmax, int tid) {
+  constexpr int HW = WD / 2;
+  uint32_t r[Q + 1][16];
 #pragma unroll
-  for (int c = 0; c < Q; ++c) TmemRow<32>::ld(tmem_row + 32 * c, r[c]);
-  TmemRow<WD>::ld(tmem_row + 32 * Q, r[Q]);
+  for (int c = 0; c < Q; ++c) TmemRow<16>::ld(tmem_row + 32 * c + 16 * half, r[c]);
+  TmemRow<HW>::ld(tmem_row + 32 * Q + HW * half, r[Q]);
   tmem_wait_ld();
   float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};      // four chains: the reductions are latency-bound
 #pragma unroll
   for (int c = 0; c < Q; ++c) {
 #pragma unroll
-    for (int t = 0; t < 32; ++t) m4[t & 3] = fmaxf(m4[t & 3], __uint_as_float(r[c][t]));
+    for (int t = 0; t < 16; ++t) m4[t & 3] = fmaxf(m4[t & 3], __uint_as_float(r[c][t]));
   }
 #pragma unroll
-  for (int t = 0; t < WD; ++t) {
-    if (t <= lrev) m4[t & 3] = fmaxf(m4[t & 3], __uint_as_float(r[Q][t]));
+  for (int t = 0; t < HW; ++t) {
+    if (HW * half + t <= lrev) m4[t & 3] = fmaxf(m4[t & 3], __uint_as_float(r[Q][t]));
   }
-  const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+  float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+  pmax[tid] = m;
+  pair_sync(wq);
+  m = fmaxf(m, pmax[tid ^ 128]);           // key 0 is never masked, so the lower half's maximum is always finite
   float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int c = 0; c <= Q; ++c) {
-    uint32_t lo[32];
+    uint32_t lo[16];
 #pragma unroll
-    for (int t = 0; t < ((c < Q) ? 32 : WD); ++t) {
+    for (int t = 0; t < ((c < Q) ? 16 : HW); ++t) {
       float p = ex2_approx(__uint_as_float(r[c][t]) - m);
-      if (c == Q && t > lrev) p = 0.f;
+      if (c == Q && HW * half + t > lrev) p = 0.f;
       l4[t & 3] += p;
       float h, lw;
       tf32_split(p, h, lw);
@@ -171,44 +194,43 @@ __device__ __forceinline__ float softmax_row(uint32_t tmem_row, int lrev) {
       lo[t] = __float_as_uint(lw);
     }
     if (c < Q) {
-      TmemRow<32>::st(tmem_row + 32 * c, r[c]);
-      TmemRow<32>::st(tmem_row + kColPlo + 32 * c, lo);
+      TmemRow<16>::st(tmem_row + 32 * c + 16 * half, r[c]);
+      TmemRow<16>::st(tmem_row + kColPlo + 32 * c + 16 * half, lo);
     } else {
-      TmemRow<WD>::st(tmem_row + 32 * c, r[c]);
-      TmemRow<WD>::st(tmem_row + kColPlo + 32 * c, lo);
+      TmemRow<HW>::st(tmem_row + 32 * c + HW * half, r[c]);
+      TmemRow<HW>::st(tmem_row + kColPlo + 32 * c + HW * half, lo);
     }
   }
   return (l4[0] + l4[1]) + (l4[2] + l4[3]);
 }
-template <int W>
-__device__ __forceinline__ void chunk_zero(uint32_t tmem_row, int key0) {
-  uint32_t z[32];
+template <int HW>
+__device__ __forceinline__ void chunk_zero(uint32_t tmem_row, int col0) {
+  uint32_t z[16];
 #pragma unroll
-  for (int t = 0; t < 32; ++t) z[t] = 0u;
-  TmemRow<W>::st(tmem_row + key0, z);
-  TmemRow<W>::st(tmem_row + kColPlo + key0, z);
+  for (int t = 0; t < 16; ++t) z[t] = 0u;
+  TmemRow<HW>::st(tmem_row + col0, z);
+  TmemRow<HW>::st(tmem_row + kColPlo + col0, z);
 }
 
 }  // namespace
 
-// grid: min(B * nhead, 2 * SMs) persistent CTAs of 128 threads; item = trajectory * nhead + head.
-// flip: the CTAs of the upper half of the grid keep their query rows in REVERSED lane order (token 127 - lane), so
-// that of two CTAs sharing an SM one has its long causal rows in warp 3 and the other in warp 0 - warps w of both
-// CTAs sit on the same scheduler, and the softmax work per scheduler evens out (144 : 160 : 160 : 144 keys instead
-// of 64 : 128 : 192 : 224).
-__global__ void __launch_bounds__(128, 2)
+// grid: min(B * nhead, 2 * SMs) persistent CTAs of 256 threads; item = trajectory * nhead + head.
+// Two threads per query row (warps w and w + 4 share TMEM lane quarter w % 4 and split every chunk's columns), so an
+// SM holds 16 warps: the softmax and the operand splits are latency-bound CUDA-core work and need the occupancy.
+// (Tried and dropped: reversing the row order in every second CTA so that the long causal rows of two co-resident
+// CTAs land on different schedulers - 0.65 ms against 0.59 ms without.)
+__global__ void __launch_bounds__(256, 2)
 tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmV,
                          const __grid_constant__ CUtensorMap tmOut, int n_items, int nhead, int L, int d, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   AttnSmem& s = *reinterpret_cast<AttnSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wq = warp & 3, half = warp >> 2;        // TMEM lane quarter; which half of the row's columns
+  const int row = wq * 32 + lane;                   // tile row / TMEM lane of this thread
   const int NK = (L + 15) & ~15;                    // keys padded to the UMMA N granularity
   const int nks = (L + 7) >> 3;                     // K = 8 steps of the second product
-  const uint32_t idesc_s = idesc_tf32(NK, false), idesc_o = idesc_tf32(kHd, !(dbg & 8));
-  const bool flip = (gridDim.x > 1) && ((int)blockIdx.x >= (int)(gridDim.x + 1) / 2) && !(dbg & 1);
-  const int qrev = flip ? 3 - warp : warp;          // logical quarter: this thread's token is 32 qrev + lrev
-  const int lrev = flip ? 31 - lane : lane;
-  const int q_dst = flip ? kRows - 1 - tid : tid;   // tile row that holds this thread's loaded Q row
+  const uint32_t idesc_s = idesc_tf32(NK, false), idesc_o = idesc_tf32(kHd, true);
+  const int qrev = wq, lrev = lane;                 // this thread's token is 32 qrev + lrev
 
   if (tid == 0) {
     if (smem_u32(smem_raw) & 1023u) __trap();       // the swizzled tiles need 1 KB alignment
@@ -227,7 +249,7 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = s.tmem_base;
-  const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);     // this warp's lane quarter
+  const uint32_t tmem_row = tmem + ((uint32_t)(wq * 32) << 16);       // this warp's lane quarter
   const float scale_log2 = rsqrtf((float)kHd) * 1.4426950408889634f;  // softmax in base 2: exp(x) = 2^(x log2 e)
 
   auto load_qk = [&](int item) {
@@ -241,10 +263,14 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     mbar_arrive_expect_tx(&s.bar_v, kTile * 4);
     tma_load_3d(&tmV, &s.bar_v, s.v_hi, 2 * d + h * kHd, 0, b);
   };
+  // The two threads of a row exchange their partial maximum / sum through the last 16 rows of the K_lo tile: the
+  // first product reads N <= 112 key rows, so those 2 KB are never an operand (and the K split leaves them alone).
+  float* const pmax = s.k_lo + kMaxKeys * kHd;
+  float* const psum = pmax + 256;
   auto split_qk = [&](uint32_t ph) {
     mbar_wait(&s.bar_qk, ph);
-    split_tile_row(s.k_hi, s.k_lo, tid);
-    split_q_row(s.q_hi, s.q_lo, tid, q_dst, scale_log2);
+    if (row < kMaxKeys) split_tile_row(s.k_hi, s.k_lo, row, half);
+    split_q_row(s.q_hi, s.q_lo, row, half, scale_log2);
     fence_proxy_async();
   };
   if ((int)blockIdx.x < n_items) {
@@ -282,29 +308,30 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     }
     // V is split while the tensor core works on S
     mbar_wait(&s.bar_v, ph);
-    split_tile_row(s.v_hi, s.v_lo, tid);
+    split_tile_row(s.v_hi, s.v_lo, row, half);
     fence_proxy_async();
 
     mbar_wait(&s.bar_s, ph);
     tcgen05_fence_after();
     if (tid == 0 && next < n_items) load_qk(next);          // Q, K tiles are free: request the next item's
-    // ---- softmax (thread = row) -----------------------------------------------------------------------------------
-    float l = 1.f;
+    // ---- softmax (two threads per row) --------------------------------------------------------------------------
     if (qrev * 32 < L && !(dbg & 4)) {
       const bool wide = NK - 32 * qrev >= 32;
+      float l;
       switch (qrev * 2 + (wide ? 1 : 0)) {
-        case 0: l = softmax_row<0, 16>(tmem_row, lrev); break;
-        case 1: l = softmax_row<0, 32>(tmem_row, lrev); break;
-        case 2: l = softmax_row<1, 16>(tmem_row, lrev); break;
-        case 3: l = softmax_row<1, 32>(tmem_row, lrev); break;
-        case 4: l = softmax_row<2, 16>(tmem_row, lrev); break;
-        case 5: l = softmax_row<2, 32>(tmem_row, lrev); break;
-        case 6: l = softmax_row<3, 16>(tmem_row, lrev); break;
-        default: l = softmax_row<3, 32>(tmem_row, lrev); break;
+        case 0: l = softmax_half_row<0, 16>(tmem_row, lrev, half, wq, pmax, tid); break;
+        case 1: l = softmax_half_row<0, 32>(tmem_row, lrev, half, wq, pmax, tid); break;
+        case 2: l = softmax_half_row<1, 16>(tmem_row, lrev, half, wq, pmax, tid); break;
+        case 3: l = softmax_half_row<1, 32>(tmem_row, lrev, half, wq, pmax, tid); break;
+        case 4: l = softmax_half_row<2, 16>(tmem_row, lrev, half, wq, pmax, tid); break;
+        case 5: l = softmax_half_row<2, 32>(tmem_row, lrev, half, wq, pmax, tid); break;
+        case 6: l = softmax_half_row<3, 16>(tmem_row, lrev, half, wq, pmax, tid); break;
+        default: l = softmax_half_row<3, 32>(tmem_row, lrev, half, wq, pmax, tid); break;
       }
-      for (int c = qrev + 1; 32 * c < NK; ++c) {             // keys beyond the warp's causal range: P = 0
-        if (NK - 32 * c >= 32) chunk_zero<32>(tmem_row, 32 * c);
-        else chunk_zero<16>(tmem_row, 32 * c);
+      psum[tid] = l;
+      for (int c = qrev + 1; 32 * c < NK; ++c) {             // keys beyond the quarter's causal range: P = 0
+        if (NK - 32 * c >= 32) chunk_zero<16>(tmem_row, 32 * c + 16 * half);
+        else chunk_zero<8>(tmem_row, 32 * c + 8 * half);
       }
       tmem_wait_st();
     }
@@ -330,27 +357,27 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     mbar_wait(&s.bar_o, ph);
     tcgen05_fence_after();
     if (tid == 0 && next < n_items) load_v(next);
-    // ---- epilogue ---------------------------------------------------------------------------------------------------
+    // ---- epilogue: each thread 16 of the row's 32 output dims -----------------------------------------------------
     if (qrev * 32 < L) {
-      uint32_t r[32];
-      TmemRow<32>::ld(tmem_row + kColO, r);
-      if (lane == 0) bulk_wait_read<0>();                    // the previous item's store has read the staging chunk
-      __syncwarp();
+      uint32_t r[16];
+      TmemRow<16>::ld(tmem_row + kColO + 16 * half, r);
+      if (half == 0 && lane == 0) bulk_wait_read<0>();       // the previous item's store has read the staging chunk
+      pair_sync(wq);
       tmem_wait_ld();
-      const float inv = 1.f / l;
-      float4 (*stg)[8] = s.stage[warp];
+      const float inv = 1.f / (psum[tid & 127] + psum[(tid & 127) + 128]);
+      float4 (*stg)[8] = s.stage[wq];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int jj = 0; jj < 4; ++jj) {
         float4 o;
-        o.x = __uint_as_float(r[4 * j + 0]) * inv;
-        o.y = __uint_as_float(r[4 * j + 1]) * inv;
-        o.z = __uint_as_float(r[4 * j + 2]) * inv;
-        o.w = __uint_as_float(r[4 * j + 3]) * inv;
-        stg[lrev][j ^ (lrev & 7)] = o;
+        o.x = __uint_as_float(r[4 * jj + 0]) * inv;
+        o.y = __uint_as_float(r[4 * jj + 1]) * inv;
+        o.z = __uint_as_float(r[4 * jj + 2]) * inv;
+        o.w = __uint_as_float(r[4 * jj + 3]) * inv;
+        stg[lrev][(4 * half + jj) ^ (lrev & 7)] = o;
       }
       fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) {
+      pair_sync(wq);
+      if (half == 0 && lane == 0) {
         tma_store_3d(&tmOut, stg, h * kHd, qrev * 32, b);
         bulk_commit();
       }
@@ -358,7 +385,7 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     tcgen05_fence_before();      // the next item's MMAs overwrite S and O; its Q / K halves must be visible to them
     __syncthreads();
   }
-  if (lane == 0) bulk_wait_read<0>();
+  if (half == 0 && lane == 0) bulk_wait_read<0>();
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -401,7 +428,7 @@ int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhe
   const char* env_dbg = getenv("QX_TF_ATTN_DBG");
   const int dbg = env_dbg ? atoi(env_dbg) : 0;
   const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;
-  tf_attention_umma_kernel<<<grid, 128, sizeof(AttnSmem), st>>>(mq, mv, mo, n_items, nhead, L, d, dbg);
+  tf_attention_umma_kernel<<<grid, 256, sizeof(AttnSmem), st>>>(mq, mv, mo, n_items, nhead, L, d, dbg);
   QX_CHECK_LAUNCH("tf_attention_umma_kernel");
   return QX_OK;
 }
