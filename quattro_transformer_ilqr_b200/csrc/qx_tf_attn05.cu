@@ -150,6 +150,7 @@ __device__ __forceinline__ void pair_sync(int wq) {
     case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
     default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
   }
+  __syncwarp();
 }
 
 // Softmax of one query row whose scores sit in this thread's TMEM lane; the row's two threads take the lower / upper
@@ -314,6 +315,7 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     mbar_wait(&s.bar_s, ph);
     tcgen05_fence_after();
     if (tid == 0 && next < n_items) load_qk(next);          // Q, K tiles are free: request the next item's
+    __syncwarp();                // reconverge (per-lane spins, thread 0's detour): the tcgen05.ld / st below are .sync.aligned
     // ---- softmax (two threads per row) --------------------------------------------------------------------------
     if (qrev * 32 < L && !(dbg & 4)) {
       const bool wide = NK - 32 * qrev >= 32;
@@ -357,6 +359,7 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     mbar_wait(&s.bar_o, ph);
     tcgen05_fence_after();
     if (tid == 0 && next < n_items) load_v(next);
+    __syncwarp();
     // ---- epilogue: each thread 16 of the row's 32 output dims -----------------------------------------------------
     if (qrev * 32 < L) {
       uint32_t r[16];

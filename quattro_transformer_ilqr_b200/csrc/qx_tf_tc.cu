@@ -42,7 +42,7 @@ struct GemmSmem {
   uint64_t full[kGemmStages], ready[kGemmStages], empty[kGemmStages], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
-constexpr size_t kGemmSmemBytes = sizeof(GemmSmem) + 1024;   // + slack to align the ring to 1024 B
+constexpr size_t kGemmSmemBytes = sizeof(GemmSmem);
 
 // D = F32, A = B = TF32, both K-major, M = 128, N = 128
 constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
@@ -52,8 +52,11 @@ __global__ void __launch_bounds__(320, 1)
 tf_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
                   const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, float* __restrict__ C,
                   int M, int N, int K) {
-  extern __shared__ uint8_t smem_raw[];
-  GemmSmem& s = *reinterpret_cast<GemmSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // No integer round trip on the pointer: the compiler must KNOW these are shared-memory accesses (LDS / STS).  As
+  // generic LD.E they are not ordered against the mbarrier arrive that hands a buffer back to the TMA producer.
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  GemmSmem& s = *reinterpret_cast<GemmSmem*>(smem_raw);
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u)) __trap();   // the swizzled tiles need 1 KB alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = K / kBK;
   const int n_tiles_n = N / kBN;
@@ -157,6 +160,7 @@ tf_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int n0 = (tile % n_tiles_n) * kBN, m0 = (tile / n_tiles_n) * kBM;
       const uint32_t buf = tl & 1u;
       mbar_wait(&s.acc_full[buf], (tl >> 1) & 1u);
+      __syncwarp();        // reconverge after the per-lane spin: tcgen05.ld / wait::ld are .sync.aligned
       tcgen05_fence_after();
 #pragma unroll
       for (int c0 = 0; c0 < kBN; c0 += 32) {
@@ -221,8 +225,7 @@ tf_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // Here:
 //  * the splitter (thread = row) reads its raw A row from the TMA landing block and writes A_hi / A_lo straight
 //    into TMEM (tcgen05.st, lane = row, column = k); the MMAs take A from there (tcgen05.mma [d], [a], b-desc), so
-//    shared memory only carries the landing of raw A, one read of it, and the B operand.  A raw block is free as
-//    soon as the splitter has it in registers: the raw ring is pure latency cover;
+//    shared memory only carries the landing of raw A, one read of it, and the B operand;
 //  * the whole MMA warp walks the issue loop (warp-uniform operands -> uniform registers, UTCHMMAs 1-4 instructions
 //    apart), one elected lane issues;
 //  * the epilogue stages 32 x 32 chunks in the 128-B-swizzle box layout and lets TMA store them
@@ -247,7 +250,7 @@ struct TaSmem {
       acc_empty[2];
   uint32_t tmem_base;
 };
-constexpr size_t kTaSmemBytes = sizeof(TaSmem) + 1024;
+constexpr size_t kTaSmemBytes = sizeof(TaSmem);
 static_assert(kTaSmemBytes <= 227 * 1024, "TMEM-A GEMM exceeds the shared memory of an SM");
 
 // kSets sets of four splitter warps take the K blocks in turn.  A set must meet EVERY phase of the barriers it waits
@@ -260,8 +263,12 @@ tf_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmC,
                   const float* __restrict__ bias, int M, int N, int K, int dbg) {
   static_assert(kTaRaw % kSets == 0 && kTaA % kSets == 0, "ring depths must be multiples of the splitter set count");
-  extern __shared__ uint8_t smem_raw[];
-  TaSmem& s = *reinterpret_cast<TaSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // No integer round trip on the pointer: the compiler must KNOW these are shared-memory accesses.  With generic
+  // LD.E.128 for the splitter's raw-row reads, the mbarrier arrive that hands the raw block back to the producer was
+  // issued while the loads were still in flight, and every ~20th launch a few rows picked up the NEXT block's data.
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  TaSmem& s = *reinterpret_cast<TaSmem*>(smem_raw);
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u)) __trap();   // the swizzled tiles need 1 KB alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = STREAM_W ? K / kBK : kTaW;
   const int n_tiles_n = N / kBN;
@@ -371,12 +378,16 @@ tf_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tf32_split(v.z, h, l); hi[4 * j + 2] = __float_as_uint(h); lo[4 * j + 2] = __float_as_uint(l);
         tf32_split(v.w, h, l); hi[4 * j + 3] = __float_as_uint(h); lo[4 * j + 3] = __float_as_uint(l);
       }
-      mbar_arrive(&s.raw_empty[st]);                   // the raw block is in registers: hand it back to the producer
       mbar_wait(&s.a_empty[sa], ((it / kTaA) & 1u) ^ 1u);
+      __syncwarp();        // the lanes leave the spin loop one by one; tcgen05.st / wait::st are .sync.aligned
       tcgen05_fence_after();
       const uint32_t taddr = tmem_a0 + sa * (2 * kBK) + ((uint32_t)(q * 32) << 16);
       tmem_st_32x32b_x32(taddr, hi);
       tmem_st_32x32b_x32(taddr + kBK, lo);
+      // Hand the raw block back to the producer only now: the stores above consume every loaded value, so the LDS have
+      // returned.  (An arrive placed right after the loads is issued while they are in flight - nothing orders a
+      // pending shared-memory read against the TMA write the arrive unblocks; that cost a few rows every ~100th launch.)
+      mbar_arrive(&s.raw_empty[st]);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tcgen05_fence_before();
       mbar_arrive(&s.a_ready[sa]);
@@ -389,6 +400,7 @@ tf_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int m0 = mt * kBM;
       const uint32_t buf = tl & 1u;
       mbar_wait(&s.acc_full[buf], (tl >> 1) & 1u);
+      __syncwarp();        // reconverge after the per-lane spin: tcgen05.ld / wait::ld are .sync.aligned
       tcgen05_fence_after();
       if (!(dbg & 4)) {
 #pragma unroll

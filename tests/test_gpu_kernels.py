@@ -312,3 +312,80 @@ def test_abi_rejects_bad_arguments():
         e.set_problem(np.zeros((8, 5)), np.zeros((8, 30, 1)))
     with pytest.raises(RuntimeError, match="qx_riccati failed"):
         e.riccati(t_start=30)
+
+
+# ---------------------------------------------------------------------------- tensor-core operators
+def _ptr(t):
+    import ctypes as C
+    return C.c_void_p(t.data_ptr())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,K,relu", [(512, 128, 1), (384, 128, 0), (128, 512, 0), (128, 128, 0)])
+def test_dense_layer_accuracy_and_run_to_run_determinism(N, K, relu):
+    """qx_tf_dense (tcgen05, A operand in tensor memory) against float64 on a ragged row count, and 40 launches on
+    identical inputs at the benchmark row count: the kernel is deterministic by construction, so any difference
+    between two launches is a synchronisation hole (one was found this way: the raw A block was handed back to the
+    TMA producer while the splitter's shared-memory reads were still in flight)."""
+    import ctypes as C
+    from quattro_transformer_ilqr_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    torch.manual_seed(3)
+    W = torch.randn(N, K, device=dev) / K ** 0.5
+    b = torch.randn(N, device=dev)
+    hi, lo = torch.empty_like(W), torch.empty_like(W)
+    _lib.check(lib.qx_tf_split(_ptr(W), _ptr(hi), _ptr(lo), C.c_size_t(W.numel()), st), "qx_tf_split")
+    assert torch.equal(hi + lo, W) or float((hi + lo - W).abs().max()) < 1e-7 * float(W.abs().max())
+    for M, reps in [(1000 * 61 + 7, 2), (8192 * 101, 40)]:
+        A = torch.randn(M, K, device=dev)
+        first = None
+        for i in range(reps):
+            out = torch.full((M, N), float("nan"), device=dev)
+            _lib.check(lib.qx_tf_dense(_ptr(A), _ptr(hi), _ptr(lo), _ptr(b), _ptr(out), M, N, K, relu, st), "qx_tf_dense")
+            torch.cuda.synchronize()
+            if first is None:
+                first = out
+                exact = A[:4096].double() @ W.double().T + b.double()
+                tail = A[-300:].double() @ W.double().T + b.double()
+                if relu:
+                    exact, tail = exact.clamp_min(0), tail.clamp_min(0)
+                scale = float(exact.abs().max())
+                assert float((out[:4096].double() - exact).abs().max()) < 5e-6 * scale
+                assert float((out[-300:].double() - tail).abs().max()) < 5e-6 * scale
+            else:
+                assert torch.equal(out, first), f"launch {i} differs from launch 0 (M={M})"
+        del A, first, out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L", [101, 61, 112, 37, 5])
+def test_attention_operator_all_kernels_and_determinism(L):
+    """qx_tf_attention: tcgen05 and mma.sync kernels against a float64 causal softmax attention, sequence lengths
+    with full, ragged and single key chunks; 20 launches of the tcgen05 kernel must be bit-identical."""
+    import ctypes as C
+    from quattro_transformer_ilqr_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    torch.manual_seed(4)
+    B, d, H = 700, 128, 4
+    qkv = torch.randn(B * L, 3 * d, device=dev)
+    x = qkv.double().view(B, L, 3, H, 32)
+    q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
+    sc = (q @ k.transpose(-1, -2)) / 32.0 ** 0.5
+    sc = sc.masked_fill(torch.triu(torch.ones(L, L, dtype=torch.bool, device=dev), 1), float("-inf"))
+    ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B * L, d)
+    first = None
+    for impl, reps in [(0, 20), (1, 1), (2, 1)]:
+        for i in range(reps):
+            out = torch.full((B * L, d), float("nan"), device=dev)
+            _lib.check(lib.qx_tf_attention(_ptr(qkv), _ptr(out), B, L, d, H, impl, st), "qx_tf_attention")
+            torch.cuda.synchronize()
+            assert float((out.double() - ref).abs().max()) < 5e-6 * float(ref.abs().max())
+            if impl == 0:
+                if first is None:
+                    first = out
+                else:
+                    assert torch.equal(out, first), f"tcgen05 attention: launch {i} differs from launch 0"
