@@ -255,6 +255,11 @@ riccati_quad_blk_kernel(const __grid_constant__ BlkConst cst, const float* __res
       qx[0] = l0.x; qx[1] = l0.y; qx[2] = l0.z; qx[3] = l0.w;
       qx[4] = l1.x; qx[5] = l1.y; qx[6] = l1.z; qx[7] = l1.w;
       qx[8] = l2.x; qx[9] = l2.y; qx[10] = l2.z; qx[11] = l2.w;
+      // every one of the 15 loads has RETURNED before the stage is handed to the next bulk copy: nothing else orders
+      // a shared-memory read still in flight against the async-proxy write that refills the stage
+      asm volatile("" ::"f"(v[0].x), "f"(v[1].x), "f"(v[2].x), "f"(v[3].x), "f"(v[4].x), "f"(v[5].x), "f"(v[6].x), "f"(v[7].x),
+                   "f"(v[8].x), "f"(v[9].x), "f"(v[10].x), "f"(v[11].x), "f"(l0.x), "f"(l1.x), "f"(l2.x)
+                   : "memory");
     }
     __syncwarp();
     // the record is in registers: refill its stage with the record of step k + stages
