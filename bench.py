@@ -64,6 +64,21 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# dense-equivalent flops of one transformer forward per trajectory (causal mask not exploited, all L
+# rows in every layer, as PyTorch does)
+TF_FLOPS = {"quadrotor": 135635456.0, "cartpole": 53757952.0}
+
+
+def tensor_peak():
+    """TF32 tensor peak = half of the measured dense bf16 figure (burst: the forward is timed alone, between events);
+    the kernels evaluate every product as 3xTF32, algorithmic flops are counted once."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return 0.5 * float(p["bf16_tflops"]), "0.5 x measured bf16 burst (MEASURED_PEAKS.json): kind::tf32 runs at half the bf16 rate"
+    return 0.5 * 1650.0, "0.5 x fallback bf16 figure (B200_PROFILING.md)"
+
+
 def ncu_reference(kernel, blk, system):
     """DRAM traffic and pipe utilisation of the dominant kernel from the committed `ncu --set full` summary of the
     same workload (profiles/): counters cannot be read live, the launch duration is (CUDA events, above)."""
@@ -214,6 +229,8 @@ def gpu_bench(args):
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
+    from quattro_transformer_ilqr_b200.sharding import bind_host_to_gpu
+    numa_bound = bind_host_to_gpu(local) if world > 1 else False     # before any pinned allocation (first touch)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:
@@ -389,15 +406,33 @@ def gpu_bench(args):
     dom = max(single, key=lambda k: kernels[k]["ms"])
     hbm, how = peaks()
     ncu = ncu_reference(dom, blk, system) if B == WORKLOADS[args.workload][2] else None
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["GBps"], "peak": hbm, "unit": "GB/s",
-                "frac": kernels[dom]["frac_hbm"], "traffic": ncu["traffic"] if ncu else None, "peak_source": how,
-                "algo_bytes_per_launch": kernels[dom]["algo_bytes_per_traj"] * B}
-    if ncu:
+    if use_tf:
+        # transformer mode: the forward (dense layers + attention on tcgen05) is 95 % of the step; it is a sequence of
+        # 22 launches, reported as one tensor-bound unit
+        tpeak, thow = tensor_peak()
+        tf_ms = kernels["transformer"]["ms"]
+        achieved = TF_FLOPS[system] * B / (tf_ms * 1e-3) / 1e12
+        kernels["transformer"].update({"algo_flops_per_traj": TF_FLOPS[system], "TFLOPs": round(achieved, 1),
+                                       "frac_tensor": round(achieved / tpeak, 4)})
+        roofline = {"kernel": "transformer forward (3xTF32 on tcgen05: dense layers + attention)", "bound": "tensor",
+                    "achieved": round(achieved, 1), "peak": tpeak, "unit": "TFLOP/s", "frac": round(achieved / tpeak, 4),
+                    "traffic": None, "peak_source": thow, "algo_flops_per_launch": TF_FLOPS[system] * B,
+                    "note": "fp32-accurate products cost three tensor-core MMAs each: the tensor pipe does 3x the algorithmic "
+                            "flops counted here; per-kernel tensor-pipe activity is in profiles/r1_ncu_full_transformer_summary.txt"}
+    else:
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["GBps"], "peak": hbm, "unit": "GB/s",
+                    "frac": kernels[dom]["frac_hbm"], "traffic": ncu["traffic"] if ncu else None, "peak_source": how,
+                    "algo_bytes_per_launch": kernels[dom]["algo_bytes_per_traj"] * B}
+    if ncu and not use_tf:
         roofline["ncu"] = ncu
-    if dom == "riccati":
+    if dom == "riccati" and not use_tf:
         roofline["note"] = ("the recursion is bound by fp32 instruction issue / the FMA pipe, not by HBM (SURVEY 8d asks for "
                             "both figures): see ncu.fma_pipe_pct and ncu.issue_active_pct")
-    cpu_val, cores, _, sample = cpu_reference(system, steps=2, warmup=1, iters_per_step=2)
+    if world == 1:      # the CPU leg runs at N = 1 only (at N > 1 the other ranks' host threads share the cores)
+        cpu_val, cores, _, sample = cpu_reference(system, steps=2, warmup=1, iters_per_step=2)
+        cpu_baseline = {"value": cpu_val, "unit": "trajectory-iterations/s", "cores": cores, "kind": "port", "sample": sample}
+    else:
+        cpu_baseline = None
     out = {
         "metric": "batched iLQR trajectory-iterations/sec (quadrotor, horizon 50)" if system == "quadrotor"
         else "batched iLQR trajectory-iterations/sec (cart-pole, horizon 30)",
@@ -411,9 +446,10 @@ def gpu_bench(args):
                    "l2": "working set per iteration (x, u ping-pong 0.21 GB + expansion 0.21 GB + gains 0.17 GB + "
                          "line-search scratch up to 0.53 GB at 16 384 trajectories) larger than the 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "trajectory-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "pipeline": f"{chunks} slices on {chunks} streams" if chunks > 1 else "single stream"},
+                "steps": e2e_steps, "pipeline": f"{chunks} slices on {chunks} streams" if chunks > 1 else "single stream",
+                "host_numa_bound": numa_bound},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels, "converge": converge,
-        "cpu_baseline": {"value": cpu_val, "unit": "trajectory-iterations/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": cpu_baseline,
     }
     args.emit(json.dumps(out))
     if world > 1:

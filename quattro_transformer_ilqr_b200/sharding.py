@@ -45,3 +45,30 @@ def gather_rows(local: torch.Tensor, total: int, group=None) -> torch.Tensor:
     if all(hi - lo == longest for lo, hi in sizes):
         return out
     return torch.cat([out[r * longest: r * longest + (hi - lo)] for r, (lo, hi) in enumerate(sizes)])
+
+
+def bind_host_to_gpu(device_index: int) -> bool:
+    """Pin the calling process to the CPU cores NVML reports as local to GPU ``device_index`` (its NUMA node / PCIe
+    root), BEFORE pinned host buffers are allocated: pinned pages are first-touched by the allocating thread, so the
+    host side of every H2D / D2H copy then lives in the memory of the socket the GPU hangs off.  With one process
+    per GPU on a two-socket box this keeps half of the ranks from pushing their 40 GB/s of result traffic across the
+    inter-socket link.  Best effort: returns False (and changes nothing) when NVML is not available."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        phys = device_index
+        if vis and all(v.strip().isdigit() for v in vis.split(",")):
+            phys = int(vis.split(",")[device_index])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, bits in enumerate(mask) for b in range(64) if (int(bits) >> b) & 1}
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return False
+        os.sched_setaffinity(0, allowed)
+        return True
+    except Exception:
+        return False
