@@ -68,25 +68,28 @@ tf_embed128_kernel(const QxTfConfig cfg, const float* __restrict__ w, const doub
   float* hb = h + (size_t)b * L * 128;
   constexpr unsigned FULL = 0xffffffffu;
   {   // ---- state rows
+    // all (N+1) n inputs of the trajectory first: 612 independent strided fp64 loads in flight at once instead of
+    // one dependent load per row (the kernel was latency-bound on them: 0.36 ms for 0.42 GB of output), normalised
+    // in fp64 like predict (transformer_ilqr.py:312-315) and parked in shared memory as the fp32 model input
+    __shared__ float xin[128 * QX_MAX_N];
+    for (int e = threadIdx.x; e < (N + 1) * n; e += blockDim.x) {
+      const int tok = e / n, i = e - tok * n;
+      const double mu = (double)w[lay.x_mean + i], sd = (double)w[lay.x_std + i];
+      xin[e] = (float)(((x[((size_t)tok * n + i) * B + b] + x_shift[i]) - mu) / sd);
+    }
     float wreg[4][QX_MAX_N];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
       for (int i = 0; i < QX_MAX_N; ++i) wreg[q][i] = (i < n) ? w[lay.ws + (size_t)(ch + q) * n + i] : 0.f;
     const float4 bias = *reinterpret_cast<const float4*>(&w[lay.bs + ch]);
-    double mu = 0.0, sd = 1.0, sh = 0.0;
-    if (lane < n) { mu = (double)w[lay.x_mean + lane]; sd = (double)w[lay.x_std + lane]; sh = x_shift[lane]; }
-    double xv = (lane < n && warp <= N) ? x[((size_t)warp * n + lane) * B + b] : 0.0;
+    __syncthreads();
     for (int tok = warp; tok <= N; tok += 4) {
-      const double xc = xv;
-      if (lane < n && tok + 4 <= N) xv = x[((size_t)(tok + 4) * n + lane) * B + b];           // next row's input in flight
-      float in = 0.f;
-      if (lane < n) in = (float)(((xc + sh) - mu) / sd);                                      // transformer_ilqr.py:312-315
       float acc[4] = {bias.x, bias.y, bias.z, bias.w};
 #pragma unroll
       for (int i = 0; i < QX_MAX_N; ++i) {
-        const float xi = __shfl_sync(FULL, in, i);
         if (i < n) {
+          const float xi = xin[tok * n + i];
 #pragma unroll
           for (int q = 0; q < 4; ++q) acc[q] += wreg[q][i] * xi;
         }
@@ -384,7 +387,7 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
   float* y = att + (size_t)rows * d;
   float* ffh = y + (size_t)rows * d;
   dim3 ge(L, B);
-  const bool per_traj = (d == 128) && lay.n <= QX_MAX_N && lay.c <= 64;
+  const bool per_traj = (d == 128) && lay.n <= QX_MAX_N && lay.c <= 64 && cfg->horizon + 1 <= 128;
   if (per_traj) {
     if (layout == QX_LAYOUT_REC) tf_embed128_kernel<QX_LAYOUT_REC><<<B, 128, 0, st>>>(*cfg, w, x, x_shift, gains, h, B);
     else tf_embed128_kernel<QX_LAYOUT_SOA><<<B, 128, 0, st>>>(*cfg, w, x, x_shift, gains, h, B);
