@@ -36,13 +36,18 @@ class StreamedILQR:
     def launches(self):
         return sum(e.launches for e in self.engines)
 
-    def run(self, x0, u_init, u_out, x_out, cost_out, iters=None, max_iter=100, tol=1e-3, force=False):
+    def run(self, x0, u_init, u_out, x_out, cost_out, iters=None, max_iter=100, tol=1e-3, force=False, join=True):
         """Upload, solve and download every slice on its own stream.
 
         ``iters`` forced iterations (``force=True``: benchmark mode, every trajectory stays active) or, with
         ``iters=None``, a solve to convergence with the reference's stopping rule.  x0 (B, n), u_init (B, N, m)
         in; u_out (B, N, m), x_out (B, N+1, n), cost_out (B,) out - host tensors, float64.  Returns after the
-        work has been ENQUEUED; call ``synchronize()`` (or record an event on ``streams``) before reading."""
+        work has been ENQUEUED; call ``synchronize()`` (or record an event on ``streams``) before reading.
+
+        ``join=True`` makes the current stream wait for every slice, so later work on it sees the results.  A caller
+        that feeds one batch after the other (a serving loop) passes ``join=False`` and calls ``join()`` once at the
+        end: the slice streams are in order by themselves, and without the per-call join the downloads of batch k
+        overlap the uploads and iterations of batch k+1 (the D2H engine never idles between batches)."""
         cur = torch.cuda.current_stream(self.device)
         for (lo, hi), eng, st in zip(self.bounds, self.engines, self.streams):
             st.wait_stream(cur)
@@ -56,6 +61,12 @@ class StreamedILQR:
                 u_out[lo:hi].copy_(eng.u_batch(), non_blocking=True)           # D2H
                 x_out[lo:hi].copy_(eng.x_batch(), non_blocking=True)
                 cost_out[lo:hi].copy_(eng.cost, non_blocking=True)
+        if join:
+            self.join()
+
+    def join(self):
+        """The current stream waits for everything enqueued on the slice streams."""
+        cur = torch.cuda.current_stream(self.device)
         for st in self.streams:
             cur.wait_stream(st)
 
