@@ -222,7 +222,8 @@ __device__ __forceinline__ void chunk_zero(uint32_t tmem_row, int col0) {
 // CTAs land on different schedulers - 0.65 ms against 0.59 ms without.)
 __global__ void __launch_bounds__(256, 2)
 tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmV,
-                         const __grid_constant__ CUtensorMap tmOut, int n_items, int nhead, int L, int d, int dbg) {
+                         const __grid_constant__ CUtensorMap tmOut, float* __restrict__ out_rows, int n_items, int nhead, int L, int d,
+                         int row_lo, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   AttnSmem& s = *reinterpret_cast<AttnSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -317,7 +318,9 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     if (tid == 0 && next < n_items) load_qk(next);          // Q, K tiles are free: request the next item's
     __syncwarp();                // reconverge (per-lane spins, thread 0's detour): the tcgen05.ld / st below are .sync.aligned
     // ---- softmax (two threads per row) --------------------------------------------------------------------------
-    if (qrev * 32 < L && !(dbg & 4)) {
+    // a quarter works when it holds a token (< L) that is asked for (>= row_lo: only the last layer asks for fewer)
+    const bool active = qrev * 32 < L && qrev * 32 + 31 >= row_lo;
+    if (active && !(dbg & 4)) {
       const bool wide = NK - 32 * qrev >= 32;
       float l;
       switch (qrev * 2 + (wide ? 1 : 0)) {
@@ -361,7 +364,7 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     if (tid == 0 && next < n_items) load_v(next);
     __syncwarp();
     // ---- epilogue: each thread 16 of the row's 32 output dims -----------------------------------------------------
-    if (qrev * 32 < L) {
+    if (active && row_lo == 0) {
       uint32_t r[16];
       TmemRow<16>::ld(tmem_row + kColO + 16 * half, r);
       if (half == 0 && lane == 0) bulk_wait_read<0>();       // the previous item's store has read the staging chunk
@@ -384,6 +387,27 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
         tma_store_3d(&tmOut, stg, h * kHd, qrev * 32, b);
         bulk_commit();
       }
+    } else if (active) {
+      // last layer: only the rows row_lo .. L-1 are wanted, compactly ([B][L - row_lo][d]); the quarter that straddles
+      // row_lo would need a store box starting at a negative row - which the hardware rejects (illegal instruction) - so
+      // these few rows go out as plain 16-B stores
+      uint32_t r[16];
+      TmemRow<16>::ld(tmem_row + kColO + 16 * half, r);
+      tmem_wait_ld();
+      const int tok = qrev * 32 + lrev;
+      if (tok >= row_lo && tok < L) {
+        const float inv = 1.f / (psum[tid & 127] + psum[(tid & 127) + 128]);
+        float4* dst = reinterpret_cast<float4*>(out_rows + ((size_t)b * (L - row_lo) + (tok - row_lo)) * d + h * kHd + 16 * half);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          float4 o;
+          o.x = __uint_as_float(r[4 * jj + 0]) * inv;
+          o.y = __uint_as_float(r[4 * jj + 1]) * inv;
+          o.z = __uint_as_float(r[4 * jj + 2]) * inv;
+          o.w = __uint_as_float(r[4 * jj + 3]) * inv;
+          dst[jj] = o;
+        }
+      }
     }
     tcgen05_fence_before();      // the next item's MMAs overwrite S and O; its Q / K halves must be visible to them
     __syncthreads();
@@ -397,9 +421,10 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
 }
 
 // Returns QX_EUNSUPPORTED when the shape is outside the kernel's range (the caller then falls back to the mma.sync
-// kernel of qx_tf_attn.cu).  qkv: [B*L][3d] packed rows, out: [B*L][d].
-int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhead, cudaStream_t st) {
-  if (d != nhead * kHd || L > kMaxKeys || L < 1 || B < 1) return QX_EUNSUPPORTED;
+// kernel of qx_tf_attn.cu).  qkv: [B*L][3d] packed rows, out: [B][L - row_lo][d] = the rows row_lo .. L-1 of every
+// trajectory (row_lo = 0: all of them).
+int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhead, int row_lo, cudaStream_t st) {
+  if (d != nhead * kHd || L > kMaxKeys || L < 1 || B < 1 || row_lo < 0 || row_lo >= L) return QX_EUNSUPPORTED;
   CUtensorMap mq, mv, mo;
   {
     const cuuint64_t dims[3] = {(cuuint64_t)(3 * d), (cuuint64_t)L, (cuuint64_t)B};
@@ -412,8 +437,9 @@ int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhe
     if (rc) return rc;
   }
   {
-    const cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)L, (cuuint64_t)B};
-    const cuuint64_t strides[2] = {(cuuint64_t)d * 4, (cuuint64_t)L * d * 4};
+    // out holds rows row_lo .. L-1 of every trajectory, compactly: [B][L - row_lo][d]
+    const cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)(L - row_lo), (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)d * 4, (cuuint64_t)(L - row_lo) * d * 4};
     const cuuint32_t box[3] = {(cuuint32_t)kHd, 32, 1};
     const int rc = make_map_nd(&mo, out, 3, dims, strides, box);
     if (rc) return rc;
@@ -431,7 +457,7 @@ int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhe
   const char* env_dbg = getenv("QX_TF_ATTN_DBG");
   const int dbg = env_dbg ? atoi(env_dbg) : 0;
   const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;
-  tf_attention_umma_kernel<<<grid, 256, sizeof(AttnSmem), st>>>(mq, mv, mo, n_items, nhead, L, d, dbg);
+  tf_attention_umma_kernel<<<grid, 256, sizeof(AttnSmem), st>>>(mq, mv, mo, out, n_items, nhead, L, d, row_lo, dbg);
   QX_CHECK_LAUNCH("tf_attention_umma_kernel");
   return QX_OK;
 }

@@ -244,12 +244,16 @@ tf_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int 
 }
 
 // ---- h = LayerNorm(h + y) * w + b, one warp per row (d == 128) -------------------------------
+// Residual source: row r of the output takes h_src row (r / per) * src_per + src_off + (r % per).  The plain layer
+// uses h_src == h with per == src_per == rows and src_off == 0; the pruned last layer gathers the T query rows of
+// every trajectory out of the full [B][L] stream into a compact [B][T] one (per = T, src_per = L, src_off = L - T).
 __global__ void __launch_bounds__(256)
-tf_add_ln_kernel(float* __restrict__ h, const float* __restrict__ y, const float* __restrict__ w,
-                 const float* __restrict__ bvec, int rows) {
+tf_add_ln_kernel(float* __restrict__ h, const float* __restrict__ h_src, const float* __restrict__ y,
+                 const float* __restrict__ w, const float* __restrict__ bvec, int rows, int per, int src_per, int src_off) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
-  float4 a = reinterpret_cast<const float4*>(h + (size_t)row * 128)[lane];
+  const size_t srow = (size_t)(row / per) * src_per + src_off + (row % per);
+  float4 a = reinterpret_cast<const float4*>(h_src + srow * 128)[lane];
   const float4 r = reinterpret_cast<const float4*>(y + (size_t)row * 128)[lane];
   a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
   float s = a.x + a.y + a.z + a.w;
@@ -314,13 +318,14 @@ __global__ void tf_unpack_kernel(const QxTfConfig cfg, const float* __restrict__
 template <int LAYOUT>
 __global__ void __launch_bounds__(128)
 tf_unpack128_kernel(const QxTfConfig cfg, const float* __restrict__ w, const float* __restrict__ y,
-                    float* __restrict__ gains, const int32_t* __restrict__ status, int B) {
+                    float* __restrict__ gains, const int32_t* __restrict__ status, int B, int compact) {
   const TfLayout lay(cfg);
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (status != nullptr && status[b] != 0) return;
   const int c = lay.c, m = cfg.m, n = lay.n, G = m + m * n;
   for (int t = warp; t < lay.T; t += 4) {
-    const float* row = y + ((size_t)b * lay.L + (lay.L - lay.T + t)) * 128;
+    // y holds the head output for all L rows of a trajectory, or (compact) for its T query rows only
+    const float* row = compact ? y + ((size_t)b * lay.T + t) * 128 : y + ((size_t)b * lay.L + (lay.L - lay.T + t)) * 128;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int o = lane + 32 * k;
@@ -354,7 +359,7 @@ static int gemm(const float* A, const float* W, const float* bias, float* C, int
 
 // tensor-core GEMM (qx_tf_tc.cu)
 int tf_attention_tc(const float* qkv, float* out, int B, int L, int d, int nhead, cudaStream_t st);   // qx_tf_attn.cu
-int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhead, cudaStream_t st); // qx_tf_attn05.cu
+int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhead, int row_lo, cudaStream_t st); // qx_tf_attn05.cu
 int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* bias, float* C, int M, int N, int K,
                bool relu, cudaStream_t st);
 int tf_split_weights(const float* w, float* hi, float* lo, size_t count, cudaStream_t st);
@@ -413,6 +418,15 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
     }
     return gemm(A, lw + w_off, lw + b_off, C, rows, N, K, relu, st);
   };
+  // Only the T query rows of the LAST layer reach the output head (transformer_model.py:138), and nothing downstream
+  // reads the other rows' attention output / FFN of that layer: with the tensor-core kernels the last layer computes
+  // Q K V for all rows, then attention, out-proj, both LayerNorms, the FFN and the head on a compact [B][T] row stream
+  // (49 of 101 rows for the quadrotor).  Row-wise arithmetic is unchanged, so the predictions are bit-identical
+  // (QX_TF_NO_PRUNE=1 switches it off for the equality test).
+  const char* env_np = getenv("QX_TF_NO_PRUNE");
+  const bool prune = wsplit != nullptr && per_traj && !(env_np != nullptr && env_np[0] == '1') && lay.T < L;
+  const int rows_c = B * lay.T;
+  bool pruned = false;
   for (int l = 0; l < lay.layers; ++l) {
     const float* lw = w + lay.layer0 + (size_t)l * lay.layer_stride;
     int rc = dense(h, lw, lay.l_inw, lay.l_inb, sp.in_hi, sp.in_lo, l, qkv, 3 * d, d, false);
@@ -422,7 +436,13 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
     rc = QX_EUNSUPPORTED;
     if (wsplit != nullptr) {
       const char* env_mma = getenv("QX_TF_ATTN_MMA");
-      if (!(env_mma != nullptr && env_mma[0] == '1')) rc = tf_attention_umma(qkv, att, B, L, d, cfg->nhead, st);
+      if (!(env_mma != nullptr && env_mma[0] == '1')) {
+        if (prune && l == lay.layers - 1) {
+          rc = tf_attention_umma(qkv, att, B, L, d, cfg->nhead, L - lay.T, st);      // att: compact [B][T][d]
+          if (rc == QX_OK) pruned = true;
+        }
+        if (!pruned) rc = tf_attention_umma(qkv, att, B, L, d, cfg->nhead, 0, st);
+      }
       if (rc == QX_EUNSUPPORTED) rc = tf_attention_tc(qkv, att, B, L, d, cfg->nhead, st);
     }
     if (rc == QX_EUNSUPPORTED) {
@@ -431,21 +451,39 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
     } else if (rc) {
       return rc;
     }
+    if (pruned) {
+      // compact stream: att -> out-proj -> y; hc = LN(h[query rows] + y) lands in att (its input is consumed)
+      float* hc = att;
+      auto dense_c = [&](const float* A, size_t b_off, size_t hi_off, size_t lo_off, float* C, int N, int K, bool relu) -> int {
+        const float* sw = wsplit + (size_t)l * sp.stride;
+        return tf_gemm_tc(A, sw + hi_off, sw + lo_off, lw + b_off, C, rows_c, N, K, relu, st);
+      };
+      if ((rc = dense_c(att, lay.l_outb, sp.out_hi, sp.out_lo, y, d, d, false))) return rc;
+      tf_add_ln_kernel<<<ceil_div(rows_c, 8), 256, 0, st>>>(hc, h, y, lw + lay.l_n1w, lw + lay.l_n1b, rows_c, lay.T, L, L - lay.T);
+      QX_CHECK_LAUNCH("tf_add_ln_kernel");
+      if ((rc = dense_c(hc, lay.l_b1, sp.w1_hi, sp.w1_lo, ffh, ff, d, true))) return rc;
+      if ((rc = dense_c(ffh, lay.l_b2, sp.w2_hi, sp.w2_lo, y, d, ff, false))) return rc;
+      tf_add_ln_kernel<<<ceil_div(rows_c, 8), 256, 0, st>>>(hc, hc, y, lw + lay.l_n2w, lw + lay.l_n2b, rows_c, rows_c, rows_c, 0);
+      QX_CHECK_LAUNCH("tf_add_ln_kernel");
+      break;
+    }
     if ((rc = dense(att, lw, lay.l_outw, lay.l_outb, sp.out_hi, sp.out_lo, l, y, d, d, false))) return rc;
-    tf_add_ln_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(h, y, lw + lay.l_n1w, lw + lay.l_n1b, rows);
+    tf_add_ln_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(h, h, y, lw + lay.l_n1w, lw + lay.l_n1b, rows, rows, rows, 0);
     QX_CHECK_LAUNCH("tf_add_ln_kernel");
     if ((rc = dense(h, lw, lay.l_w1, lay.l_b1, sp.w1_hi, sp.w1_lo, l, ffh, ff, d, true))) return rc;
     if ((rc = dense(ffh, lw, lay.l_w2, lay.l_b2, sp.w2_hi, sp.w2_lo, l, y, d, ff, false))) return rc;
-    tf_add_ln_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(h, y, lw + lay.l_n2w, lw + lay.l_n2b, rows);
+    tf_add_ln_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(h, h, y, lw + lay.l_n2w, lw + lay.l_n2b, rows, rows, rows, 0);
     QX_CHECK_LAUNCH("tf_add_ln_kernel");
   }
   dim3 go(lay.T, B);
-  if (wsplit != nullptr) {      // output head as one more tensor-core GEMM over all rows (N padded to 128)
-    int rc = tf_gemm_tc(h, wsplit + sp.head_hi, wsplit + sp.head_lo, wsplit + sp.head_bias, y, rows, 128, d, false, st);
+  if (wsplit != nullptr) {      // output head as one more tensor-core GEMM (N padded to 128) over the rows that are left
+    const float* hsrc = pruned ? att : h;
+    int rc = tf_gemm_tc(hsrc, wsplit + sp.head_hi, wsplit + sp.head_lo, wsplit + sp.head_bias, y, pruned ? rows_c : rows, 128, d,
+                        false, st);
     if (rc) return rc;
     if (per_traj) {
-      if (layout == QX_LAYOUT_REC) tf_unpack128_kernel<QX_LAYOUT_REC><<<B, 128, 0, st>>>(*cfg, w, y, gains, status, B);
-      else tf_unpack128_kernel<QX_LAYOUT_SOA><<<B, 128, 0, st>>>(*cfg, w, y, gains, status, B);
+      if (layout == QX_LAYOUT_REC) tf_unpack128_kernel<QX_LAYOUT_REC><<<B, 128, 0, st>>>(*cfg, w, y, gains, status, B, pruned ? 1 : 0);
+      else tf_unpack128_kernel<QX_LAYOUT_SOA><<<B, 128, 0, st>>>(*cfg, w, y, gains, status, B, pruned ? 1 : 0);
     } else {
       if (layout == QX_LAYOUT_REC) tf_unpack_kernel<QX_LAYOUT_REC><<<go, 64, 0, st>>>(*cfg, w, y, gains, status, B);
       else tf_unpack_kernel<QX_LAYOUT_SOA><<<go, 64, 0, st>>>(*cfg, w, y, gains, status, B);
@@ -540,7 +578,7 @@ extern "C" int qx_tf_attention(const float* qkv, float* out, int B, int L, int d
   QX_CHECK_ARG(B >= 0 && L > 0 && d > 0 && nhead > 0 && d == 32 * nhead, "bad shape (head dimension must be 32)");
   if (B == 0) return QX_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (impl == 0) return qx::tf_attention_umma(qkv, out, B, L, d, nhead, st);
+  if (impl == 0) return qx::tf_attention_umma(qkv, out, B, L, d, nhead, 0, st);
   if (impl == 1) return qx::tf_attention_tc(qkv, out, B, L, d, nhead, st);
   QX_CHECK_ARG(impl == 2, "impl must be 0, 1 or 2");
   static bool att_cfg = false;

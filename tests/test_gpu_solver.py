@@ -346,6 +346,25 @@ def test_tcgen05_attention_matches_mma_sync_and_exact_attention(system, mode, go
 
 
 @pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
+def test_last_layer_on_query_rows_only_is_bit_identical(system, golden_dir, monkeypatch):
+    """The last encoder layer runs its attention output, out-proj, LayerNorms, FFN and the head on the T query rows
+    only (compact [B][T] stream, TMA stores with negative row coordinates clipped by the map): row-wise arithmetic
+    is unchanged, so the predictions must equal those of the full-width layer bit for bit."""
+    g = np.load(f"{golden_dir}/tf_forward_{system}.npz")
+    w = _wrapper(system, "rand")
+    rng = np.random.default_rng(7)
+    reps = 600 // len(g["x_err"])
+    x = np.concatenate([g["x_err"] * (1.0 + 0.05 * rng.standard_normal(g["x_err"].shape)) for _ in range(reps)])
+    kK = np.concatenate([g["kK"] * (1.0 + 0.05 * rng.standard_normal(g["kK"].shape)) for _ in range(reps)])
+    monkeypatch.setenv("QX_TF_NO_PRUNE", "1")
+    full = w.predict(x, kK)
+    monkeypatch.setenv("QX_TF_NO_PRUNE", "0")
+    pruned = w.predict(x, kK)
+    assert np.isfinite(pruned).all()
+    assert np.array_equal(full, pruned)
+
+
+@pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
 @pytest.mark.parametrize("mode", ["fp32", "rand"])
 def test_transformer_mode_matches_golden_runs(system, mode):
     """optimize() with the transformer in the loop vs the reference (same weights, fp32)."""
