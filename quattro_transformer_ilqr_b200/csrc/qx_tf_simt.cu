@@ -62,28 +62,39 @@ __global__ void __launch_bounds__(128)
 tf_embed128_kernel(const QxTfConfig cfg, const float* __restrict__ w, const double* __restrict__ x,
                    const double* __restrict__ x_shift, const float* __restrict__ gains, float* __restrict__ h, int B) {
   const TfLayout lay(cfg);
-  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = cfg.horizon, n = lay.n, c = lay.c, P = lay.P, m = cfg.m, L = lay.L, T = lay.T;
   const int ch = 4 * lane;
-  float* hb = h + (size_t)b * L * 128;
   constexpr unsigned FULL = 0xffffffffu;
+  // Persistent CTAs (a few per SM), each walking trajectories b, b + grid, ..: the weight staging below is paid once
+  // per CTA instead of once per trajectory.
+  // Both embedding weights are staged TRANSPOSED in shared memory ([input][channel]) with coalesced global reads: read
+  // in place ([channel][input], a lane's four channels 4 n floats apart) every load touched 32 sectors, 12.7 K of the
+  // 16 K L1 sectors a CTA moved, and the kernel ran at 1.2 TB/s of output.
+  __shared__ float xin[128 * QX_MAX_N];
+  __shared__ __align__(16) float sws[QX_MAX_N * 128];
+  __shared__ __align__(16) float swc[64 * 128];
+  for (int e = threadIdx.x; e < 128 * n; e += blockDim.x) sws[(e % n) * 128 + e / n] = w[lay.ws + e];
+  for (int e = threadIdx.x; e < 128 * c; e += blockDim.x) swc[(e % c) * 128 + e / c] = w[lay.wc + e];
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+  float* hb = h + (size_t)b * L * 128;
+  __syncthreads();          // the previous trajectory's rows are done with xin (and, first time, the weights are staged)
+  // all (N+1) n inputs of the trajectory: 612 independent strided fp64 loads in flight at once, normalised in fp64
+  // like predict (transformer_ilqr.py:312-315) and parked as the fp32 model input
+  for (int e = threadIdx.x; e < (N + 1) * n; e += blockDim.x) {
+    const int tok = e / n, i = e - tok * n;
+    const double mu = (double)w[lay.x_mean + i], sd = (double)w[lay.x_std + i];
+    xin[e] = (float)(((x[((size_t)tok * n + i) * B + b] + x_shift[i]) - mu) / sd);
+  }
+  __syncthreads();
   {   // ---- state rows
-    // all (N+1) n inputs of the trajectory first: 612 independent strided fp64 loads in flight at once instead of
-    // one dependent load per row (the kernel was latency-bound on them: 0.36 ms for 0.42 GB of output), normalised
-    // in fp64 like predict (transformer_ilqr.py:312-315) and parked in shared memory as the fp32 model input
-    __shared__ float xin[128 * QX_MAX_N];
-    for (int e = threadIdx.x; e < (N + 1) * n; e += blockDim.x) {
-      const int tok = e / n, i = e - tok * n;
-      const double mu = (double)w[lay.x_mean + i], sd = (double)w[lay.x_std + i];
-      xin[e] = (float)(((x[((size_t)tok * n + i) * B + b] + x_shift[i]) - mu) / sd);
-    }
     float wreg[4][QX_MAX_N];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-      for (int i = 0; i < QX_MAX_N; ++i) wreg[q][i] = (i < n) ? w[lay.ws + (size_t)(ch + q) * n + i] : 0.f;
+    for (int i = 0; i < QX_MAX_N; ++i) {
+      const float4 wv = (i < n) ? *reinterpret_cast<const float4*>(&sws[i * 128 + ch]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      wreg[0][i] = wv.x; wreg[1][i] = wv.y; wreg[2][i] = wv.z; wreg[3][i] = wv.w;
+    }
     const float4 bias = *reinterpret_cast<const float4*>(&w[lay.bs + ch]);
-    __syncthreads();
     for (int tok = warp; tok <= N; tok += 4) {
       float acc[4] = {bias.x, bias.y, bias.z, bias.w};
 #pragma unroll
@@ -115,8 +126,8 @@ tf_embed128_kernel(const QxTfConfig cfg, const float* __restrict__ w, const doub
     float acc[4] = {bias.x, bias.y, bias.z, bias.w};
     for (int i = 0; i < c; ++i) {
       const float xi = __shfl_sync(FULL, (i < 32) ? in[0] : in[1], i & 31);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q] += w[lay.wc + (size_t)(ch + q) * c + i] * xi;
+      const float4 wv = *reinterpret_cast<const float4*>(&swc[i * 128 + ch]);
+      acc[0] += wv.x * xi; acc[1] += wv.y * xi; acc[2] += wv.z * xi; acc[3] += wv.w * xi;
     }
     const float4 pe = *reinterpret_cast<const float4*>(&w[lay.pe + (size_t)tok * 128 + ch]);
     *reinterpret_cast<float4*>(&hb[(size_t)tok * 128 + ch]) = make_float4(acc[0] + pe.x, acc[1] + pe.y, acc[2] + pe.z, acc[3] + pe.w);
@@ -128,6 +139,7 @@ tf_embed128_kernel(const QxTfConfig cfg, const float* __restrict__ w, const doub
     const float4 pe = *reinterpret_cast<const float4*>(&w[lay.pe + (size_t)tok * 128 + ch]);
     *reinterpret_cast<float4*>(&hb[(size_t)tok * 128 + ch]) = make_float4(tg.x + pe.x, tg.y + pe.y, tg.z + pe.z, tg.w + pe.w);
   }
+  }   // trajectories of this CTA
 }
 
 // ---- C[M][N] = act(A[M][K] W[N][K]^T + bias) ----------------------------------------------------
@@ -394,8 +406,16 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
   dim3 ge(L, B);
   const bool per_traj = (d == 128) && lay.n <= QX_MAX_N && lay.c <= 64 && cfg->horizon + 1 <= 128;
   if (per_traj) {
-    if (layout == QX_LAYOUT_REC) tf_embed128_kernel<QX_LAYOUT_REC><<<B, 128, 0, st>>>(*cfg, w, x, x_shift, gains, h, B);
-    else tf_embed128_kernel<QX_LAYOUT_SOA><<<B, 128, 0, st>>>(*cfg, w, x, x_shift, gains, h, B);
+    static int embed_ctas = 0;
+    if (embed_ctas == 0) {
+      int dev = 0, sms = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      embed_ctas = 5 * sms;          // 45 KB of shared memory per CTA: five fit an SM
+    }
+    const int ge128 = B < embed_ctas ? B : embed_ctas;
+    if (layout == QX_LAYOUT_REC) tf_embed128_kernel<QX_LAYOUT_REC><<<ge128, 128, 0, st>>>(*cfg, w, x, x_shift, gains, h, B);
+    else tf_embed128_kernel<QX_LAYOUT_SOA><<<ge128, 128, 0, st>>>(*cfg, w, x, x_shift, gains, h, B);
   } else {
     if (layout == QX_LAYOUT_REC) tf_embed_kernel<QX_LAYOUT_REC><<<ge, d, 0, st>>>(*cfg, w, x, x_shift, gains, h, B);
     else tf_embed_kernel<QX_LAYOUT_SOA><<<ge, d, 0, st>>>(*cfg, w, x, x_shift, gains, h, B);
