@@ -454,6 +454,7 @@ int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhe
     cfg = true;
   }
   const int n_items = B * nhead;
+  // QX_TF_ATTN_DBG (timing experiments only, results are then wrong on purpose): bit 1 no P V MMAs, bit 2 no softmax
   const char* env_dbg = getenv("QX_TF_ATTN_DBG");
   const int dbg = env_dbg ? atoi(env_dbg) : 0;
   const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;

@@ -247,6 +247,33 @@ def test_streamed_host_batch_equals_single_engine():
         StreamedILQR(DeviceModel("quadrotor"), 4, N, chunks=5)
 
 
+def test_graph_replayed_iteration_pairs_equal_plain_iterations():
+    """BatchedILQR.iterate_pair (two iterations as one CUDA-graph replay) against the same iterations launched
+    kernel by kernel: costs, controls, alphas and iteration counts must agree bit for bit, also across a problem
+    reset and from the odd buffer parity."""
+    from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel
+    B, N = 2048, 50
+    x0 = sample_x0("quadrotor", B, seed=21)
+    u0 = np.zeros((B, N, 4))
+    a = BatchedILQR(DeviceModel("quadrotor"), B, N)
+    b = BatchedILQR(DeviceModel("quadrotor"), B, N)
+    for rounds in range(2):
+        a.set_problem(x0, u0)
+        b.set_problem(x0, u0)
+        for _ in range(3):              # plain, capture, replay
+            a.iterate_pair(1e-3, force=True)
+        a.iterate(1e-3, force=True)     # odd parity from here on
+        a.iterate_pair(1e-3, force=True)
+        a.iterate_pair(1e-3, force=True)
+        a.iterate_pair(1e-3, force=True)
+        for _ in range(13):
+            b.iterate(1e-3, force=True)
+        torch.cuda.synchronize()
+        assert a.cur == b.cur and a.launches == b.launches
+        assert torch.equal(a.cost, b.cost) and torch.equal(a.alpha, b.alpha) and torch.equal(a.iters, b.iters)
+        assert torch.equal(a.u[a.cur], b.u[b.cur]) and torch.equal(a.x[a.cur], b.x[b.cur])
+
+
 # ---------------------------------------------------------------------------- transformer mode
 def _wrapper(system, mode):
     from quattro_transformer_ilqr_b200 import TransformerILQR, TransformerPredictor
