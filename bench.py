@@ -283,6 +283,15 @@ def gpu_bench(args):
 
     state = {"i": 0}
     run_steps(args.warmup, state)
+    if tf is None and args.graph:
+        # capture the iteration-pair graphs for both buffer parities now, whatever W was: a capture costs milliseconds
+        # and must not land inside the timed region
+        for parity in (0, 1):
+            eng.set_problem(x0_d, u0_d)
+            if eng.cur != parity:
+                eng.iterate(tol, force=True)
+            for _ in range(3):
+                eng.iterate_pair(tol, force=True)
     sampler = ClockSampler(local)
     sync_all()
     if rank == 0:
