@@ -243,20 +243,32 @@ def test_streamed_host_batch_equals_single_engine():
     e.solve(fixed_iters=5)
     assert torch.equal(u_out, e.u_batch().cpu()) and torch.equal(x_out, e.x_batch().cpu())
     assert torch.equal(c_out, e.cost.cpu())
+    # a serving loop: batches fed back to back without a join per batch (the slice streams order themselves),
+    # one join at the end; the last batch's results are the ones in the output buffers
+    x0b = torch.as_tensor(sample_x0("quadrotor", B, seed=10)).pin_memory()
+    for xin in (x0, x0b, x0, x0b):
+        pipe.run(xin, u0, u_out, x_out, c_out, iters=5, tol=1e-3, force=True, join=False)
+    pipe.join()
+    torch.cuda.current_stream().synchronize()
+    e.set_problem(x0b, u0)
+    e.solve(fixed_iters=5)
+    assert torch.equal(u_out, e.u_batch().cpu()) and torch.equal(x_out, e.x_batch().cpu())
+    assert torch.equal(c_out, e.cost.cpu())
     with pytest.raises(ValueError):
         StreamedILQR(DeviceModel("quadrotor"), 4, N, chunks=5)
 
 
-def test_graph_replayed_iteration_pairs_equal_plain_iterations():
+@pytest.mark.parametrize("system", ["quadrotor", "cartpole"])
+def test_graph_replayed_iteration_pairs_equal_plain_iterations(system):
     """BatchedILQR.iterate_pair (two iterations as one CUDA-graph replay) against the same iterations launched
     kernel by kernel: costs, controls, alphas and iteration counts must agree bit for bit, also across a problem
-    reset and from the odd buffer parity."""
+    reset and from the odd buffer parity (block path for the quadrotor, generic kernels for the cart-pole)."""
     from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel
-    B, N = 2048, 50
-    x0 = sample_x0("quadrotor", B, seed=21)
-    u0 = np.zeros((B, N, 4))
-    a = BatchedILQR(DeviceModel("quadrotor"), B, N)
-    b = BatchedILQR(DeviceModel("quadrotor"), B, N)
+    B, N = 2048, HORIZON[system]
+    x0 = sample_x0(system, B, seed=21)
+    u0 = np.zeros((B, N, 4 if system == "quadrotor" else 1))
+    a = BatchedILQR(DeviceModel(system), B, N)
+    b = BatchedILQR(DeviceModel(system), B, N)
     for rounds in range(2):
         a.set_problem(x0, u0)
         b.set_problem(x0, u0)
