@@ -247,7 +247,7 @@ struct TaSmem {
   float raw[kTaRaw][kBM * kBK];
   float4 epi[4][2][32][8];       // per epilogue warp: two 32 x 32 fp32 chunks in the TMA 128-B swizzle layout
   uint64_t w_full[kTaW], w_empty[kTaW], full[kTaRaw], raw_empty[kTaRaw], a_ready[kTaA], a_empty[kTaA], acc_full[2],
-      acc_empty[2];
+      acc_empty[2], res_full[4][2];
   uint32_t tmem_base;
 };
 constexpr size_t kTaSmemBytes = sizeof(TaSmem);
@@ -257,11 +257,21 @@ static_assert(kTaSmemBytes <= 227 * 1024, "TMEM-A GEMM exceeds the shared memory
 // on (a parity wait cannot tell phase p from phase p + 2), hence ring depths that are multiples of the set count.
 // STREAM_W: K > 128, the weight ring cycles (K % 128 == 0 keeps block kb in slot kb % 4).
 // dbg (timing experiments only, QX_TF_GEMM_DBG): bit 0 no stores, bit 2 no epilogue work.
-template <bool RELU, bool STREAM_W, int kSets>
+// LN (N == 128 only, the CTA owns whole rows): the epilogue computes C = LayerNorm(res + (A W^T + bias)) * gamma + beta
+// instead of a plain store - the post-norm residual blocks of nn.TransformerEncoderLayer (norm1 after out_proj, norm2
+// after linear2; transformer_model.py:112-113) without the 2 x 512 B per row round trip of a separate add + LN kernel.
+// tmR maps the residual stream [M][128] with the (32 x 32) box of the output map; it may be the output itself.
+struct LnArgs {
+  const float* gamma;
+  const float* beta;
+};
+
+template <bool RELU, bool STREAM_W, int kSets, bool LN = false>
 __global__ void __launch_bounds__(ta_threads(kSets), 1)
 tf_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
                   const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmC,
-                  const float* __restrict__ bias, int M, int N, int K, int dbg) {
+                  const float* __restrict__ bias, int M, int N, int K, int dbg, const __grid_constant__ CUtensorMap tmR,
+                  const LnArgs ln) {
   static_assert(kTaRaw % kSets == 0 && kTaA % kSets == 0, "ring depths must be multiples of the splitter set count");
   // No integer round trip on the pointer: the compiler must KNOW these are shared-memory accesses.  With generic
   // LD.E.128 for the splitter's raw-row reads, the mbarrier arrive that hands the raw block back to the producer was
@@ -294,6 +304,7 @@ tf_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&s.acc_full[i], 1);
       mbar_init(&s.acc_empty[i], 128);
     }
+    for (int i = 0; i < 8; ++i) mbar_init(&s.res_full[i >> 1][i & 1], 1);
     mbar_fence_init();
   }
   if (warp == 1) {   // all 512 columns: 2 accumulators + 4 A stages
@@ -396,13 +407,112 @@ tf_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ---- epilogue: TMEM -> registers (+ bias, ReLU) -> swizzled staging chunk -> TMA store ------------------------
     const int q = warp & 3;
     uint32_t tl = 0, chunk = 0;
+    if (LN && lane == 0 && g0 < m_tiles) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        mbar_arrive_expect_tx(&s.res_full[q][c], 32 * 32 * 4);
+        tma_load_2d(&tmR, &s.res_full[q][c], s.epi[q][c], 32 * c, g0 * kBM + q * 32);
+      }
+    }
     for (int mt = g0; mt < m_tiles; mt += groups, ++tl) {
       const int m0 = mt * kBM;
       const uint32_t buf = tl & 1u;
       mbar_wait(&s.acc_full[buf], (tl >> 1) & 1u);
       __syncwarp();        // reconverge after the per-lane spin: tcgen05.ld / wait::ld are .sync.aligned
       tcgen05_fence_after();
-      if (!(dbg & 4)) {
+      if constexpr (LN) {
+        // thread = row (TMEM lane): the whole 128-column row sits in registers after ONE pass over tensor memory (its
+        // 64 B/clk read port is shared with the A operand of the running MMAs), so the accumulator goes back to the
+        // MMA warp at once.  The residual rows arrive as four 32 x 32 TMA boxes in the staging chunks (two before the
+        // accumulator is waited for, two as the first ones are consumed); a = res + (acc + bias), mean, centred second
+        // moment, normalise, scale, and the same staging chunks carry the result to the TMA store.
+        const uint32_t tacc = tmem + buf * kBN + ((uint32_t)(q * 32) << 16);
+        uint32_t r[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tacc + 32 * c, r[c]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tcgen05_fence_before();
+        mbar_arrive(&s.acc_empty[buf]);
+        // Summation order = tf_add_ln_kernel's (qx_tf_simt.cu), so fused and separate launches agree bit for bit: four
+        // columns left to right (its lane), pairwise over the 8 "lanes" of a chunk, pairwise over the 4 chunks.
+        float pc[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float4 (*stg)[8] = s.epi[q][c & 1];
+          mbar_wait(&s.res_full[q][c & 1], (uint32_t)(c >> 1));     // two uses of each chunk per tile: parity = c / 2
+          const float4* b4 = reinterpret_cast<const float4*>(bias + 32 * c);
+          float t[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = b4[j];
+            const float4 hh = stg[lane][j ^ (lane & 7)];
+            const float a0 = __fadd_rn(hh.x, __fadd_rn(__uint_as_float(r[c][4 * j + 0]), bb.x));
+            const float a1 = __fadd_rn(hh.y, __fadd_rn(__uint_as_float(r[c][4 * j + 1]), bb.y));
+            const float a2 = __fadd_rn(hh.z, __fadd_rn(__uint_as_float(r[c][4 * j + 2]), bb.z));
+            const float a3 = __fadd_rn(hh.w, __fadd_rn(__uint_as_float(r[c][4 * j + 3]), bb.w));
+            t[j] = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
+            r[c][4 * j + 0] = __float_as_uint(a0); r[c][4 * j + 1] = __float_as_uint(a1);
+            r[c][4 * j + 2] = __float_as_uint(a2); r[c][4 * j + 3] = __float_as_uint(a3);
+          }
+          pc[c] = __fadd_rn(__fadd_rn(__fadd_rn(t[0], t[1]), __fadd_rn(t[2], t[3])),
+                            __fadd_rn(__fadd_rn(t[4], t[5]), __fadd_rn(t[6], t[7])));
+          __syncwarp();                                  // every lane has its values: the chunk may be overwritten
+          if (c < 2 && lane == 0) {
+            mbar_arrive_expect_tx(&s.res_full[q][c & 1], 32 * 32 * 4);
+            tma_load_2d(&tmR, &s.res_full[q][c & 1], stg, 32 * (c + 2), m0 + q * 32);
+          }
+        }
+        const float mu = __fmul_rn(__fadd_rn(__fadd_rn(pc[0], pc[1]), __fadd_rn(pc[2], pc[3])), 1.f / 128.f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float t[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float d0 = __fsub_rn(__uint_as_float(r[c][4 * j + 0]), mu), d1 = __fsub_rn(__uint_as_float(r[c][4 * j + 1]), mu);
+            const float d2 = __fsub_rn(__uint_as_float(r[c][4 * j + 2]), mu), d3 = __fsub_rn(__uint_as_float(r[c][4 * j + 3]), mu);
+            t[j] = __fmaf_rn(d3, d3, __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0))));
+            r[c][4 * j + 0] = __float_as_uint(d0); r[c][4 * j + 1] = __float_as_uint(d1);
+            r[c][4 * j + 2] = __float_as_uint(d2); r[c][4 * j + 3] = __float_as_uint(d3);
+          }
+          pc[c] = __fadd_rn(__fadd_rn(__fadd_rn(t[0], t[1]), __fadd_rn(t[2], t[3])),
+                            __fadd_rn(__fadd_rn(t[4], t[5]), __fadd_rn(t[6], t[7])));
+        }
+        const float rs = rsqrtf(__fmaf_rn(__fadd_rn(__fadd_rn(pc[0], pc[1]), __fadd_rn(pc[2], pc[3])), 1.f / 128.f, 1e-5f));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (lane == 0) bulk_wait_read<1>();          // the store that last used this staging chunk has read it
+          __syncwarp();
+          const float4* g4 = reinterpret_cast<const float4*>(ln.gamma + 32 * c);
+          const float4* e4 = reinterpret_cast<const float4*>(ln.beta + 32 * c);
+          float4 (*stg)[8] = s.epi[q][c & 1];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 g = g4[j], be = e4[j];
+            float4 o;
+            o.x = __fmaf_rn(__fmul_rn(__uint_as_float(r[c][4 * j + 0]), rs), g.x, be.x);
+            o.y = __fmaf_rn(__fmul_rn(__uint_as_float(r[c][4 * j + 1]), rs), g.y, be.y);
+            o.z = __fmaf_rn(__fmul_rn(__uint_as_float(r[c][4 * j + 2]), rs), g.z, be.z);
+            o.w = __fmaf_rn(__fmul_rn(__uint_as_float(r[c][4 * j + 3]), rs), g.w, be.w);
+            stg[lane][j ^ (lane & 7)] = o;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, stg, 32 * c, m0 + q * 32);
+            bulk_commit();
+          }
+        }
+        if (lane == 0 && mt + groups < m_tiles) {      // next tile's first two residual chunks: in flight during its MMAs
+          bulk_wait_read<0>();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            mbar_arrive_expect_tx(&s.res_full[q][c], 32 * 32 * 4);
+            tma_load_2d(&tmR, &s.res_full[q][c], s.epi[q][c], 32 * c, m0 + groups * kBM + q * 32);
+          }
+        }
+        __syncwarp();
+        continue;                                       // the accumulator was released above
+      } else if (!(dbg & 4)) {
 #pragma unroll
         for (int c0 = 0; c0 < kBN; c0 += 32, ++chunk) {
           uint32_t r[32];
@@ -515,7 +625,7 @@ int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* 
                            (int)kTaSmemBytes);                                                                          \
       cfgd = true;                                                                                                      \
     }                                                                                                                   \
-    tf_gemm_ta_kernel<RELU_, STREAM_, SETS><<<grid, ta_threads(SETS), kTaSmemBytes, st>>>(ma, mh, ml, mc, bias, M, N, K, dbg); \
+    tf_gemm_ta_kernel<RELU_, STREAM_, SETS><<<grid, ta_threads(SETS), kTaSmemBytes, st>>>(ma, mh, ml, mc, bias, M, N, K, dbg, mc, LnArgs{}); \
   } while (0)
     const bool stream_w = K != kTaW * kBK;
     if (variant == 1) {
@@ -538,6 +648,41 @@ int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* 
   if (relu) tf_gemm_tc_kernel<true><<<grid, 320, kGemmSmemBytes, st>>>(ma, mh, ml, bias, C, M, N, K);
   else tf_gemm_tc_kernel<false><<<grid, 320, kGemmSmemBytes, st>>>(ma, mh, ml, bias, C, M, N, K);
   QX_CHECK_LAUNCH("tf_gemm_tc_kernel");
+  return QX_OK;
+}
+
+// C[M][128] = LayerNorm(res + (A[M][K] W[128][K]^T + bias)) * gamma + beta in one launch (the LN variant of the TMEM-A
+// kernel).  C may be res itself (a tile's residual rows are consumed before its stores are issued, and no other CTA
+// touches them) but must not be A.  QX_EUNSUPPORTED when the shape does not fit.
+int tf_gemm_ln_tc(const float* A, const float* Whi, const float* Wlo, const float* bias, const float* res, const float* gamma,
+                  const float* beta, float* C, int M, int K, cudaStream_t st) {
+  const int N = kBN;
+  if (K % (kTaW * kBK) != 0) return QX_EUNSUPPORTED;
+  CUtensorMap ma, mh, ml, mc, mr;
+  int rc;
+  if ((rc = make_map(&ma, A, M, K)) || (rc = make_map(&mh, Whi, N, K)) || (rc = make_map(&ml, Wlo, N, K)) ||
+      (rc = make_map(&mc, C, M, N, 32, 32)) || (rc = make_map(&mr, res, M, N, 32, 32)))
+    return rc;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int m_tiles = ceil_div(M, kBM);
+  const int grid = num_sms < m_tiles ? num_sms : m_tiles;
+  const LnArgs ln{gamma, beta};
+  static bool cfgd = false;
+  if (!cfgd) {
+    cudaFuncSetAttribute(tf_gemm_ta_kernel<false, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTaSmemBytes);
+    cudaFuncSetAttribute(tf_gemm_ta_kernel<false, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTaSmemBytes);
+    cfgd = true;
+  }
+  if (K != kTaW * kBK)
+    tf_gemm_ta_kernel<false, true, 1, true><<<grid, ta_threads(1), kTaSmemBytes, st>>>(ma, mh, ml, mc, bias, M, N, K, 0, mr, ln);
+  else
+    tf_gemm_ta_kernel<false, false, 1, true><<<grid, ta_threads(1), kTaSmemBytes, st>>>(ma, mh, ml, mc, bias, M, N, K, 0, mr, ln);
+  QX_CHECK_LAUNCH("tf_gemm_ta_kernel<LN>");
   return QX_OK;
 }
 

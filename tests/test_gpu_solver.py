@@ -348,6 +348,7 @@ def test_resident_weight_gemm_equals_streaming_gemm_bitwise(system, golden_dir, 
     reps = 1200 // len(g["x_err"])
     x = np.concatenate([g["x_err"] * (1.0 + 0.05 * rng.standard_normal(g["x_err"].shape)) for _ in range(reps)])
     kK = np.concatenate([g["kK"] * (1.0 + 0.05 * rng.standard_normal(g["kK"].shape)) for _ in range(reps)])
+    monkeypatch.setenv("QX_TF_FUSE_LN", "0")       # plain epilogues on both sides: all four GEMMs of a layer are compared
     monkeypatch.setenv("QX_TF_GEMM_STREAM", "1")
     streamed = w.predict(x, kK)
     monkeypatch.setenv("QX_TF_GEMM_STREAM", "0")
@@ -401,6 +402,38 @@ def test_last_layer_on_query_rows_only_is_bit_identical(system, golden_dir, monk
     pruned = w.predict(x, kK)
     assert np.isfinite(pruned).all()
     assert np.array_equal(full, pruned)
+
+
+@pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
+@pytest.mark.parametrize("mode", ["rand", "fp32"])
+def test_layernorm_fused_into_gemm_epilogue_matches_separate_kernel(system, mode, golden_dir, monkeypatch):
+    """out-proj + residual + norm1 and linear2 + residual + norm2 as ONE launch each (thread-per-row LayerNorm on the
+    accumulator rows, residual through TMA) against the GEMM followed by the warp-per-row add + LN kernel: both spell
+    out the same roundings in the same order, so the predictions must be bit-identical.  1 200 trajectories: dozens
+    of m tiles per CTA, both accumulators, the ragged last tile, the in-place update of the residual stream."""
+    g = np.load(f"{golden_dir}/tf_forward_{system}.npz")
+    w = _wrapper(system, mode)
+    rng = np.random.default_rng(8)
+    reps = 1200 // len(g["x_err"])
+    x = np.concatenate([g["x_err"] * (1.0 + 0.05 * rng.standard_normal(g["x_err"].shape)) for _ in range(reps)])
+    kK = np.concatenate([g["kK"] * (1.0 + 0.05 * rng.standard_normal(g["kK"].shape)) for _ in range(reps)])
+    monkeypatch.setenv("QX_TF_FUSE_LN", "0")
+    separate = w.predict(x, kK)
+    outs = {}
+    for bits in ("1", "2", "3"):
+        monkeypatch.setenv("QX_TF_FUSE_LN", bits)
+        outs[bits] = w.predict(x, kK)
+        assert np.isfinite(outs[bits]).all()
+    again = w.predict(x, kK)
+    assert np.array_equal(again, outs["3"])
+    monkeypatch.setenv("QX_TF_NO_PRUNE", "1")
+    assert np.array_equal(w.predict(x, kK), outs["3"])      # same row arithmetic on the full-width last layer
+    monkeypatch.setenv("QX_TF_NO_PRUNE", "0")
+    w.tensor_cores = False
+    exact = w.predict(x, kK)
+    for bits, o in outs.items():
+        assert np.array_equal(o, separate), f"QX_TF_FUSE_LN={bits}: {relmax(o, separate):.2e}"
+    assert relmax(outs["3"], exact) < (5e-6 if mode == "rand" else 5e-5)
 
 
 @pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
