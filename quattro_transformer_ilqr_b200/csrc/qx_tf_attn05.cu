@@ -204,6 +204,67 @@ __device__ __forceinline__ float softmax_half_row(uint32_t tmem_row, int lrev, i
   }
   return (l4[0] + l4[1]) + (l4[2] + l4[3]);
 }
+// ---- PAIR mode (L <= 64, the cart-pole's 61 tokens): TWO trajectories share the M = 128 tile ---------------------------
+// rows 0-63 = trajectory 2p, rows 64-127 = trajectory 2p + 1 (a TMA box of 64 tokens x 2 trajectories lands exactly so).
+// S = Q [K_a ; K_b]^T is one N = 128 product; a row of trajectory t reads its scores in columns [64 t, 64 t + 64) and
+// leaves P_hi in columns [0, 64), P_lo in [64, 128) whatever t is (all loads of a row precede its stores); the second
+// product runs once per trajectory (B = V_a into O_a, B = V_b into O_b: a row reads the one that is its own).
+// TMEM: S / P [0,128) | O_a [128,160) | O_b [160,192) | pair exchange [192,196) - the K_lo tile has no spare rows here.
+constexpr uint32_t kPairPlo = 64, kPairO = 128, kPairX = 192;
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, float v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(__float_as_uint(v)) : "memory");
+}
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {      // completes the load
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  return __uint_as_float(v);
+}
+// softmax_half_row for a PAIR tile: Q (0 / 1) full chunks, then the 32-wide chunk with the diagonal; the row's two
+// threads swap their partial maxima through two TMEM columns of their (shared) lane
+template <int Q>
+__device__ __forceinline__ float softmax_pair_row(uint32_t tmem_row, uint32_t s_col, int lrev, int half, int wq) {
+  uint32_t r[Q + 1][16];
+#pragma unroll
+  for (int c = 0; c <= Q; ++c) TmemRow<16>::ld(tmem_row + s_col + 32 * c + 16 * half, r[c]);
+  tmem_wait_ld();
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+  for (int c = 0; c < Q; ++c) {
+#pragma unroll
+    for (int t = 0; t < 16; ++t) m4[t & 3] = fmaxf(m4[t & 3], __uint_as_float(r[c][t]));
+  }
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    if (16 * half + t <= lrev) m4[t & 3] = fmaxf(m4[t & 3], __uint_as_float(r[Q][t]));
+  }
+  float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+  tmem_st1(tmem_row + kPairX + half, m);
+  tmem_wait_st();
+  tcgen05_fence_before();
+  pair_sync(wq);
+  tcgen05_fence_after();
+  m = fmaxf(m, tmem_ld1(tmem_row + kPairX + (half ^ 1)));      // -inf from an upper half that is fully masked
+  float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c <= Q; ++c) {
+    uint32_t lo[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      float p = ex2_approx(__uint_as_float(r[c][t]) - m);
+      if (c == Q && 16 * half + t > lrev) p = 0.f;
+      l4[t & 3] += p;
+      float h, lw;
+      tf32_split(p, h, lw);
+      r[c][t] = __float_as_uint(h);
+      lo[t] = __float_as_uint(lw);
+    }
+    TmemRow<16>::st(tmem_row + 32 * c + 16 * half, r[c]);
+    TmemRow<16>::st(tmem_row + kPairPlo + 32 * c + 16 * half, lo);
+  }
+  return (l4[0] + l4[1]) + (l4[2] + l4[3]);
+}
+
 template <int HW>
 __device__ __forceinline__ void chunk_zero(uint32_t tmem_row, int col0) {
   uint32_t z[16];
@@ -220,19 +281,21 @@ __device__ __forceinline__ void chunk_zero(uint32_t tmem_row, int col0) {
 // SM holds 16 warps: the softmax and the operand splits are latency-bound CUDA-core work and need the occupancy.
 // (Tried and dropped: reversing the row order in every second CTA so that the long causal rows of two co-resident
 // CTAs land on different schedulers - 0.65 ms against 0.59 ms without.)
+template <bool PAIR>
 __global__ void __launch_bounds__(256, 2)
 tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmV,
-                         const __grid_constant__ CUtensorMap tmOut, float* __restrict__ out_rows, int n_items, int nhead, int L, int d,
-                         int row_lo, int dbg) {
+                         const __grid_constant__ CUtensorMap tmOut, float* __restrict__ out_rows, int n_items, int n_traj, int nhead, int L,
+                         int d, int row_lo, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   AttnSmem& s = *reinterpret_cast<AttnSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wq = warp & 3, half = warp >> 2;        // TMEM lane quarter; which half of the row's columns
   const int row = wq * 32 + lane;                   // tile row / TMEM lane of this thread
-  const int NK = (L + 15) & ~15;                    // keys padded to the UMMA N granularity
+  const int NK = PAIR ? kRows : (L + 15) & ~15;     // keys padded to the UMMA N granularity (PAIR: 2 x 64)
   const int nks = (L + 7) >> 3;                     // K = 8 steps of the second product
   const uint32_t idesc_s = idesc_tf32(NK, false), idesc_o = idesc_tf32(kHd, true);
-  const int qrev = wq, lrev = lane;                 // this thread's token is 32 qrev + lrev
+  const int th = PAIR ? (wq >> 1) : 0;              // PAIR: which trajectory of the tile this row belongs to
+  const int qrev = PAIR ? (wq & 1) : wq, lrev = lane;   // this thread's token is 32 qrev + lrev
 
   if (tid == 0) {
     if (smem_u32(smem_raw) & 1023u) __trap();       // the swizzled tiles need 1 KB alignment
@@ -255,13 +318,13 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
   const float scale_log2 = rsqrtf((float)kHd) * 1.4426950408889634f;  // softmax in base 2: exp(x) = 2^(x log2 e)
 
   auto load_qk = [&](int item) {
-    const int b = item / nhead, h = item - b * nhead;
+    const int b = (PAIR ? 2 : 1) * (item / nhead), h = item % nhead;
     mbar_arrive_expect_tx(&s.bar_qk, 2 * kTile * 4);
     tma_load_3d(&tmQkv, &s.bar_qk, s.q_hi, h * kHd, 0, b);
     tma_load_3d(&tmQkv, &s.bar_qk, s.k_hi, d + h * kHd, 0, b);
   };
   auto load_v = [&](int item) {
-    const int b = item / nhead, h = item - b * nhead;
+    const int b = (PAIR ? 2 : 1) * (item / nhead), h = item % nhead;
     mbar_arrive_expect_tx(&s.bar_v, kTile * 4);
     tma_load_3d(&tmV, &s.bar_v, s.v_hi, 2 * d + h * kHd, 0, b);
   };
@@ -271,7 +334,7 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
   float* const psum = pmax + 256;
   auto split_qk = [&](uint32_t ph) {
     mbar_wait(&s.bar_qk, ph);
-    if (row < kMaxKeys) split_tile_row(s.k_hi, s.k_lo, row, half);
+    if (PAIR || row < kMaxKeys) split_tile_row(s.k_hi, s.k_lo, row, half);
     split_q_row(s.q_hi, s.q_lo, row, half, scale_log2);
     fence_proxy_async();
   };
@@ -288,7 +351,8 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
   uint32_t it = 0;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
     const uint32_t ph = it & 1u;
-    const int b = item / nhead, h = item - b * nhead;
+    const int h = item % nhead;
+    const int b = PAIR ? 2 * (item / nhead) + th : item / nhead;      // this row's trajectory
     const int next = item + gridDim.x;
 
     // ---- S = (scaled Q) K^T ---------------------------------------------------------------------------------------
@@ -320,7 +384,19 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     // ---- softmax (two threads per row) --------------------------------------------------------------------------
     // a quarter works when it holds a token (< L) that is asked for (>= row_lo: only the last layer asks for fewer)
     const bool active = qrev * 32 < L && qrev * 32 + 31 >= row_lo;
-    if (active && !(dbg & 4)) {
+    if (PAIR && active) {
+      const float l = qrev == 0 ? softmax_pair_row<0>(tmem_row, 64u * th, lrev, half, wq)
+                                : softmax_pair_row<1>(tmem_row, 64u * th, lrev, half, wq);
+      tmem_st1(tmem_row + kPairX + 2 + half, l);
+      if (qrev == 0) {                                        // keys 32-63 are beyond this quarter's causal range: P = 0
+        uint32_t z[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) z[t] = 0u;
+        TmemRow<16>::st(tmem_row + 32 + 16 * half, z);
+        TmemRow<16>::st(tmem_row + kPairPlo + 32 + 16 * half, z);
+      }
+      tmem_wait_st();
+    } else if (active && !(dbg & 4)) {
       const bool wide = NK - 32 * qrev >= 32;
       float l;
       switch (qrev * 2 + (wide ? 1 : 0)) {
@@ -345,7 +421,24 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     // ---- O = P V ----------------------------------------------------------------------------------------------------
     if (warp == 0) {
       tcgen05_fence_after();
-      if (elect_one()) {
+      if (PAIR) {
+        if (elect_one()) {
+          for (int ks = 0; ks < nks; ++ks) {
+            const uint32_t a_hi = tmem + 8 * ks, a_lo = tmem + kPairPlo + 8 * ks;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {                     // O_t = P V_t: valid in the rows of trajectory t
+              const float* vh = s.v_hi + (64 * t + ks * 8) * kHd;
+              const float* vl = s.v_lo + (64 * t + ks * 8) * kHd;
+              const uint64_t dv_hi = umma_desc_mn_sw128_32b(vh), dv_lo = umma_desc_mn_sw128_32b(vl);
+              const uint32_t acc = tmem + kPairO + 32 * t;
+              mma_tf32_ta(acc, a_lo, dv_hi, idesc_o, ks ? 1u : 0u);
+              mma_tf32_ta(acc, a_hi, dv_lo, idesc_o, 1u);
+              mma_tf32_ta(acc, a_hi, dv_hi, idesc_o, 1u);
+            }
+          }
+          tcgen05_commit(&s.bar_o);
+        }
+      } else if (elect_one()) {
         for (int ks = 0; ks < ((dbg & 2) ? 0 : nks); ++ks) {
           const uint64_t dv_hi = umma_desc_mn_sw128_32b(s.v_hi + ks * 8 * kHd), dv_lo = umma_desc_mn_sw128_32b(s.v_lo + ks * 8 * kHd);
           const uint32_t a_hi = tmem + 8 * ks, a_lo = tmem + kColPlo + 8 * ks;
@@ -364,13 +457,21 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     if (tid == 0 && next < n_items) load_v(next);
     __syncwarp();
     // ---- epilogue: each thread 16 of the row's 32 output dims -----------------------------------------------------
+    const uint32_t col_o = PAIR ? kPairO + 32 * th : kColO;
+    auto row_sum = [&]() -> float {      // the partial sums of the row's two threads, lower half first
+      if (PAIR) {
+        const float l0 = tmem_ld1(tmem_row + kPairX + 2);
+        return l0 + tmem_ld1(tmem_row + kPairX + 3);
+      }
+      return psum[tid & 127] + psum[(tid & 127) + 128];
+    };
     if (active && row_lo == 0) {
       uint32_t r[16];
-      TmemRow<16>::ld(tmem_row + kColO + 16 * half, r);
+      TmemRow<16>::ld(tmem_row + col_o + 16 * half, r);
       if (half == 0 && lane == 0) bulk_wait_read<0>();       // the previous item's store has read the staging chunk
       pair_sync(wq);
       tmem_wait_ld();
-      const float inv = 1.f / (psum[tid & 127] + psum[(tid & 127) + 128]);
+      const float inv = 1.f / row_sum();
       float4 (*stg)[8] = s.stage[wq];
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
@@ -383,7 +484,7 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
       }
       fence_proxy_async();
       pair_sync(wq);
-      if (half == 0 && lane == 0) {
+      if (half == 0 && lane == 0 && b < n_traj) {
         tma_store_3d(&tmOut, stg, h * kHd, qrev * 32, b);
         bulk_commit();
       }
@@ -392,11 +493,12 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
       // row_lo would need a store box starting at a negative row - which the hardware rejects (illegal instruction) - so
       // these few rows go out as plain 16-B stores
       uint32_t r[16];
-      TmemRow<16>::ld(tmem_row + kColO + 16 * half, r);
+      TmemRow<16>::ld(tmem_row + col_o + 16 * half, r);
       tmem_wait_ld();
       const int tok = qrev * 32 + lrev;
-      if (tok >= row_lo && tok < L) {
-        const float inv = 1.f / (psum[tid & 127] + psum[(tid & 127) + 128]);
+      const float rsum = row_sum();
+      if (tok >= row_lo && tok < L && b < n_traj) {
+        const float inv = 1.f / rsum;
         float4* dst = reinterpret_cast<float4*>(out_rows + ((size_t)b * (L - row_lo) + (tok - row_lo)) * d + h * kHd + 16 * half);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
@@ -425,11 +527,15 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
 // trajectory (row_lo = 0: all of them).
 int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhead, int row_lo, cudaStream_t st) {
   if (d != nhead * kHd || L > kMaxKeys || L < 1 || B < 1 || row_lo < 0 || row_lo >= L) return QX_EUNSUPPORTED;
+  // QX_TF_ATTN_PAIR=0 keeps one trajectory per tile whatever L is (A/B runs and the equality test)
+  const char* env_pair = getenv("QX_TF_ATTN_PAIR");
+  const bool pair = L <= 64 && !(env_pair != nullptr && env_pair[0] == '0');
   CUtensorMap mq, mv, mo;
   {
     const cuuint64_t dims[3] = {(cuuint64_t)(3 * d), (cuuint64_t)L, (cuuint64_t)B};
     const cuuint64_t strides[2] = {(cuuint64_t)(3 * d) * 4, (cuuint64_t)L * 3 * d * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)kHd, (cuuint32_t)kRows, 1};
+    const cuuint32_t box1[3] = {(cuuint32_t)kHd, (cuuint32_t)kRows, 1}, box2[3] = {(cuuint32_t)kHd, 64, 2};
+    const cuuint32_t* box = pair ? box2 : box1;
     int rc = make_map_nd(&mq, qkv, 3, dims, strides, box);
     if (rc) return rc;
     // V is an MN-major operand of the second product: 32-B swizzle atoms (see umma_desc_mn_sw128_32b)
@@ -447,18 +553,20 @@ int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhe
   static bool cfg = false;
   static int num_sms = 0;
   if (!cfg) {
-    cudaFuncSetAttribute(tf_attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmem));
+    cudaFuncSetAttribute(tf_attention_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmem));
+    cudaFuncSetAttribute(tf_attention_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmem));
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     cfg = true;
   }
-  const int n_items = B * nhead;
+  const int n_items = (pair ? (B + 1) / 2 : B) * nhead;
   // QX_TF_ATTN_DBG (timing experiments only, results are then wrong on purpose): bit 1 no P V MMAs, bit 2 no softmax
   const char* env_dbg = getenv("QX_TF_ATTN_DBG");
   const int dbg = env_dbg ? atoi(env_dbg) : 0;
   const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;
-  tf_attention_umma_kernel<<<grid, 256, sizeof(AttnSmem), st>>>(mq, mv, mo, out, n_items, nhead, L, d, row_lo, dbg);
+  if (pair) tf_attention_umma_kernel<true><<<grid, 256, sizeof(AttnSmem), st>>>(mq, mv, mo, out, n_items, B, nhead, L, d, row_lo, dbg);
+  else tf_attention_umma_kernel<false><<<grid, 256, sizeof(AttnSmem), st>>>(mq, mv, mo, out, n_items, B, nhead, L, d, row_lo, dbg);
   QX_CHECK_LAUNCH("tf_attention_umma_kernel");
   return QX_OK;
 }

@@ -385,6 +385,36 @@ def test_tcgen05_attention_matches_mma_sync_and_exact_attention(system, mode, go
     assert e_mma < tol and e_exact < tol
 
 
+@pytest.mark.parametrize("mode", ["rand", "fp32"])
+@pytest.mark.parametrize("batch", [1, 2, 1201])
+def test_two_cartpole_trajectories_per_attention_tile(mode, batch, golden_dir, monkeypatch):
+    """L = 61 fills half of the M = 128 attention tile, so two cart-pole trajectories share one (rows 0-63 / 64-127,
+    one N = 128 score product, one P V product per trajectory): against one trajectory per tile, the mma.sync kernel
+    and the exact-fp32 path; odd batches leave the last tile half empty (zero-filled by TMA, never stored)."""
+    g = np.load(f"{golden_dir}/tf_forward_cartpole.npz")
+    w = _wrapper("cartpole", mode)
+    rng = np.random.default_rng(9)
+    reps = -(-batch // len(g["x_err"]))
+    x = np.concatenate([g["x_err"] * (1.0 + 0.05 * rng.standard_normal(g["x_err"].shape)) for _ in range(reps)])[:batch]
+    kK = np.concatenate([g["kK"] * (1.0 + 0.05 * rng.standard_normal(g["kK"].shape)) for _ in range(reps)])[:batch]
+    monkeypatch.setenv("QX_TF_ATTN_PAIR", "0")
+    single = w.predict(x, kK)
+    monkeypatch.setenv("QX_TF_ATTN_PAIR", "1")
+    paired = w.predict(x, kK)
+    assert np.isfinite(paired).all() and paired.shape == single.shape
+    assert np.array_equal(w.predict(x, kK), paired)                      # run-to-run
+    monkeypatch.setenv("QX_TF_NO_PRUNE", "1")
+    assert np.array_equal(w.predict(x, kK), paired)                      # full-width last layer (TMA-store epilogue)
+    monkeypatch.setenv("QX_TF_NO_PRUNE", "0")
+    w.tensor_cores = False
+    exact = w.predict(x, kK)
+    e_single, e_exact = relmax(paired, single), relmax(paired, exact)
+    print(f"cartpole/{mode}/B={batch}: paired vs single tile {e_single:.2e} (bitwise {np.array_equal(paired, single)}), vs exact fp32 {e_exact:.2e}")
+    # every score, probability and output element is the same chain of MMAs and roundings in both tilings
+    assert np.array_equal(paired, single)
+    assert e_exact < (5e-6 if mode == "rand" else 5e-5)
+
+
 @pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
 def test_last_layer_on_query_rows_only_is_bit_identical(system, golden_dir, monkeypatch):
     """The last encoder layer runs its attention output, out-proj, LayerNorms, FFN and the head on the T query rows
