@@ -433,7 +433,7 @@ def gpu_bench(args):
     ncu = ncu_reference(dom, blk, system) if B == WORKLOADS[args.workload][2] else None
     if use_tf:
         # transformer mode: the forward (dense layers + attention on tcgen05) is 95 % of the step; it is a sequence of
-        # 22 launches, reported as one tensor-bound unit
+        # 19 launches, reported as one tensor-bound unit
         tpeak, thow = tensor_peak()
         tf_ms = kernels["transformer"]["ms"]
         achieved = TF_FLOPS[system] * B / (tf_ms * 1e-3) / 1e12

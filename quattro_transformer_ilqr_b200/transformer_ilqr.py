@@ -166,7 +166,12 @@ class TransformerILQR:
                                      C.c_void_p(self._shift.data_ptr()), C.c_void_p(engine.gains.data_ptr()),
                                      engine.model.model_id, C.c_void_p(engine.status.data_ptr()),
                                      C.c_void_p(self._ws.data_ptr()), engine.B, engine.stream), "qx_tf_forward")
-        engine.launches += 3 + 7 * self.num_decoder_layers
+        # embed, head, unpack + per layer QKV, attention, out-proj, add+LN, linear1, linear2, add+LN; on the tensor-core
+        # path the two add+LN ride in the GEMM epilogues (QX_TF_FUSE_LN, qx_tf_simt.cu), except norm1 of the pruned last layer
+        fuse = int(os.environ.get("QX_TF_FUSE_LN", "3")) if self.tensor_cores else 0
+        pruned = self.tensor_cores and os.environ.get("QX_TF_NO_PRUNE", "0") != "1"
+        engine.launches += (3 + (7 - (fuse & 1) - ((fuse >> 1) & 1)) * self.num_decoder_layers
+                            + (1 if (fuse & 1) and pruned else 0))
 
     def predict(self, x_seq, kK_seq):
         """x_seq (T, n) [or (B, T, n)], kK_seq (>= prompt_len, c): de-normalised predictions
