@@ -323,15 +323,15 @@ def gpu_bench(args):
 
     # ---- end to end through the host-facing call: pinned inputs in, results out, every step -------
     # StreamedILQR (quattro_transformer_ilqr_b200/pipeline.py) cuts the batch into slices with their own engine and
-    # stream, so uploads, iterations and downloads of different slices overlap; classic mode only (the transformer
-    # wrapper owns one set of device buffers), otherwise the plain engine is used.
+    # stream, so uploads, iterations and downloads of different slices overlap (transformer mode: two slices sharing the
+    # wrapper's weights, each engine with its own activations workspace).
     u_out = torch.empty((B, N, m), dtype=torch.float64).pin_memory()
     x_out = torch.empty((B, N + 1, n), dtype=torch.float64).pin_memory()
     c_out = torch.empty(B, dtype=torch.float64).pin_memory()
-    chunks = args.e2e_chunks if tf is None else 1
+    chunks = args.e2e_chunks if tf is None else min(args.e2e_chunks, 2)     # transformer mode: two slices (each owns a workspace)
     if chunks > 1:
         from quattro_transformer_ilqr_b200.pipeline import StreamedILQR
-        pipe = StreamedILQR(model, B, N, chunks=chunks, device=dev)
+        pipe = StreamedILQR(model, B, N, chunks=chunks, device=dev, tf=tf)
 
         def e2e_step():
             # join=False: consecutive batches pipeline (batch k's downloads overlap batch k+1's uploads and kernels);

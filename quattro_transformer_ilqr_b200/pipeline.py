@@ -31,6 +31,11 @@ class StreamedILQR:
         self.engines = [BatchedILQR(model, hi - lo, N, device=self.device, tf=tf, **engine_kw) for lo, hi in self.bounds]
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.chunks)]
         self.n, self.m = self.engines[0].n, self.engines[0].m
+        if tf is not None:
+            # transformer mode: the slices share the wrapper's device weights (uploaded and split here, once, before any
+            # slice stream can ask for them) and its state shift; each engine owns its activations workspace
+            tf._device_weights(self.device)
+            torch.cuda.current_stream(self.device).synchronize()
 
     @property
     def launches(self):

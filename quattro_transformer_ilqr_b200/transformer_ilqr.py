@@ -38,7 +38,6 @@ class TransformerILQR:
         self._packed = None          # (device, packed weights, TF32 hi/lo split of the dense weights)
         self.tensor_cores = True     # dense layers on tcgen05 (3xTF32); False = exact-fp32 CUDA cores
         self._shift = None
-        self._ws = None
         self._solo = None            # 1-trajectory scratch engine state for predict()
 
     # ------------------------------------------------------------------ checkpoint wire format
@@ -155,8 +154,11 @@ class TransformerILQR:
         dev = engine.device
         w, split = self._device_weights(dev)
         need = lib.qx_tf_workspace_bytes(C.byref(cfg), engine.B)
-        if self._ws is None or self._ws.device != dev or self._ws.numel() * 4 < need:
-            self._ws = torch.empty(need // 4, dtype=torch.float32, device=dev)
+        # the activations live with the ENGINE, not with the wrapper: slices of a batch that run on their own streams
+        # (pipeline.StreamedILQR) share the weights but must not share a workspace
+        ws = getattr(engine, "_tf_ws", None)
+        if ws is None or ws.device != dev or ws.numel() * 4 < need:
+            ws = engine._tf_ws = torch.empty(need // 4, dtype=torch.float32, device=dev)
         if self._shift is None or self._shift.device != dev:
             self.set_shift(np.zeros(self.state_dim), dev)
         c = engine.cur
@@ -165,7 +167,7 @@ class TransformerILQR:
                                      C.c_void_p(engine.x[c].data_ptr()),
                                      C.c_void_p(self._shift.data_ptr()), C.c_void_p(engine.gains.data_ptr()),
                                      engine.model.model_id, C.c_void_p(engine.status.data_ptr()),
-                                     C.c_void_p(self._ws.data_ptr()), engine.B, engine.stream), "qx_tf_forward")
+                                     C.c_void_p(ws.data_ptr()), engine.B, engine.stream), "qx_tf_forward")
         # embed, head, unpack + per layer QKV, attention, out-proj, add+LN, linear1, linear2, add+LN; on the tensor-core
         # path the two add+LN ride in the GEMM epilogues (QX_TF_FUSE_LN, qx_tf_simt.cu), except norm1 of the pruned last layer
         fuse = int(os.environ.get("QX_TF_FUSE_LN", "3")) if self.tensor_cores else 0

@@ -258,6 +258,42 @@ def test_streamed_host_batch_equals_single_engine():
         StreamedILQR(DeviceModel("quadrotor"), 4, N, chunks=5)
 
 
+@pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
+def test_streamed_host_batch_in_transformer_mode_equals_single_engine(system):
+    """StreamedILQR with the transformer in the loop: the slices share the wrapper's device weights, each engine owns
+    its activations workspace, so slices running on different streams (and batches fed back to back without a join)
+    give the bits of one engine over the whole batch."""
+    from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel
+    from quattro_transformer_ilqr_b200.pipeline import StreamedILQR
+    B, N = 301, HORIZON[system]
+    n, m = (12, 4) if system == "quadrotor" else (4, 1)
+    tf = _wrapper(system, "rand")
+    dev = torch.device("cuda:0")
+    shift = np.zeros(n)
+    if system == "quadrotor":
+        shift[2] = 0.5 - 0.5          # state_offset - x_ref (quadrotor_mpc.py:64-66)
+    tf.set_shift(shift, dev)
+    x0 = torch.as_tensor(sample_x0(system, B, seed=12)).pin_memory()
+    x0b = torch.as_tensor(sample_x0(system, B, seed=13)).pin_memory()
+    u0 = torch.zeros((B, N, m), dtype=torch.float64).pin_memory()
+    u_out = torch.empty((B, N, m), dtype=torch.float64).pin_memory()
+    x_out = torch.empty((B, N + 1, n), dtype=torch.float64).pin_memory()
+    c_out = torch.empty(B, dtype=torch.float64).pin_memory()
+    pipe = StreamedILQR(DeviceModel(system), B, N, chunks=2, tf=tf)
+    for xin in (x0, x0b, x0, x0b):
+        pipe.run(xin, u0, u_out, x_out, c_out, iters=3, tol=1e-3, force=True, join=False)
+    pipe.join()
+    torch.cuda.current_stream().synchronize()
+    e = BatchedILQR(DeviceModel(system), B, N, tf=tf)
+    e.set_problem(x0b, u0)
+    for _ in range(3):
+        e.iterate(1e-3, force=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(c_out).all()
+    assert torch.equal(u_out, e.u_batch().cpu()) and torch.equal(x_out, e.x_batch().cpu())
+    assert torch.equal(c_out, e.cost.cpu())
+
+
 @pytest.mark.parametrize("system", ["quadrotor", "cartpole"])
 def test_graph_replayed_iteration_pairs_equal_plain_iterations(system):
     """BatchedILQR.iterate_pair (two iterations as one CUDA-graph replay) against the same iterations launched
