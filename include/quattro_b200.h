@@ -184,6 +184,13 @@ int qx_tf_forward(const QxTfConfig* cfg, const float* weights, const float* wspl
 int qx_tf_split(const float* w, float* hi, float* lo, size_t count, void* stream);
 int qx_tf_dense(const float* A, const float* w_hi, const float* w_lo, const float* bias, float* C, int M, int N, int K,
                 int relu, void* stream);
+/* A sub-layer's output GEMM with the residual add and the LayerNorm of the post-norm encoder block in its epilogue
+ * (nn.TransformerEncoderLayer, transformer_model.py:112-113: x = norm1(x + out_proj(attn)), x = norm2(x + linear2(..))):
+ * C[M][128] = LayerNorm(res[M][128] + A[M][K] W[128][K]^T + bias) * gamma + beta, eps = 1e-5, row-major fp32.
+ * K % 128 == 0 (else QX_EUNSUPPORTED); C may be res (in-place update of the residual stream), never A.
+ * Bit-identical to qx_tf_dense followed by the separate add + LayerNorm kernel of qx_tf_forward. */
+int qx_tf_dense_ln(const float* A, const float* w_hi, const float* w_lo, const float* bias, const float* res,
+                   const float* gamma, const float* beta, float* C, int M, int K, void* stream);
 /* The causal self-attention core of the encoder layers (nn.MultiheadAttention inside nn.TransformerEncoderLayer,
  * transformer_model.py:112-113; mask :134-135): qkv [B*L][3d] = packed in_proj output, out [B*L][d], 32-wide heads,
  * softmax(Q K^T / sqrt(32) + causal mask) V.  impl 0: tcgen05 (L <= 112), 1: mma.sync (L <= 112), 2: exact fp32. */

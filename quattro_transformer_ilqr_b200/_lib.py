@@ -65,6 +65,7 @@ SIGNATURES = {
     "qx_tf_attention": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "qx_tf_split": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
     "qx_tf_dense": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "qx_tf_dense_ln": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
 }
 
 _lib = None

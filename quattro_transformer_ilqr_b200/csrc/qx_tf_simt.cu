@@ -611,6 +611,17 @@ extern "C" int qx_tf_dense(const float* A, const float* w_hi, const float* w_lo,
   return qx::tf_gemm_tc(A, w_hi, w_lo, bias, C, M, N, K, relu != 0, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int qx_tf_dense_ln(const float* A, const float* w_hi, const float* w_lo, const float* bias, const float* res,
+                              const float* gamma, const float* beta, float* C, int M, int K, void* stream) {
+  QX_CHECK_ARG(A && w_hi && w_lo && bias && res && gamma && beta && C, "null pointer");
+  QX_CHECK_ARG(M >= 0 && K > 0, "bad shape");
+  QX_CHECK_ARG(C != A, "the output may alias the residual, not the A operand");
+  if (M == 0) return QX_OK;
+  const int rc = qx::tf_gemm_ln_tc(A, w_hi, w_lo, bias, res, gamma, beta, C, M, K, static_cast<cudaStream_t>(stream));
+  if (rc == QX_EUNSUPPORTED) qx::set_error("qx_tf_dense_ln needs K %% 128 == 0 (got K=%d)", K);
+  return rc;
+}
+
 // Causal self-attention core of nn.MultiheadAttention as the model uses it (transformer_model.py:112-113, :134-136):
 // qkv [B*L][3d] packed in_proj output -> out [B*L][d] (heads concatenated), head dimension 32.
 // impl 0: tcgen05 kernel, 1: mma.sync kernel, 2: exact-fp32 CUDA-core kernel.

@@ -389,3 +389,54 @@ def test_attention_operator_all_kernels_and_determinism(L):
                     first = out
                 else:
                     assert torch.equal(out, first), f"tcgen05 attention: launch {i} differs from launch 0"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K", [128, 256, 512])
+def test_dense_layer_with_layernorm_epilogue(K):
+    """qx_tf_dense_ln (sub-layer GEMM + residual + LayerNorm in the epilogue; out_proj -> norm1 and linear2 -> norm2 of
+    nn.TransformerEncoderLayer, transformer_model.py:112-113) against torch in float64 and in float32 on a ragged row
+    count, out of place and in place on the residual stream; 30 launches on identical inputs at the benchmark row
+    count are bit-identical; unsupported K is refused."""
+    import ctypes as C
+    from quattro_transformer_ilqr_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    torch.manual_seed(4)
+    N = 128
+    W = torch.randn(N, K, device=dev) / K ** 0.5
+    b = torch.randn(N, device=dev)
+    gamma, beta = 1.0 + 0.1 * torch.randn(N, device=dev), 0.1 * torch.randn(N, device=dev)
+    hi, lo = torch.empty_like(W), torch.empty_like(W)
+    _lib.check(lib.qx_tf_split(_ptr(W), _ptr(hi), _ptr(lo), W.numel(), st), "qx_tf_split")
+    for M, reps in ((128 * 37 + 45, 2), (8192 * 101, 30)):
+        A = torch.randn(M, K, device=dev)
+        res = 0.3 + 2.0 * torch.randn(M, N, device=dev)          # a mean the normalisation has to remove
+        first = None
+        for i in range(reps):
+            out = torch.full((M, N), float("nan"), device=dev)
+            _lib.check(lib.qx_tf_dense_ln(_ptr(A), _ptr(hi), _ptr(lo), _ptr(b), _ptr(res), _ptr(gamma), _ptr(beta), _ptr(out),
+                                          M, K, st), "qx_tf_dense_ln")
+            torch.cuda.synchronize()
+            if first is None:
+                first = out
+                for sl in (slice(0, 4096), slice(M - 300, M)):
+                    pre = res[sl].double() + A[sl].double() @ W.double().T + b.double()
+                    exact = torch.nn.functional.layer_norm(pre, (N,), gamma.double(), beta.double(), 1e-5)
+                    assert float((out[sl].double() - exact).abs().max()) < 5e-6 * float(exact.abs().max())
+                    ref32 = torch.nn.functional.layer_norm(res[sl] + torch.nn.functional.linear(A[sl], W, b), (N,), gamma, beta, 1e-5)
+                    assert float((out[sl] - ref32).abs().max()) < 2e-5 * float(exact.abs().max())   # torch's GEMM may run TF32-free fp32
+            else:
+                assert torch.equal(out, first), f"launch {i} differs from launch 0 (M={M})"
+        inplace = res.clone()
+        _lib.check(lib.qx_tf_dense_ln(_ptr(A), _ptr(hi), _ptr(lo), _ptr(b), _ptr(inplace), _ptr(gamma), _ptr(beta), _ptr(inplace),
+                                      M, K, st), "qx_tf_dense_ln")
+        torch.cuda.synchronize()
+        assert torch.equal(inplace, first)
+        del A, res, first, inplace
+    small = torch.zeros(128, 96, device=dev)
+    rc = lib.qx_tf_dense_ln(_ptr(small), _ptr(hi), _ptr(lo), _ptr(b), _ptr(small), _ptr(gamma), _ptr(beta), _ptr(torch.zeros(128, 128, device=dev)),
+                            128, 96, st)
+    assert rc != 0 and b"K" in lib.qx_last_error()
+
