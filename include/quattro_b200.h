@@ -147,9 +147,11 @@ int qx_riccati_blk(const QxParams* p, const float* expansion, const float* termi
  * A trajectory that finishes has its final iterate in BOTH (x_in,u_in) and (x_out,u_out), so the
  * caller can ping-pong the buffers.  n_active (device int32, may be NULL) is incremented by the
  * number of trajectories still active afterwards.
- * workspace (qx_linesearch_workspace_bytes(), may be NULL): with it, models that support it run the
- * search in two phases - alpha = 1 for every trajectory, then the five remaining alphas of the rejected
- * ones concurrently (candidates parked in the workspace) - instead of one alpha after the other. */
+ * workspace (qx_linesearch_workspace_bytes(), may be NULL): with it the candidates are evaluated concurrently
+ * instead of one alpha after the other - quadrotor (diagonal weights): alpha = 1 for every trajectory, then the
+ * remaining alphas of the rejected ones in two stages (candidates parked in the workspace); cart-pole: the six
+ * alphas side by side (costs only; alpha = 1 also stored), then the winners other than alpha = 1 re-rolled and
+ * stored (the workspace holds one int32 hint per trajectory).  Results are bit-identical with and without it. */
 size_t qx_linesearch_workspace_bytes(int model_id, int B, int N);
 int qx_linesearch(const QxParams* p, double* x_in, double* u_in, const float* gains, double* cost,
                   int32_t* status, int32_t* iters, int32_t* alpha, double* x_out, double* u_out,

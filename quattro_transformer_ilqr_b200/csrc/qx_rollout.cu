@@ -222,6 +222,166 @@ linesearch_kernel(const __grid_constant__ QxParams p, double* __restrict__ x_in,
 }
 
 // ------------------------------------------------------------------------------------------
+// Parallel-alpha line search for the SOA layout (cart-pole).  The kernel above walks the alpha list inside one thread:
+// up to six dependent rollouts of N sequential steps on a grid of B/32 warps - a few warps per SM, pure latency
+// (0.12 ms at 4 096 cart-pole trajectories when smaller steps are needed).  Here the six candidates of a trajectory
+// are rolled out SIDE BY SIDE: CTA = 32 trajectories x 6 warps, warp a takes alpha_a and computes the candidate's
+// cost; warp 0 (alpha = 1, the usual winner) also stores its candidate.  The first accepted alpha (:440-451, "<=") is
+// picked through shared memory.  Trajectories that take alpha = 1 or none are finished on the spot; the others are
+// re-rolled with their winner by linesearch_hint_kernel, which stores it: one or two rollout latencies instead of up to
+// six.  The file is compiled with -fmad=false and the candidate arithmetic is the sequential kernel's, so costs,
+// decisions and trajectories are bit-identical to it (tests: both paths against the oracle and against each other).
+template <class Mdl, bool STORE>
+__device__ __forceinline__ double ls_candidate_soa(const QxParams& p, const double* __restrict__ x_in,
+                                                   const double* __restrict__ u_in, const float* __restrict__ gains,
+                                                   double* __restrict__ x_out, double* __restrict__ u_out, double alpha,
+                                                   int b, int B, int N) {
+  constexpr int n = Mdl::n, m = Mdl::m;
+  constexpr int G = Rec<n, m>::gain;
+  double xh[n], xn[n], un[m], uh[m], xnext[n], xn_nx[n], un_nx[m];
+  float g[G], g_nx[G];
+  auto fetch = [&](int t) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) xn_nx[i] = x_in[((size_t)t * n + i) * B + b];
+#pragma unroll
+    for (int j = 0; j < m; ++j) un_nx[j] = u_in[((size_t)t * m + j) * B + b];
+#pragma unroll
+    for (int q = 0; q < G; ++q) g_nx[q] = gains[((size_t)t * G + q) * B + b];
+  };
+  fetch(0);
+#pragma unroll
+  for (int i = 0; i < n; ++i) xh[i] = xn_nx[i];          // x_hat_0 = x_0
+  double c = 0.0;
+  for (int t = 0; t < N; ++t) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) xn[i] = xn_nx[i];
+#pragma unroll
+    for (int j = 0; j < m; ++j) un[j] = un_nx[j];
+#pragma unroll
+    for (int q = 0; q < G; ++q) g[q] = g_nx[q];
+    if (t + 1 < N) fetch(t + 1);
+#pragma unroll
+    for (int j = 0; j < m; ++j) {
+      double kd = 0.0;
+#pragma unroll
+      for (int i = 0; i < n; ++i) kd += (double)g[m + j * n + i] * (xh[i] - xn[i]);
+      const double du = (double)g[j] + kd;
+      uh[j] = un[j] + alpha * du;
+    }
+    if (STORE) {
+#pragma unroll
+      for (int i = 0; i < n; ++i) x_out[((size_t)t * n + i) * B + b] = xh[i];
+#pragma unroll
+      for (int j = 0; j < m; ++j) u_out[((size_t)t * m + j) * B + b] = uh[j];
+    }
+    c += running_cost<Mdl, double>(xh, uh, p);
+    discrete_step<Mdl, double>(xh, uh, p, xnext);
+#pragma unroll
+    for (int i = 0; i < n; ++i) xh[i] = xnext[i];
+  }
+  if (STORE) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) x_out[((size_t)N * n + i) * B + b] = xh[i];
+  }
+  return c + final_cost<Mdl, double>(xh, p);
+}
+
+// Bookkeeping of one trajectory once its alpha is known (the tail of linesearch_kernel): stopping rule (:472), the
+// nominal kept when no alpha was accepted, the final iterate mirrored into both buffers.  Returns "still active".
+template <class Mdl>
+__device__ __forceinline__ bool ls_finish_soa(double* __restrict__ x_in, double* __restrict__ u_in, double* __restrict__ x_out,
+                                              double* __restrict__ u_out, double* __restrict__ cost, int32_t* __restrict__ status,
+                                              int32_t* __restrict__ iters, int32_t* __restrict__ alpha_out, int idx, double cur,
+                                              double new_cost, double tol, uint32_t flags, int b, int B, int N) {
+  constexpr int n = Mdl::n, m = Mdl::m;
+  const bool found = idx >= 0;
+  bool done = (!found) || (fabs(cur - new_cost) < tol);
+  if (flags & QX_LS_FORCE_ACTIVE) done = false;
+  if (!found) {
+    for (int t = 0; t <= N; ++t)
+#pragma unroll
+      for (int i = 0; i < n; ++i) x_out[((size_t)t * n + i) * B + b] = x_in[((size_t)t * n + i) * B + b];
+    for (int t = 0; t < N; ++t)
+#pragma unroll
+      for (int j = 0; j < m; ++j) u_out[((size_t)t * m + j) * B + b] = u_in[((size_t)t * m + j) * B + b];
+  } else if (done) {
+    for (int t = 0; t <= N; ++t)
+#pragma unroll
+      for (int i = 0; i < n; ++i) x_in[((size_t)t * n + i) * B + b] = x_out[((size_t)t * n + i) * B + b];
+    for (int t = 0; t < N; ++t)
+#pragma unroll
+      for (int j = 0; j < m; ++j) u_in[((size_t)t * m + j) * B + b] = u_out[((size_t)t * m + j) * B + b];
+  }
+  cost[b] = found ? new_cost : cur;
+  alpha_out[b] = idx;
+  iters[b] += 1;
+  if (done) status[b] = 1;
+  return !done;
+}
+
+template <class Mdl>
+__global__ void __launch_bounds__(32 * QX_NUM_ALPHA)
+linesearch_par_kernel(const __grid_constant__ QxParams p, double* x_in, double* u_in, const float* __restrict__ gains,
+                      double* __restrict__ cost, int32_t* __restrict__ status, int32_t* __restrict__ iters,
+                      int32_t* __restrict__ alpha_out, double* x_out, double* u_out, int32_t* __restrict__ n_active,
+                      int32_t* __restrict__ hint, double tol, uint32_t flags, int B, int N) {
+  static_assert(Mdl::layout == QX_LAYOUT_SOA, "parallel-alpha search: SOA layout only");
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ double cand[QX_NUM_ALPHA][32];
+  const int lane = threadIdx.x, a = threadIdx.y;
+  const int b = blockIdx.x * 32 + lane;
+  const bool mine = (b < B) && (status[b] == 0);
+  if (mine) {
+    cand[a][lane] = (a == 0) ? ls_candidate_soa<Mdl, true>(p, x_in, u_in, gains, x_out, u_out, kAlphas[0], b, B, N)
+                             : ls_candidate_soa<Mdl, false>(p, x_in, u_in, gains, x_out, u_out, kAlphas[a], b, B, N);
+  }
+  __syncthreads();
+  if (a != 0) return;
+  bool still_active = false;
+  if (b < B) {
+    int pending = 0;
+    if (mine) {
+      const double cur = cost[b];
+      int idx = -1;
+#pragma unroll
+      for (int q = QX_NUM_ALPHA - 1; q >= 0; --q)
+        if (cand[q][lane] <= cur) idx = q;                 // the FIRST accepted alpha, "<=" (quattro_ilqr_tf.py:444)
+      if (idx <= 0)
+        still_active = ls_finish_soa<Mdl>(x_in, u_in, x_out, u_out, cost, status, iters, alpha_out, idx, cur, cand[0][lane], tol,
+                                          flags, b, B, N);
+      else
+        pending = idx;
+    }
+    hint[b] = pending;
+  }
+  const unsigned act = __ballot_sync(FULL, still_active);
+  if (lane == 0 && n_active != nullptr && act != 0u) atomicAdd(n_active, __popc(act));
+}
+
+template <class Mdl>
+__global__ void __launch_bounds__(32)
+linesearch_hint_kernel(const __grid_constant__ QxParams p, double* x_in, double* u_in, const float* __restrict__ gains,
+                       double* __restrict__ cost, int32_t* __restrict__ status, int32_t* __restrict__ iters,
+                       int32_t* __restrict__ alpha_out, double* x_out, double* u_out, int32_t* __restrict__ n_active,
+                       const int32_t* __restrict__ hint, double tol, uint32_t flags, int B, int N) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x;
+  const int b = blockIdx.x * 32 + lane;
+  const int idx = (b < B) ? hint[b] : 0;
+  if (!__any_sync(FULL, idx > 0)) return;
+  bool still_active = false;
+  if (idx > 0) {
+    const double cur = cost[b];
+    const double c = ls_candidate_soa<Mdl, true>(p, x_in, u_in, gains, x_out, u_out, kAlphas[idx], b, B, N);
+    // same arithmetic as the probe, so c <= cur holds again; were it ever not to, the nominal is kept
+    still_active = ls_finish_soa<Mdl>(x_in, u_in, x_out, u_out, cost, status, iters, alpha_out, c <= cur ? idx : -1, cur, c, tol,
+                                      flags, b, B, N);
+  }
+  const unsigned act = __ballot_sync(FULL, still_active);
+  if (lane == 0 && n_active != nullptr && act != 0u) atomicAdd(n_active, __popc(act));
+}
+
+// ------------------------------------------------------------------------------------------
 // One candidate rollout with a caller-chosen alpha: iLQR_TF.forward_pass (quattro_ilqr_tf.py:377-390)
 // as a stand-alone entry point (API completeness; the solver itself uses the fused line search).
 template <class Mdl>
@@ -283,6 +443,20 @@ static int launch_linesearch(const QxParams* p, double* x_in, double* u_in, cons
   return QX_OK;
 }
 
+// SOA layout with a workspace (int32 hint per trajectory): the six alphas side by side, then the winners
+template <class Mdl>
+static int launch_linesearch_par(const QxParams* p, double* x_in, double* u_in, const float* gains, double* cost,
+                                 int32_t* status, int32_t* iters, int32_t* alpha, double* x_out, double* u_out,
+                                 int32_t* n_active, int32_t* hint, double tol, uint32_t flags, int B, int N, cudaStream_t st) {
+  linesearch_par_kernel<Mdl><<<ceil_div(B, 32), dim3(32, QX_NUM_ALPHA), 0, st>>>(*p, x_in, u_in, gains, cost, status, iters, alpha,
+                                                                                  x_out, u_out, n_active, hint, tol, flags, B, N);
+  QX_CHECK_LAUNCH("linesearch_par_kernel");
+  linesearch_hint_kernel<Mdl><<<ceil_div(B, 32), 32, 0, st>>>(*p, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out,
+                                                              n_active, hint, tol, flags, B, N);
+  QX_CHECK_LAUNCH("linesearch_hint_kernel");
+  return QX_OK;
+}
+
 // distributed-state 4-lane kernels of qx_quadls.cu (quadrotor, diagonal weights)
 size_t qd_workspace_bytes(int B, int N);
 int qd_launch_rollout(const QxParams* p, const double* x0, const double* u, double* x, double* cost,
@@ -312,7 +486,9 @@ extern "C" int qx_rollout_cost(const QxParams* p, const double* x0, const double
 }
 
 extern "C" size_t qx_linesearch_workspace_bytes(int model_id, int B, int N) {
-  if (model_id != QX_MODEL_QUADROTOR || B <= 0 || N <= 0) return 0;
+  if (B <= 0 || N <= 0) return 0;
+  if (model_id == QX_MODEL_CARTPOLE) return ((size_t)B * sizeof(int32_t) + 127) & ~(size_t)127;   // winner hints
+  if (model_id != QX_MODEL_QUADROTOR) return 0;
   return qx::qd_workspace_bytes(B, N);
 }
 
@@ -327,6 +503,9 @@ extern "C" int qx_linesearch(const QxParams* p, double* x_in, double* u_in, cons
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (p->model_id) {
     case QX_MODEL_CARTPOLE:
+      if (workspace != nullptr)       // six alphas side by side + winners (two launches); NULL: the sequential kernel
+        return qx::launch_linesearch_par<qx::CartPole>(p, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out, n_active,
+                                                       static_cast<int32_t*>(workspace), tol, flags, B, N, st);
       return qx::launch_linesearch<qx::CartPole>(p, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out,
                                                  n_active, tol, flags, B, N, st);
     case QX_MODEL_QUADROTOR: {

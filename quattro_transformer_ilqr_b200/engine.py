@@ -138,8 +138,10 @@ class BatchedILQR:
                                           _lib.QX_LS_FORCE_ACTIVE if force else 0, self.B, self.N, self.stream),
                    "qx_linesearch")
         # the staged search of the quadrotor (diagonal weights, workspace given) is five kernels: A, B1, C1, B2, C2
+        # the cart-pole with a workspace is two: the six alphas side by side, then the winners that are not alpha = 1
         staged = self.ls_workspace is not None and self.model.model_id == _lib.QX_MODEL_QUADROTOR and self.params.diag_cost
-        self.launches += 5 if staged else 1
+        par = self.ls_workspace is not None and self.model.model_id == _lib.QX_MODEL_CARTPOLE
+        self.launches += 5 if staged else (2 if par else 1)
         self.cur = 1 - c
 
     def forward_pass(self, alpha):

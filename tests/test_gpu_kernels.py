@@ -194,11 +194,11 @@ def test_riccati_block_path_indefinite_quu():
     assert relmax(K[:, N - 3:], K_ref) < 1e-4 and relmax(k[:, N - 3:], k_ref) < 1e-4
 
 
-@pytest.mark.parametrize("system,B,us", CASES + [("quadrotor-sequential", 97, 1.5)])
+@pytest.mark.parametrize("system,B,us", CASES + [("quadrotor-sequential", 97, 1.5), ("cartpole-sequential", 257, 3.0)])
 def test_linesearch_decisions_and_candidates(system, B, us):
     """Same gains on both sides (the oracle's, rounded to fp32): identical accepted alpha,
     candidates and costs to fp64 round-off; covers alphas other than 1 and the no-accept case."""
-    two_phase = not system.endswith("-sequential")       # quadrotor: both launch structures
+    two_phase = not system.endswith("-sequential")       # both launch structures (staged / parallel-alpha vs one kernel)
     system = system.split("-")[0]
     x0, u = _problem(system, B, 4, 0.5 * us)
     model = make_model(system)

@@ -294,6 +294,36 @@ def test_streamed_host_batch_in_transformer_mode_equals_single_engine(system):
     assert torch.equal(c_out, e.cost.cpu())
 
 
+@pytest.mark.parametrize("forced", [False, True])
+def test_cartpole_parallel_alpha_search_equals_sequential_kernel(forced):
+    """Cart-pole line search with the six alphas rolled out side by side (+ the winners re-rolled) against the
+    one-thread-walks-the-list kernel: costs, decisions, iteration counts and trajectories bit for bit, over a whole
+    solve (reference stopping rule) and in forced fixed-iteration mode; ragged batch, B = 1 included."""
+    from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel
+    for B in (1, 1003):
+        N = HORIZON["cartpole"]
+        x0 = sample_x0("cartpole", B, seed=31)
+        u0 = np.zeros((B, N, 1))
+        par = BatchedILQR(DeviceModel("cartpole"), B, N)
+        seq = BatchedILQR(DeviceModel("cartpole"), B, N)
+        assert par.ls_workspace is not None
+        seq.ls_workspace = None
+        for e in (par, seq):
+            e.set_problem(x0, u0)
+            if forced:
+                e.solve(fixed_iters=12)
+            else:
+                e.solve(max_iter=100, tol=1e-1)
+        torch.cuda.synchronize()
+        assert par.cur == seq.cur
+        assert torch.equal(par.cost, seq.cost) and torch.equal(par.alpha, seq.alpha) and torch.equal(par.iters, seq.iters)
+        assert torch.equal(par.status, seq.status) and torch.equal(par.n_active, seq.n_active)
+        for buf in (0, 1):
+            assert torch.equal(par.u[buf], seq.u[buf]) and torch.equal(par.x[buf], seq.x[buf])
+        if B > 1:
+            assert len(torch.unique(par.alpha)) >= 3 or not forced       # several alphas occur in forced mode
+
+
 @pytest.mark.parametrize("system", ["quadrotor", "cartpole"])
 def test_graph_replayed_iteration_pairs_equal_plain_iterations(system):
     """BatchedILQR.iterate_pair (two iterations as one CUDA-graph replay) against the same iterations launched
