@@ -78,9 +78,21 @@ riccati_soa_kernel(const float* __restrict__ expansion, const float* __restrict_
 #pragma unroll
     for (int j = 0; j < n; ++j) V[i][j] = terminal[(size_t)(n + i * n + j) * B + b];
 
-  for (int t = N - 1; t >= t_start; --t) {
+  // The record of step t-1 is fetched while step t is computed: with a few warps per SM (one thread per trajectory)
+  // nothing else hides the HBM latency of the 46 loads, and a step costs load latency + arithmetic otherwise.
+  float nxt[R::size];
+  auto fetch = [&](int t) {
     const float* e = expansion + (size_t)t * R::size * B + b;
-    auto ld = [&](int idx) { return e[(size_t)idx * B]; };
+#pragma unroll
+    for (int idx = 0; idx < R::size; ++idx) nxt[idx] = e[(size_t)idx * B];
+  };
+  if (N - 1 >= t_start) fetch(N - 1);
+  for (int t = N - 1; t >= t_start; --t) {
+    float rec[R::size];
+#pragma unroll
+    for (int idx = 0; idx < R::size; ++idx) rec[idx] = nxt[idx];
+    if (t > t_start) fetch(t - 1);
+    auto ld = [&](int idx) { return rec[idx]; };
     float A[n][n], Bm[n][m];
 #pragma unroll
     for (int i = 0; i < n; ++i)
