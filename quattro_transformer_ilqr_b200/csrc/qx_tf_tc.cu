@@ -456,7 +456,11 @@ tf_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           pc[c] = __fadd_rn(__fadd_rn(__fadd_rn(t[0], t[1]), __fadd_rn(t[2], t[3])),
                             __fadd_rn(__fadd_rn(t[4], t[5]), __fadd_rn(t[6], t[7])));
-          __syncwarp();                                  // every lane has its values: the chunk may be overwritten
+          // every lane has CONSUMED its values before the chunk is handed to the next bulk copy: the partial sum below
+          // depends on each of the shared-memory loads, and the empty asm pins its computation in front of the barrier
+          // (an issued-but-pending LDS is not ordered against the async-proxy write the copy performs)
+          asm volatile("" ::"f"(pc[c]) : "memory");
+          __syncwarp();
           if (c < 2 && lane == 0) {
             mbar_arrive_expect_tx(&s.res_full[q][c & 1], 32 * 32 * 4);
             tma_load_2d(&tmR, &s.res_full[q][c & 1], stg, 32 * (c + 2), m0 + q * 32);
