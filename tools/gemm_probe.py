@@ -7,6 +7,8 @@ Variants are selected through the library's debugging environment (read per call
 QX_TF_GEMM_STREAM=1 -> streaming kernel; QX_TF_GEMM_VARIANT=32|22|21 -> raw/hi and lo ring depths of the
 resident-weight kernel; QX_TF_GEMM_DBG bit 0: no global stores, bit 1: no split, bit 2: no epilogue work
 (timing experiments only - results are then wrong on purpose).
+Variant "ln" (N = 128 shapes only): qx_tf_dense_ln, the same GEMM with residual + LayerNorm in its epilogue, timed next to
+qx_tf_dense + the bytes a separate add + LN launch would move (2 x 512 B per row).
 """
 import argparse
 import ctypes as C
@@ -44,6 +46,36 @@ def main():
         Cout = torch.empty(M, N, device=dev)
         ref = None
         for var in args.variants.split(","):
+            if var == "ln":
+                if N != 128 or relu:
+                    continue
+                res = torch.randn(M, N, device=dev)
+                g, be = 1.0 + 0.1 * torch.randn(N, device=dev), 0.1 * torch.randn(N, device=dev)
+
+                def run_ln():
+                    _lib.check(lib.qx_tf_dense_ln(C.c_void_p(A.data_ptr()), C.c_void_p(hi.data_ptr()), C.c_void_p(lo.data_ptr()),
+                                                  C.c_void_p(b.data_ptr()), C.c_void_p(res.data_ptr()), C.c_void_p(g.data_ptr()),
+                                                  C.c_void_p(be.data_ptr()), C.c_void_p(Cout.data_ptr()), M, K, st), "qx_tf_dense_ln")
+                run_ln()
+                torch.cuda.synchronize()
+                ts = []
+                for _ in range(args.reps):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    run_ln()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                ms = float(np.median(ts))
+                pre = res[:4096].double() + A[:4096].double() @ W.double().T + b.double()
+                exact = torch.nn.functional.layer_norm(pre, (N,), g.double(), be.double(), 1e-5)
+                err = ((Cout[:4096].double() - exact).abs().max() / exact.abs().max()).item()
+                gb = M * (K + 2 * N) * 4 / 1e9
+                print(f"N={N:4d} K={K:4d} + residual + LayerNorm (one launch): {ms:7.4f} ms  {gb / (ms * 1e-3):6.0f} GB/s of A + res + C"
+                      f"  relerr vs fp64 {err:.1e}", flush=True)
+                del res
+                continue
             os.environ.pop("QX_TF_GEMM_STREAM", None)
             os.environ.pop("QX_TF_GEMM_VARIANT", None)
             os.environ.pop("QX_TF_GEMM_DBG", None)
