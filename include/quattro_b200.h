@@ -195,7 +195,8 @@ int qx_tf_dense_ln(const float* A, const float* w_hi, const float* w_lo, const f
                    const float* gamma, const float* beta, float* C, int M, int K, void* stream);
 /* The causal self-attention core of the encoder layers (nn.MultiheadAttention inside nn.TransformerEncoderLayer,
  * transformer_model.py:112-113; mask :134-135): qkv [B*L][3d] = packed in_proj output, out [B*L][d], 32-wide heads,
- * softmax(Q K^T / sqrt(32) + causal mask) V.  impl 0: tcgen05 (L <= 112), 1: mma.sync (L <= 112), 2: exact fp32. */
+ * softmax(Q K^T / sqrt(32) + causal mask) V.  impl 0: tcgen05 (L <= 112; for L <= 64 two trajectories share one
+ * M = 128 tile, bit-identical to one per tile), 1: mma.sync (L <= 112), 2: exact fp32. */
 int qx_tf_attention(const float* qkv, float* out, int B, int L, int d, int nhead, int impl, void* stream);
 
 #ifdef __cplusplus
