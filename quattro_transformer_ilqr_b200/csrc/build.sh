@@ -7,6 +7,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr"
 SRCS=$(ls *.cu)
 mkdir -p build
+rm -f build/*.o          # stale objects of deleted sources must not be linked
 pids=()
 for s in $SRCS; do
   EXTRA=""

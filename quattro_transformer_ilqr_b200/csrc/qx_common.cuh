@@ -47,6 +47,16 @@ struct Rec {
 
 __host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Gains are stored with the trajectory index fastest, so that a warp of consecutive trajectories touches whole lines:
+//   QX_LAYOUT_SOA (cart-pole)  float  [N][G][B]
+//   QX_LAYOUT_REC (quadrotor)  float4 [N][G/4][B]   G = 52: float4 #0 = k, #1..#12 = K row-major, four entries each
+// (one 16-B load per thread fetches four entries and a warp's load is 512 contiguous bytes).
+template <int LAYOUT>
+__host__ __device__ __forceinline__ size_t gain_index(int t, int ch, int b, int B, int G) {
+  return (LAYOUT == QX_LAYOUT_REC) ? ((((size_t)t * (G >> 2) + (ch >> 2)) * B + b) << 2) + (ch & 3)
+                                   : ((size_t)t * G + ch) * B + b;
+}
+
 static __constant__ double kAlphas[QX_NUM_ALPHA] = {1.0, 0.5, 0.25, 0.1, 0.05, 0.01};
 
 }  // namespace qx

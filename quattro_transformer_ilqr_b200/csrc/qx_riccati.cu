@@ -458,20 +458,19 @@ riccati_warp_kernel(const float* __restrict__ expansion, const float* __restrict
         for (int c = 0; c < m; ++c) acc = fmaf(Quu[a][c], z[c], acc);
         hm[a] = acc;                         // Q_uu K + Q_ux (column), or Q_uu k + Q_u
       }
-      float* g = gains + ((size_t)t * B + b) * R::gain;
       if (hl < n) {
 #pragma unroll
         for (int a = 0; a < m; ++a) {
           s.Ks[a * n + hl] = z[a];
           s.Ms[a * n + hl] = hm[a];
-          if (valid) g[m + a * n + hl] = z[a];
+          if (valid) gains[gain_index<QX_LAYOUT_REC>(t, m + a * n + hl, b, B, R::gain)] = z[a];
         }
       } else if (hl == n) {
 #pragma unroll
         for (int a = 0; a < m; ++a) {
           s.kh[a] = z[a];
           s.kh[m + a] = hm[a];
-          if (valid) g[a] = z[a];
+          if (valid) gains[gain_index<QX_LAYOUT_REC>(t, a, b, B, R::gain)] = z[a];
         }
       }
     }

@@ -1,20 +1,14 @@
 // Forward rollouts, generic models: nominal simulate+cost, and the fused line search (thread per trajectory).
-// The quadrotor with diagonal weights takes the 4-lane distributed-state kernels of qx_quadls.cu instead.
+// The quadrotor with diagonal weights takes the thread-per-candidate kernels of qx_quadls.cu instead.
 //
 //   rollout_cost_kernel  = iLQR_TF.simulate + compute_total_cost   (quattro_ilqr_tf.py:127-143)
 //   linesearch_kernel    = the alpha loop of optimize (:440-451) around forward_pass (:377-390)
 //                          plus the stopping rule (:472), one launch for the whole batch.
 //
 // One thread owns one trajectory (a rollout is a strictly sequential recursion over t); the
-// batch index is the fastest-varying index of x/u so every global access of a warp is one
-// fully used 256-B (fp64) segment.  All arithmetic is fp64: the accept test compares costs
+// batch index is the fastest-varying index of x, u and the gains, so every global access of a warp is a
+// run of whole lines.  All arithmetic is fp64: the accept test compares costs
 // whose relative difference is routinely 1e-7..1e-9 near convergence (SURVEY.md hard part 3).
-//
-// Gains in the REC layout ([t][b][52] floats, written by the warp-per-trajectory Riccati kernel)
-// are staged per warp through shared memory with 1-D bulk async copies (TMA, SASS UBLKCP): for a
-// fixed t the 32 records of a warp are one contiguous 6656-B chunk; a 4-stage mbarrier ring keeps
-// the copy of step t+3 in flight while step t is computed.
-#include "qx_async.cuh"
 #include "qx_models.cuh"
 
 namespace qx {
@@ -49,14 +43,22 @@ rollout_cost_kernel(const __grid_constant__ QxParams p, const double* __restrict
 }
 
 // ------------------------------------------------------------------------------------------
-constexpr int kLsStages = 4;
-
+// gains of step t for trajectory b into registers (both layouts have b fastest: coalesced)
 template <class Mdl>
-struct LsSmem {
-  static constexpr int G = Rec<Mdl::n, Mdl::m>::gain;
-  alignas(128) float ring[kLsStages][32 * G];
-  alignas(8) uint64_t bar[kLsStages];
-};
+__device__ __forceinline__ void load_gains(const float* __restrict__ gains, int t, int b, int B, float* g) {
+  constexpr int G = Rec<Mdl::n, Mdl::m>::gain;
+  if (Mdl::layout == QX_LAYOUT_REC) {
+    const float4* g4 = reinterpret_cast<const float4*>(gains) + (size_t)t * (G / 4) * B + b;
+#pragma unroll
+    for (int q = 0; q < G / 4; ++q) {
+      const float4 v = g4[(size_t)q * B];
+      g[4 * q + 0] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < G; ++q) g[q] = gains[((size_t)t * G + q) * B + b];
+  }
+}
 
 template <class Mdl>
 __global__ void __launch_bounds__(32)
@@ -67,31 +69,12 @@ linesearch_kernel(const __grid_constant__ QxParams p, double* __restrict__ x_in,
                   int B, int N) {
   constexpr int n = Mdl::n, m = Mdl::m;
   constexpr int G = Rec<n, m>::gain;
-  constexpr bool kRec = (Mdl::layout == QX_LAYOUT_REC);
   constexpr unsigned FULL = 0xffffffffu;
 
   const int lane = threadIdx.x;
-  const int b0 = blockIdx.x * 32;
-  const int b = b0 + lane;
+  const int b = blockIdx.x * 32 + lane;
   const bool mine = (b < B) && (status[b] == 0);
   if (!__any_sync(FULL, mine)) return;
-  const int nb = min(32, B - b0);                       // trajectories covered by this warp
-
-  __shared__ LsSmem<Mdl> sm;
-  uint32_t seq_issue = 0, seq_wait = 0;                 // ring positions (warp-uniform)
-  if (kRec) {
-    if (lane == 0) {
-      for (int s = 0; s < kLsStages; ++s) mbar_init(&sm.bar[s], 1);
-      mbar_fence_init();
-    }
-    __syncwarp();
-  }
-  auto issue = [&](int t) {                             // lane 0 only
-    const int s = seq_issue % kLsStages;
-    const uint32_t bytes = (uint32_t)nb * G * sizeof(float);
-    mbar_arrive_expect_tx(&sm.bar[s], bytes);
-    bulk_g2s(sm.ring[s], gains + ((size_t)t * B + b0) * G, bytes, &sm.bar[s]);
-  };
 
   const double cur = mine ? cost[b] : 0.0;
   double x_first[n];
@@ -108,54 +91,28 @@ linesearch_kernel(const __grid_constant__ QxParams p, double* __restrict__ x_in,
     const double alpha = kAlphas[a];
     double xh[n], xn[n], un[m], uh[m], xnext[n];
     double xn_nx[n], un_nx[m];        // nominal of step t+1, fetched while step t is computed
-    float g_nx[kRec ? 1 : G];         // SOA gains of step t+1 (the REC layout comes through the ring)
+    float g_nx[G];                    // gains of step t+1
 #pragma unroll
     for (int i = 0; i < n; ++i) xh[i] = x_first[i];
     double c = 0.0;
 
-    if (kRec) {
-      if (lane == 0)
-        for (int t = 0; t < kLsStages - 1 && t < N; ++t) { issue(t); ++seq_issue; }
-      seq_issue = __shfl_sync(FULL, seq_issue, 0);
-    }
     auto fetch = [&](int t) {
 #pragma unroll
       for (int i = 0; i < n; ++i) xn_nx[i] = x_in[((size_t)t * n + i) * B + b];
 #pragma unroll
       for (int j = 0; j < m; ++j) un_nx[j] = u_in[((size_t)t * m + j) * B + b];
-      if (!kRec) {
-#pragma unroll
-        for (int q = 0; q < G; ++q) g_nx[q] = gains[((size_t)t * G + q) * B + b];
-      }
+      load_gains<Mdl>(gains, t, b, B, g_nx);
     };
     if (run) fetch(0);
     for (int t = 0; t < N; ++t) {
-      if (kRec) {
-        // all lanes finished reading the stage that is about to be refilled (step t-1's)
-        __syncwarp();
-        if (t + kLsStages - 1 < N) {
-          if (lane == 0) issue(t + kLsStages - 1);
-          ++seq_issue;
-        }
-        mbar_wait(&sm.bar[seq_wait % kLsStages], (seq_wait / kLsStages) & 1u);
-      }
       if (run) {
         float g[G];
 #pragma unroll
         for (int i = 0; i < n; ++i) xn[i] = xn_nx[i];
 #pragma unroll
         for (int j = 0; j < m; ++j) un[j] = un_nx[j];
-        if (kRec) {
-          const float4* r4 = reinterpret_cast<const float4*>(&sm.ring[seq_wait % kLsStages][lane * G]);
 #pragma unroll
-          for (int q = 0; q < G / 4; ++q) {
-            const float4 v = r4[q];
-            g[4 * q + 0] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w;
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < G; ++q) g[q] = g_nx[q];
-        }
+        for (int q = 0; q < G; ++q) g[q] = g_nx[q];
         if (t + 1 < N) fetch(t + 1);
         // du = k + K (x_hat - x);  u_hat = u + alpha * du   (alpha scales the feedback too)
 #pragma unroll
@@ -175,7 +132,6 @@ linesearch_kernel(const __grid_constant__ QxParams p, double* __restrict__ x_in,
 #pragma unroll
         for (int i = 0; i < n; ++i) xh[i] = xnext[i];
       }
-      if (kRec) ++seq_wait;
     }
     if (run) {
 #pragma unroll
@@ -401,10 +357,7 @@ forward_pass_kernel(const __grid_constant__ QxParams p, const double* __restrict
     for (int i = 0; i < n; ++i) xn[i] = x_in[((size_t)t * n + i) * B + b];
 #pragma unroll
     for (int j = 0; j < m; ++j) {
-      auto gv = [&](int q) {
-        return (double)((Mdl::layout == QX_LAYOUT_REC) ? gains[((size_t)t * B + b) * G + q]
-                                                       : gains[((size_t)t * G + q) * B + b]);
-      };
+      auto gv = [&](int q) { return (double)gains[gain_index<Mdl::layout>(t, q, b, B, G)]; };
       double kd = 0.0;
 #pragma unroll
       for (int i = 0; i < n; ++i) kd += gv(m + j * n + i) * (xh[i] - xn[i]);
@@ -457,7 +410,7 @@ static int launch_linesearch_par(const QxParams* p, double* x_in, double* u_in, 
   return QX_OK;
 }
 
-// distributed-state 4-lane kernels of qx_quadls.cu (quadrotor, diagonal weights)
+// thread-per-candidate kernels of qx_quadls.cu (quadrotor, diagonal weights)
 size_t qd_workspace_bytes(int B, int N);
 int qd_launch_rollout(const QxParams* p, const double* x0, const double* u, double* x, double* cost,
                       const int32_t* status, int B, int N, cudaStream_t st);
@@ -478,7 +431,7 @@ extern "C" int qx_rollout_cost(const QxParams* p, const double* x0, const double
   switch (p->model_id) {
     case QX_MODEL_CARTPOLE: return qx::launch_rollout<qx::CartPole>(p, x0, u, x, cost, status, B, N, st);
     case QX_MODEL_QUADROTOR:
-      if (p->diag_cost) return qx::qd_launch_rollout(p, x0, u, x, cost, status, B, N, st);   // same arithmetic as the 4-lane line search
+      if (p->diag_cost) return qx::qd_launch_rollout(p, x0, u, x, cost, status, B, N, st);   // same arithmetic as the line search
       return qx::launch_rollout<qx::Quadrotor>(p, x0, u, x, cost, status, B, N, st);
   }
   qx::set_error("unknown model_id %d", p->model_id);

@@ -39,8 +39,7 @@ __global__ void tf_embed_kernel(const QxTfConfig cfg, const float* __restrict__ 
     const int t = N - P + (tok - N - 1);             // absolute time of this prompt row
     if (ch < c) {
       const int G = m + m * n;
-      const float g = (LAYOUT == QX_LAYOUT_REC) ? gains[((size_t)t * B + b) * G + ch]
-                                                : gains[((size_t)t * G + ch) * B + b];
+      const float g = gains[gain_index<LAYOUT>(t, ch, b, B, G)];
       in[ch] = (float)(((double)g - (double)w[lay.u_mean + ch]) / (double)w[lay.u_std + ch]);
     }
     __syncthreads();
@@ -118,7 +117,7 @@ tf_embed128_kernel(const QxTfConfig cfg, const float* __restrict__ w, const doub
     for (int k = 0; k < 2; ++k) {
       const int o = lane + 32 * k;
       if (o < c) {
-        const float g = (LAYOUT == QX_LAYOUT_REC) ? gains[((size_t)t * B + b) * G + o] : gains[((size_t)t * G + o) * B + b];
+        const float g = gains[gain_index<LAYOUT>(t, o, b, B, G)];
         in[k] = (float)(((double)g - (double)w[lay.u_mean + o]) / (double)w[lay.u_std + o]);
       }
     }
@@ -308,8 +307,7 @@ __global__ void tf_output_kernel(const QxTfConfig cfg, const float* __restrict__
   const int a = o / (1 + n), j = o % (1 + n);                        // row a of [k_a | K_a,:]
   const int slot = (j == 0) ? a : (m + a * n + (j - 1));
   const int G = m + m * n;
-  if (LAYOUT == QX_LAYOUT_REC) gains[((size_t)t * B + b) * G + slot] = val;
-  else gains[((size_t)t * G + slot) * B + b] = val;
+  gains[gain_index<LAYOUT>(t, slot, b, B, G)] = val;
 }
 
 // de-normalise + unpack of a precomputed output head y[rows][128] (tensor-core path)
@@ -326,8 +324,7 @@ __global__ void tf_unpack_kernel(const QxTfConfig cfg, const float* __restrict__
   const int a = o / (1 + n), j = o % (1 + n);
   const int slot = (j == 0) ? a : (m + a * n + (j - 1));
   const int G = m + m * n;
-  if (LAYOUT == QX_LAYOUT_REC) gains[((size_t)t * B + b) * G + slot] = val;
-  else gains[((size_t)t * G + slot) * B + b] = val;
+  gains[gain_index<LAYOUT>(t, slot, b, B, G)] = val;
 }
 
 // the same, one CTA per trajectory (c <= 64): warp w takes the target rows t = w (mod 4)
@@ -349,8 +346,7 @@ tf_unpack128_kernel(const QxTfConfig cfg, const float* __restrict__ w, const flo
         const float val = row[o] * w[lay.u_std + o] + w[lay.u_mean + o];
         const int a = o / (1 + n), j = o % (1 + n);
         const int slot = (j == 0) ? a : (m + a * n + (j - 1));
-        if (LAYOUT == QX_LAYOUT_REC) gains[((size_t)t * B + b) * G + slot] = val;
-        else gains[((size_t)t * G + slot) * B + b] = val;
+        gains[gain_index<LAYOUT>(t, slot, b, B, G)] = val;
       }
     }
   }

@@ -305,8 +305,8 @@ class BatchedILQR:
         """K (B, N, m, n), k (B, N, m) as float32 tensors."""
         B, N, n, m = self.B, self.N, self.n, self.m
         G = m + m * n
-        if self.layout == _lib.QX_LAYOUT_REC:
-            g = self.gains.view(N, B, G).permute(1, 0, 2)
+        if self.layout == _lib.QX_LAYOUT_REC:        # float4 [N][G/4][B]
+            g = self.gains.view(N, G // 4, B, 4).permute(2, 0, 1, 3).reshape(B, N, G)
         else:
             g = self.gains.view(N, G, B).permute(2, 0, 1)
         return (g[..., m:].reshape(B, N, m, n).clone(memory_format=torch.contiguous_format),
@@ -318,7 +318,7 @@ class BatchedILQR:
         g = torch.cat([torch.as_tensor(k, dtype=torch.float32).reshape(B, N, m),
                        torch.as_tensor(K, dtype=torch.float32).reshape(B, N, m * n)], dim=-1).to(self.device)
         if self.layout == _lib.QX_LAYOUT_REC:
-            self.gains.copy_(g.permute(1, 0, 2).reshape(-1))
+            self.gains.copy_(g.view(B, N, (m + m * n) // 4, 4).permute(1, 2, 0, 3).reshape(-1))
         else:
             self.gains.copy_(g.permute(1, 2, 0).reshape(-1))
 
