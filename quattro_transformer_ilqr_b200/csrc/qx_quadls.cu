@@ -31,13 +31,12 @@
 // operation order (block sums of the cost, partial sums of K dx) is the one of the four-lane version, whose
 // results this file reproduces bit for bit.
 //
-// Line search = three stages, so that the first accepted alpha is found without rolling out all six:
-//   A   alpha = 1 for every active trajectory, candidate written straight into (x_out, u_out)
-//   B1  alpha = .5, .25 of the rejected ones, one thread each (queue compacted by A)   -> C1 picks / re-queues
-//   B2  alpha = .1, .05, .01 of the still rejected ones                                 -> C2 picks / gives up
-// Candidates of B are parked in a scratch [plane][row][b]; C copies the winner out with thread-per-trajectory
-// (coalesced) row loops.  Queues are appended per warp in trajectory order, so the threads of a B warp touch
-// neighbouring columns.
+// Line search = three launches, so that the first accepted alpha is found without six sequential rollouts:
+//   A   alpha = 1 for every active trajectory, candidate written straight into (x_out, u_out); the rejected
+//       trajectories are queued (appended per warp in trajectory order, so neighbours stay neighbours)
+//   B   alpha = .5, .25, .1, .05, .01 of the queued ones side by side, one thread each, costs only
+//   W   the first accepted alpha of a queued trajectory is rolled out once more, into (x_out, u_out); stopping rule
+// B and W exit at once when the queue is empty.
 #include "qx_common.cuh"
 #include "qx_fp64math.cuh"
 
@@ -183,41 +182,77 @@ __device__ __forceinline__ void qd_final(const double* x, const QdK& k, double* 
 
 __device__ __forceinline__ double qd_total(const double* c) { return (c[0] + c[1]) + (c[2] + c[3]); }
 
+// Staging buffer of one warp (= one CTA): the nominal and the gains of the NEXT step of every lane, copied
+// global -> shared by cp.async (LDGSTS) while the current step is computed.  In registers the same prefetch costs
+// 84 of them (the kernels sat at 255 with spills: two warps per scheduler); staged, a candidate needs <= 168 and
+// three warps share a scheduler.  [row][lane] layout: conflict free, and a thread only reads what it copied itself.
+struct QdStage {
+  double xu[2][kN + kM][32];
+  float4 g[2][kG / 4][32];
+};
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
 // One candidate rollout (forward_pass :377-390, step size alpha) by one thread.  Nominal at xin / uin (row stride sB),
 // gains at rec (float4 [N][13][B], same row stride); the candidate goes to xo / uo (row stride sO).  `limit`: the
 // candidate is abandoned (its thread stops loading and storing) once its partial cost exceeds it; +inf = never.
 // All 32 lanes of the warp must call it; lanes with run == false only take part in the votes.
 // Returns the total cost, or a partial cost > limit for an abandoned candidate.
-template <int INTEG>
-__device__ __forceinline__ double qd_candidate(const QdK& k, bool run, const double* __restrict__ xin,
+template <int INTEG, bool STORE>
+__device__ __forceinline__ double qd_candidate(const QdK& k, QdStage& st, bool run, const double* __restrict__ xin,
                                                const double* __restrict__ uin, const float4* __restrict__ rec, size_t sB,
                                                double alpha, double limit, double* __restrict__ xo,
                                                double* __restrict__ uo, size_t sO, int N) {
-  double xh[kN], xn[kN], un[kM];
-  float4 g[kG / 4];
+  const int lane = threadIdx.x & 31;
+  double xh[kN];
 #pragma unroll
   for (int i = 0; i < kN; ++i) xh[i] = run ? xin[(size_t)i * sB] : 0.0;
-  auto fetch = [&]() {
+  // the copies of step t land in buffer t & 1; one commit group per step (empty when there is nothing to copy), so
+  // "all but the newest group" is always "everything up to step t"
+  auto fetch = [&](int buf, bool doit) {
+    if (doit) {
 #pragma unroll
-    for (int i = 0; i < kN; ++i) xn[i] = xin[(size_t)i * sB];
+      for (int i = 0; i < kN; ++i) cp_async8(&st.xu[buf][i][lane], xin + (size_t)i * sB);
 #pragma unroll
-    for (int j = 0; j < kM; ++j) un[j] = uin[(size_t)j * sB];
+      for (int j = 0; j < kM; ++j) cp_async8(&st.xu[buf][kN + j][lane], uin + (size_t)j * sB);
 #pragma unroll
-    for (int q = 0; q < kG / 4; ++q) g[q] = rec[(size_t)q * sB];
+      for (int q = 0; q < kG / 4; ++q) cp_async16(&st.g[buf][q][lane], rec + (size_t)q * sB);
+    }
+    cp_async_commit();
     xin += kN * sB;
     uin += kM * sB;
     rec += (kG / 4) * sB;
   };
-  if (run) fetch();
+  fetch(0, run);
+  fetch(1, run && N > 1);
   double c[4] = {0.0, 0.0, 0.0, 0.0};
   for (int t = 0; t < N; ++t) {
     if (!__any_sync(FULL, run)) break;
+    cp_async_wait<1>();
+    const int buf = t & 1;
     double uh[kM];
     {
       double dx[kN];
 #pragma unroll
-      for (int i = 0; i < kN; ++i) dx[i] = xh[i] - xn[i];
-      const float* gf = reinterpret_cast<const float*>(g);
+      for (int i = 0; i < kN; ++i) dx[i] = xh[i] - st.xu[buf][i][lane];
+      float gf[kG];
+#pragma unroll
+      for (int q = 0; q < kG / 4; ++q) {
+        const float4 v = st.g[buf][q][lane];
+        gf[4 * q] = v.x; gf[4 * q + 1] = v.y; gf[4 * q + 2] = v.z; gf[4 * q + 3] = v.w;
+      }
 #pragma unroll
       for (int j = 0; j < kM; ++j) {
         // du_j = k_j + K[j,:] (x_hat - x)
@@ -227,27 +262,36 @@ __device__ __forceinline__ double qd_candidate(const QdK& k, bool run, const dou
 #pragma unroll
           for (int i = 0; i < 3; ++i) acc[i] = fma((double)gf[kM + j * kN + 3 * q + i], dx[3 * q + i], acc[i]);
         const double kd = (acc[0] + acc[1]) + acc[2];
-        uh[j] = fma(alpha, (double)gf[j] + kd, un[j]);        // alpha scales the feedback term too (:382-383)
+        const double un = st.xu[buf][kN + j][lane];
+        // alpha scales the feedback term too (:382-383); alpha = 0 is the nominal itself, whatever the gains hold
+        uh[j] = (alpha != 0.0) ? fma(alpha, (double)gf[j] + kd, un) : un;
       }
     }
-    // nominal and gains of this step are consumed: the loads of the next step fly during the rest of this one
-    if (run && t + 1 < N) fetch();
-    if (run) {
+    // Nominal and gains of this step are consumed - u_hat depends on every staged value, so once it exists all reads
+    // of the buffer have returned - and it is refilled with step t + 2: the copies have almost two steps to land.
+    asm volatile("" ::"d"(uh[0]), "d"(uh[1]), "d"(uh[2]), "d"(uh[3]) : "memory");
+    fetch(buf, run && t + 2 < N);
+    if (STORE) {
+      if (run) {
 #pragma unroll
-      for (int j = 0; j < kM; ++j) uo[(size_t)j * sO] = uh[j];
+        for (int j = 0; j < kM; ++j) uo[(size_t)j * sO] = uh[j];
 #pragma unroll
-      for (int i = 0; i < kN; ++i) xo[(size_t)i * sO] = xh[i];
+        for (int i = 0; i < kN; ++i) xo[(size_t)i * sO] = xh[i];
+      }
+      uo += kM * sO;
+      xo += kN * sO;
     }
-    uo += kM * sO;
-    xo += kN * sO;
     qd_running(xh, uh, k, c);
     qd_step<INTEG>(xh, uh, k);
     run = run && !(qd_total(c) > limit);
     if (!run) { xh[6] = 0.0; xh[7] = 0.0; xh[8] = 0.0; }      // a dead lane never sends the warp into the slow sincos
   }
+  cp_async_wait<0>();
   if (run) {
+    if (STORE) {
 #pragma unroll
-    for (int i = 0; i < kN; ++i) xo[(size_t)i * sO] = xh[i];
+      for (int i = 0; i < kN; ++i) xo[(size_t)i * sO] = xh[i];
+    }
     qd_final(xh, k, c);
   }
   return qd_total(c);
@@ -268,35 +312,30 @@ __device__ __forceinline__ void qd_ordered_append(bool flag, int value, int32_t*
 
 // Workspace of the staged search (device memory, qx_linesearch_workspace_bytes()).
 struct QdWork {
-  int32_t* ctl;        // [0] = |queue1|, [1] = |queue2|
-  int32_t *queue1, *queue2, *pend1, *pend2;
+  int32_t* ctl;        // [0] = |queue|
+  int32_t *queue, *pend, *mirror;
   double* cur;         // cost of the nominal, snapshot taken by phase A
   double* cand;        // [5][B] candidate costs, plane = alpha index - 1
-  double *xs, *us;     // [5][(N+1) n][B], [5][N m][B]
 };
 
 __host__ __device__ inline size_t qd_align16(size_t v) { return (v + 15) / 16 * 16; }
 
 size_t qd_workspace_bytes(int B, int N) {
-  constexpr size_t n = 12, m = 4, A = QX_NUM_ALPHA - 1;
-  return 32 + 4 * qd_align16((size_t)B * 4) + (size_t)B * 8 + A * (size_t)B * 8 +
-         A * ((size_t)(N + 1) * n + (size_t)N * m) * (size_t)B * 8;
+  (void)N;
+  constexpr size_t A = QX_NUM_ALPHA - 1;
+  return 32 + 3 * qd_align16((size_t)B * 4) + (size_t)B * 8 + A * (size_t)B * 8;
 }
 
-static QdWork qd_carve(void* workspace, int B, int N) {
-  constexpr size_t n = 12, m = 4, A = QX_NUM_ALPHA - 1;
+static QdWork qd_carve(void* workspace, int B) {
   uint8_t* w = static_cast<uint8_t*>(workspace);
   const size_t qb = qd_align16((size_t)B * 4);
   QdWork k;
   k.ctl = reinterpret_cast<int32_t*>(w);
-  k.queue1 = reinterpret_cast<int32_t*>(w + 32);
-  k.queue2 = reinterpret_cast<int32_t*>(w + 32 + qb);
-  k.pend1 = reinterpret_cast<int32_t*>(w + 32 + 2 * qb);
-  k.pend2 = reinterpret_cast<int32_t*>(w + 32 + 3 * qb);
-  k.cur = reinterpret_cast<double*>(w + 32 + 4 * qb);
+  k.queue = reinterpret_cast<int32_t*>(w + 32);
+  k.pend = reinterpret_cast<int32_t*>(w + 32 + qb);
+  k.mirror = reinterpret_cast<int32_t*>(w + 32 + 2 * qb);
+  k.cur = reinterpret_cast<double*>(w + 32 + 3 * qb);
   k.cand = k.cur + B;
-  k.xs = k.cand + A * B;
-  k.us = k.xs + A * (size_t)(N + 1) * n * B;
   return k;
 }
 
@@ -336,25 +375,46 @@ rollout_qd_kernel(const __grid_constant__ QdK k, const double* __restrict__ x0, 
   cost[b] = qd_total(c);
 }
 
-// Bookkeeping after the line search of one trajectory (stopping rule :472).  Leaves the next iterate in
-// (x_out,u_out); a finished trajectory has it in both buffers.  Returns "still active".
+// Bookkeeping after the line search of one trajectory (stopping rule :472).  The next iterate must end up in
+// (x_out,u_out), and a finished trajectory keeps its final iterate in both buffers.  Returns "still active".
+// INLINE_COPY (single-launch search): the copies that this takes - the nominal into (x_out,u_out) when no alpha was
+// accepted, the final iterate back into (x_in,u_in) - are made here, by the trajectory's own thread.  Otherwise only
+// *mirror is set (1: copy out -> in) and ls_qd_mirror_kernel does it with the whole machine; a trajectory without an
+// accepted alpha has already been given its nominal by phase W (alpha = 0 rollout).
+template <bool INLINE_COPY>
 __device__ __forceinline__ bool qd_finalize(int b, int idx, double cur, double new_cost, double tol, uint32_t flags,
                                             double* __restrict__ x_in, double* __restrict__ u_in,
                                             double* __restrict__ x_out, double* __restrict__ u_out,
                                             double* __restrict__ cost, int32_t* __restrict__ status,
-                                            int32_t* __restrict__ iters, int32_t* __restrict__ alpha_out, int B, int N) {
+                                            int32_t* __restrict__ iters, int32_t* __restrict__ alpha_out,
+                                            int32_t* __restrict__ mirror, int B, int N) {
   const bool found = idx >= 0;
   bool done = (!found) || (fabs(cur - new_cost) < tol);
   if (flags & QX_LS_FORCE_ACTIVE) done = false;
-  if (!found || done) {
-    // no alpha: (x_out,u_out) <- nominal;  finished with an update: (x_in,u_in) <- final iterate
-    const double* xs = found ? x_out : x_in;
-    const double* us = found ? u_out : u_in;
-    double* xd = found ? x_in : x_out;
-    double* ud = found ? u_in : u_out;
-    const int xrows = (N + 1) * kN, urows = N * kM;
-    for (int r = 0; r < xrows; ++r) xd[(size_t)r * B + b] = xs[(size_t)r * B + b];
-    for (int r = 0; r < urows; ++r) ud[(size_t)r * B + b] = us[(size_t)r * B + b];
+  if (INLINE_COPY) {
+    if (!found || done) {
+      // no alpha: (x_out,u_out) <- nominal;  finished with an update: (x_in,u_in) <- final iterate
+      const double* xs = found ? x_out : x_in;
+      const double* us = found ? u_out : u_in;
+      double* xd = found ? x_in : x_out;
+      double* ud = found ? u_in : u_out;
+      const int xrows = (N + 1) * kN, rows = xrows + N * kM;
+      constexpr int U = 8;                      // loads batched eight deep: the copy is latency-bound
+      for (int r = 0; r < rows; r += U) {
+        double v[U];
+#pragma unroll
+        for (int q = 0; q < U; ++q)
+          if (r + q < rows) v[q] = (r + q < xrows) ? xs[(size_t)(r + q) * B + b] : us[(size_t)(r + q - xrows) * B + b];
+#pragma unroll
+        for (int q = 0; q < U; ++q)
+          if (r + q < rows) {
+            if (r + q < xrows) xd[(size_t)(r + q) * B + b] = v[q];
+            else ud[(size_t)(r + q - xrows) * B + b] = v[q];
+          }
+      }
+    }
+  } else {
+    *mirror = (found && done) ? 1 : 0;
   }
   cost[b] = new_cost;
   alpha_out[b] = idx;
@@ -366,17 +426,18 @@ __device__ __forceinline__ bool qd_finalize(int b, int idx, double cur, double n
 // MODE 0: the whole alpha list sequentially with early exit (single launch, no workspace).
 // MODE 1: phase A of the staged search: alpha = 1 only; rejected trajectories are queued.
 template <int MODE, int INTEG>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, 8)
 ls_qd_phaseA_kernel(const __grid_constant__ QdK k, double* __restrict__ x_in, double* __restrict__ u_in,
                     const float* __restrict__ gains, double* __restrict__ cost, int32_t* __restrict__ status,
                     int32_t* __restrict__ iters, int32_t* __restrict__ alpha_out, double* __restrict__ x_out,
                     double* __restrict__ u_out, int32_t* __restrict__ n_active, QdWork ws, double tol, uint32_t flags,
                     int B, int N) {
+  __shared__ QdStage stage;
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const bool mine = (b < B) && (status[b] == 0);
   if (!__any_sync(FULL, mine)) {
-    if (MODE == 1 && b < B) ws.pend1[b] = 0;
+    if (MODE == 1 && b < B) { ws.pend[b] = 0; ws.mirror[b] = 0; }
     return;
   }
   const int bs = mine ? b : 0;
@@ -389,7 +450,7 @@ ls_qd_phaseA_kernel(const __grid_constant__ QdK k, double* __restrict__ x_in, do
   for (int a = 0; a < n_alpha; ++a) {
     if (!__any_sync(FULL, !accepted)) break;
     const bool run = !accepted;
-    const double cst = qd_candidate<INTEG>(k, run, x_in + bs, u_in + bs, reinterpret_cast<const float4*>(gains) + bs,
+    const double cst = qd_candidate<INTEG, true>(k, stage, run, x_in + bs, u_in + bs, reinterpret_cast<const float4*>(gains) + bs,
                                            (size_t)B, kAlphas[a], limit, x_out + bs, u_out + bs, (size_t)B, N);
     if (run && cst <= cur) {       // first accepted alpha, "<=" (quattro_ilqr_tf.py:444)
       accepted = true;
@@ -399,139 +460,129 @@ ls_qd_phaseA_kernel(const __grid_constant__ QdK k, double* __restrict__ x_in, do
   }
   bool still_active = false;
   const bool pending = (MODE == 1) && mine && idx < 0;
+  int mir = 0;
   if (mine && !pending)
-    still_active = qd_finalize(b, idx, cur, new_cost, tol, flags, x_in, u_in, x_out, u_out, cost, status, iters, alpha_out,
-                               B, N);
+    still_active = qd_finalize<MODE == 0>(b, idx, cur, new_cost, tol, flags, x_in, u_in, x_out, u_out, cost, status, iters,
+                                          alpha_out, &mir, B, N);
   if (MODE == 1) {
     if (b < B) {
-      ws.pend1[b] = pending ? 1 : 0;
+      ws.pend[b] = pending ? 1 : 0;
+      ws.mirror[b] = mir;
       if (pending) ws.cur[b] = cur;
     }
-    qd_ordered_append(pending, b, ws.queue1, &ws.ctl[0]);
+    qd_ordered_append(pending, b, ws.queue, &ws.ctl[0]);
   }
   const unsigned act = __ballot_sync(FULL, still_active);
   if (lane == 0 && n_active != nullptr && act != 0u) atomicAdd(n_active, __popc(act));
 }
 
-// Phase B: one thread per (queued trajectory, alpha of the stage); blockIdx.y selects the alpha, so the warps of
-// the NA candidates of a trajectory read the same nominal and gain lines (L2 hits) and stay coalesced.
+// Phase B: one thread per (queued trajectory, alpha in {.5, .25, .1, .05, .01}), COSTS ONLY.  The alpha is the fast
+// grid index, so the five candidates of the same 32 trajectories are dispatched together and meet their nominal and
+// gain lines in L2.  (Parking the five candidates in HBM and copying the winner out made this stage HBM-bound:
+// 1.4 GB per launch at 16 384 trajectories, profiles/r2_*; the winner is re-rolled instead, by phase W.)
 template <int INTEG>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, 8)
 ls_qd_phaseB_kernel(const __grid_constant__ QdK k, const double* __restrict__ x_in, const double* __restrict__ u_in,
-                    const float* __restrict__ gains, const int32_t* __restrict__ queue, const int32_t* __restrict__ nq_ptr,
-                    QdWork ws, int a_first, int B, int N) {
-  const int nq = *nq_ptr;
-  if ((int)(blockIdx.x * blockDim.x) >= nq) return;
-  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+                    const float* __restrict__ gains, QdWork ws, int B, int N) {
+  constexpr int NA = QX_NUM_ALPHA - 1;
+  __shared__ QdStage stage;
+  const int nq = ws.ctl[0];
+  const int qb = blockIdx.x / NA;
+  if (qb * 32 >= nq) return;
+  const int item = qb * 32 + threadIdx.x;
   const bool run = item < nq;
-  const int b = run ? queue[item] : 0;
-  const int a = a_first + blockIdx.y, plane = a - 1;
+  const int b = run ? ws.queue[item] : 0;
+  const int a = 1 + (int)(blockIdx.x % NA);
   const double cur = ws.cur[b];
   const double limit = k.early ? cur : __longlong_as_double(0x7ff0000000000000LL);
-  double* xd = ws.xs + (size_t)plane * (N + 1) * kN * B + b;
-  double* ud = ws.us + (size_t)plane * N * kM * B + b;
-  const double cst = qd_candidate<INTEG>(k, run, x_in + b, u_in + b, reinterpret_cast<const float4*>(gains) + b, (size_t)B,
-                                         kAlphas[a], limit, xd, ud, (size_t)B, N);
-  if (run) ws.cand[(size_t)plane * B + b] = cst;
+  const double cst = qd_candidate<INTEG, false>(k, stage, run, x_in + b, u_in + b, reinterpret_cast<const float4*>(gains) + b,
+                                                (size_t)B, kAlphas[a], limit, nullptr, nullptr, 0, N);
+  if (run) ws.cand[(size_t)(a - 1) * B + b] = cst;
 }
 
-// Phase C: one thread per trajectory (coalesced rows).  A pending trajectory takes the first accepted alpha of
-// the stage: its candidate is copied out of the scratch and the stopping rule applied; otherwise it is queued
-// for the next stage, or (FINAL) keeps its nominal and finishes.  blockIdx.y splits the rows of the copy;
-// slice 0 does the bookkeeping.
-template <bool FINAL>
-__global__ void __launch_bounds__(128)
-ls_qd_phaseC_kernel(double* __restrict__ x_in, double* __restrict__ u_in, double* __restrict__ cost,
-                    int32_t* __restrict__ status, int32_t* __restrict__ iters, int32_t* __restrict__ alpha_out,
-                    double* __restrict__ x_out, double* __restrict__ u_out, int32_t* __restrict__ n_active, QdWork ws,
-                    const int32_t* __restrict__ pend_in, int32_t* __restrict__ pend_out, int32_t* __restrict__ queue_out,
-                    int32_t* __restrict__ nq_out, int a_first, int n_alpha, double tol, uint32_t flags, int B, int N) {
-  constexpr int n = 12, m = 4;
+// Phase W: one thread per trajectory.  A pending trajectory takes the first alpha of the stage whose cost passed the
+// test (:440-451) and rolls that candidate out again, this time straight into (x_out, u_out) - the same arithmetic
+// as the probe, so the same cost - then the stopping rule.  Without an accepted alpha it keeps its nominal (:447-451):
+// its thread rolls out alpha = 0, which reproduces the nominal bit for bit (u_hat = u, and x is the rollout of u by
+// this very code), so (x_out, u_out) receive it without a separate copy pass.
+template <int INTEG>
+__global__ void __launch_bounds__(32, 8)
+ls_qd_phaseW_kernel(const __grid_constant__ QdK k, double* __restrict__ x_in, double* __restrict__ u_in,
+                    const float* __restrict__ gains, double* __restrict__ cost, int32_t* __restrict__ status,
+                    int32_t* __restrict__ iters, int32_t* __restrict__ alpha_out, double* __restrict__ x_out,
+                    double* __restrict__ u_out, int32_t* __restrict__ n_active, QdWork ws, double tol, uint32_t flags,
+                    int B, int N) {
+  constexpr int NA = QX_NUM_ALPHA - 1;
+  __shared__ QdStage stage;
+  const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool mine = (b < B) && (pend_in[b] != 0);
-  const bool book = blockIdx.y == 0;
+  const bool mine = (b < B) && (ws.pend[b] != 0);
+  if (!__any_sync(FULL, mine)) return;
+  const int bs = mine ? b : 0;
+  const double cur = mine ? ws.cur[b] : 0.0;
   int idx = -1;
-  double cur = 0.0, new_cost = 0.0;
-  bool done = false;
+  double alpha = 0.0, new_cost = cur;
   if (mine) {
-    cur = ws.cur[b];
-    new_cost = cur;
-    for (int a = 0; a < n_alpha; ++a) {
-      const double cc = ws.cand[(size_t)(a_first + a - 1) * B + b];
-      if (cc <= cur) { idx = a_first + a; new_cost = cc; break; }
-    }
-    const bool found = idx >= 0;
-    done = ((!found) || (fabs(cur - new_cost) < tol)) && !(flags & QX_LS_FORCE_ACTIVE);
-    // rows [r0, r1) of the concatenated [x rows | u rows] space belong to this slice
-    const int xrows = (N + 1) * n, rows = xrows + N * m;
-    const int per = (rows + (int)gridDim.y - 1) / (int)gridDim.y;
-    const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
-    // one source / up to two destinations per row, loads batched eight deep to keep HBM busy
-    const double* xsrc = nullptr;
-    const double* usrc = nullptr;
-    double *xd0 = nullptr, *ud0 = nullptr, *xd1 = nullptr, *ud1 = nullptr;
-    if (found) {
-      xsrc = ws.xs + (size_t)(idx - 1) * xrows * B;
-      usrc = ws.us + (size_t)(idx - 1) * (N * m) * B;
-      xd0 = x_out; ud0 = u_out;
-      if (done) { xd1 = x_in; ud1 = u_in; }     // finished: the final iterate also goes to the other buffer
-    } else if (FINAL) {                          // no alpha accepted: keep the nominal
-      xsrc = x_in; usrc = u_in;
-      xd0 = x_out; ud0 = u_out;
-    }
-    if (xsrc != nullptr) {
-      constexpr int U = 8;
-      for (int r = r0; r < r1; r += U) {
-        double v[U];
 #pragma unroll
-        for (int q = 0; q < U; ++q) {
-          const int rr = r + q;
-          if (rr < r1) v[q] = (rr < xrows) ? xsrc[(size_t)rr * B + b] : usrc[(size_t)(rr - xrows) * B + b];
-        }
-#pragma unroll
-        for (int q = 0; q < U; ++q) {
-          const int rr = r + q;
-          if (rr < r1) {
-            if (rr < xrows) {
-              xd0[(size_t)rr * B + b] = v[q];
-              if (xd1 != nullptr) xd1[(size_t)rr * B + b] = v[q];
-            } else {
-              ud0[(size_t)(rr - xrows) * B + b] = v[q];
-              if (ud1 != nullptr) ud1[(size_t)(rr - xrows) * B + b] = v[q];
-            }
-          }
-        }
+    for (int a = NA; a >= 1; --a) {
+      const double cc = ws.cand[(size_t)(a - 1) * B + b];
+      if (cc <= cur) {                     // the FIRST accepted alpha, "<=" (quattro_ilqr_tf.py:444)
+        idx = a;
+        alpha = kAlphas[a];
+        new_cost = cc;
       }
     }
   }
-  if (!book) return;
-  const bool settle = mine && (idx >= 0 || FINAL);
-  const bool requeue = mine && !settle;
-  if (settle) {
-    cost[b] = new_cost;
-    alpha_out[b] = idx;
-    iters[b] += 1;
-    if (done) status[b] = 1;
+  qd_candidate<INTEG, true>(k, stage, mine, x_in + bs, u_in + bs, reinterpret_cast<const float4*>(gains) + bs, (size_t)B, alpha,
+                            __longlong_as_double(0x7ff0000000000000LL), x_out + bs, u_out + bs, (size_t)B, N);
+  bool still_active = false;
+  if (mine) {
+    int mir = 0;
+    still_active = qd_finalize<false>(b, idx, cur, new_cost, tol, flags, x_in, u_in, x_out, u_out, cost, status, iters,
+                                      alpha_out, &mir, B, N);
+    ws.mirror[b] = mir;
   }
-  if (!FINAL) {
-    if (b < B) pend_out[b] = requeue ? 1 : 0;
-    qd_ordered_append(requeue, b, queue_out, nq_out);
+  const unsigned act = __ballot_sync(FULL, still_active);
+  if (lane == 0 && n_active != nullptr && act != 0u) atomicAdd(n_active, __popc(act));
+}
+
+// The final iterate of the trajectories that finished in this line search, copied (x_out,u_out) -> (x_in,u_in) so
+// that both buffers hold it: thread per trajectory (coalesced rows), blockIdx.y splits the rows, loads batched.
+__global__ void __launch_bounds__(128)
+ls_qd_mirror_kernel(double* __restrict__ x_in, double* __restrict__ u_in, const double* __restrict__ x_out,
+                    const double* __restrict__ u_out, const int32_t* __restrict__ mirror, int B, int N) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B || mirror[b] == 0) return;
+  const int xrows = (N + 1) * kN, rows = xrows + N * kM;
+  const int per = (rows + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+  constexpr int U = 8;
+  for (int r = r0; r < r1; r += U) {
+    double v[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q)
+      if (r + q < r1) v[q] = (r + q < xrows) ? x_out[(size_t)(r + q) * B + b] : u_out[(size_t)(r + q - xrows) * B + b];
+#pragma unroll
+    for (int q = 0; q < U; ++q)
+      if (r + q < r1) {
+        if (r + q < xrows) x_in[(size_t)(r + q) * B + b] = v[q];
+        else u_in[(size_t)(r + q - xrows) * B + b] = v[q];
+      }
   }
-  const unsigned act = __ballot_sync(FULL, settle && !done);
-  if ((threadIdx.x & 31) == 0 && n_active != nullptr && act != 0u) atomicAdd(n_active, __popc(act));
 }
 
 // forward_pass with a caller-chosen alpha (quattro_ilqr_tf.py:377-390): the same candidate arithmetic as the
 // line search, so qx_forward_pass(alpha) reproduces the candidate the search evaluated bit for bit
 template <int INTEG>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, 8)
 forward_pass_qd_kernel(const __grid_constant__ QdK k, const double* __restrict__ x_in, const double* __restrict__ u_in,
                        const float* __restrict__ gains, double alpha, double* __restrict__ x_out, double* __restrict__ u_out,
                        double* __restrict__ cost_out, int B, int N) {
+  __shared__ QdStage stage;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const bool run = b < B;
   const int bs = run ? b : 0;
-  const double cst = qd_candidate<INTEG>(k, run, x_in + bs, u_in + bs, reinterpret_cast<const float4*>(gains) + bs, (size_t)B,
+  const double cst = qd_candidate<INTEG, true>(k, stage, run, x_in + bs, u_in + bs, reinterpret_cast<const float4*>(gains) + bs, (size_t)B,
                                          alpha, __longlong_as_double(0x7ff0000000000000LL), x_out + bs, u_out + bs,
                                          (size_t)B, N);
   if (run) cost_out[b] = cst;
@@ -575,25 +626,21 @@ static int qd_linesearch_t(const QxParams* p, double* x_in, double* u_in, const 
     return QX_OK;
   }
   QX_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, "workspace must be 16-byte aligned");
-  const QdWork ws = qd_carve(workspace, B, N);
+  const QdWork ws = qd_carve(workspace, B);
   cudaError_t e = cudaMemsetAsync(ws.ctl, 0, 32, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(ctl)");
   ls_qd_phaseA_kernel<1, INTEG><<<grid, 32, 0, st>>>(k, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out,
                                                      n_active, ws, tol, flags, B, N);
   QX_CHECK_LAUNCH("ls_qd_phaseA_kernel<1>");
-  const dim3 gridC(ceil_div(B, 128), 16);
-  // stage 1: alpha = .5, .25
-  ls_qd_phaseB_kernel<INTEG><<<dim3(grid, 2), 32, 0, st>>>(k, x_in, u_in, gains, ws.queue1, &ws.ctl[0], ws, 1, B, N);
-  QX_CHECK_LAUNCH("ls_qd_phaseB_kernel<1>");
-  ls_qd_phaseC_kernel<false><<<gridC, 128, 0, st>>>(x_in, u_in, cost, status, iters, alpha, x_out, u_out, n_active, ws,
-                                                    ws.pend1, ws.pend2, ws.queue2, &ws.ctl[1], 1, 2, tol, flags, B, N);
-  QX_CHECK_LAUNCH("ls_qd_phaseC_kernel<false>");
-  // stage 2: alpha = .1, .05, .01
-  ls_qd_phaseB_kernel<INTEG><<<dim3(grid, 3), 32, 0, st>>>(k, x_in, u_in, gains, ws.queue2, &ws.ctl[1], ws, 3, B, N);
-  QX_CHECK_LAUNCH("ls_qd_phaseB_kernel<2>");
-  ls_qd_phaseC_kernel<true><<<gridC, 128, 0, st>>>(x_in, u_in, cost, status, iters, alpha, x_out, u_out, n_active, ws,
-                                                   ws.pend2, nullptr, nullptr, nullptr, 3, 3, tol, flags, B, N);
-  QX_CHECK_LAUNCH("ls_qd_phaseC_kernel<true>");
+  ls_qd_phaseB_kernel<INTEG><<<grid * (QX_NUM_ALPHA - 1), 32, 0, st>>>(k, x_in, u_in, gains, ws, B, N);
+  QX_CHECK_LAUNCH("ls_qd_phaseB_kernel");
+  ls_qd_phaseW_kernel<INTEG><<<grid, 32, 0, st>>>(k, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out, n_active, ws,
+                                                  tol, flags, B, N);
+  QX_CHECK_LAUNCH("ls_qd_phaseW_kernel");
+  if (!(flags & QX_LS_FORCE_ACTIVE)) {      // forced mode never finishes a trajectory: nothing to mirror
+    ls_qd_mirror_kernel<<<dim3(ceil_div(B, 128), 16), 128, 0, st>>>(x_in, u_in, x_out, u_out, ws.mirror, B, N);
+    QX_CHECK_LAUNCH("ls_qd_mirror_kernel");
+  }
   return QX_OK;
 }
 

@@ -56,7 +56,7 @@ class BatchedILQR:
         self.exp_layout = None
         self.expansion = self.terminal = None
         self.gains = torch.zeros(self.lib.qx_gains_bytes(mid, B, N) // 4, dtype=f32, device=dev)
-        # scratch of the two-phase line search (quadrotor): candidates of the 5 smaller alphas
+        # scratch of the staged line search: queue, flags and candidate costs (quadrotor), winner hints (cart-pole)
         ws = self.lib.qx_linesearch_workspace_bytes(mid, B, N)
         self.ls_workspace = torch.empty(ws, dtype=torch.uint8, device=dev) if (ws and two_phase_linesearch) else None
         self.cur = 0
@@ -137,11 +137,12 @@ class BatchedILQR:
                                           _ptr(self.ls_workspace), float(tol),
                                           _lib.QX_LS_FORCE_ACTIVE if force else 0, self.B, self.N, self.stream),
                    "qx_linesearch")
-        # the staged search of the quadrotor (diagonal weights, workspace given) is five kernels: A, B1, C1, B2, C2
+        # the staged search of the quadrotor (diagonal weights, workspace given) is three kernels: A, B, W,
+        # plus the mirror copy of the finished trajectories when trajectories may finish (not forced)
         # the cart-pole with a workspace is two: the six alphas side by side, then the winners that are not alpha = 1
         staged = self.ls_workspace is not None and self.model.model_id == _lib.QX_MODEL_QUADROTOR and self.params.diag_cost
         par = self.ls_workspace is not None and self.model.model_id == _lib.QX_MODEL_CARTPOLE
-        self.launches += 5 if staged else (2 if par else 1)
+        self.launches += (3 if force else 4) if staged else (2 if par else 1)
         self.cur = 1 - c
 
     def forward_pass(self, alpha):
