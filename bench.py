@@ -82,8 +82,8 @@ def tensor_peak():
 def ncu_reference(kernel, blk, system):
     """DRAM traffic and pipe utilisation of the dominant kernel from the committed `ncu --set full` summary of the
     same workload (profiles/): counters cannot be read live, the launch duration is (CUDA events, above)."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_full_classic_summary.txt")
-    sym = {("riccati", True): "riccati_quad_blk_kernel", ("linearize", True): "linearize_quad_blk_kernel"}.get((kernel, blk))
+    path = os.path.join(ROOT, "profiles", "r2_ncu_full_classic_summary.txt")
+    sym = {("riccati", True): "riccati_quad_thr_kernel", ("linearize", True): "linearize_quad_blk_kernel"}.get((kernel, blk))
     if system != "quadrotor" or sym is None or not os.path.exists(path):
         return None
     vals, inside = {}, False
@@ -106,7 +106,7 @@ def ncu_reference(kernel, blk, system):
     def byt(k):
         v, u = vals[k]
         return v * scale.get(u, 1.0)
-    return {"source": "profiles/r1_ncu_full_classic_summary.txt", "traffic": byt("dram__bytes_read.sum") + byt("dram__bytes_write.sum"),
+    return {"source": "profiles/r2_ncu_full_classic_summary.txt", "traffic": byt("dram__bytes_read.sum") + byt("dram__bytes_write.sum"),
             "fma_pipe_pct": vals.get("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", (None,))[0],
             "issue_active_pct": vals.get("smsp__issue_active.avg.pct_of_peak_sustained_active", (None,))[0],
             "dram_pct": vals.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", (None,))[0]}
@@ -426,7 +426,7 @@ def gpu_bench(args):
             dist.destroy_process_group()
         return
     # dominant KERNEL = the longest single launch: linearise and Riccati are one launch each, the line search is
-    # five (stages A, B1, C1, B2, C2; 0.04-0.2 ms each), so it is reported in `kernels` but is not "a kernel"
+    # three (stages A, B, W: a rollout each), so it is reported in `kernels` but is not "a kernel"
     single = [k for k in kernels if "GBps" in kernels[k] and k != "linesearch"] or [k for k in kernels if "GBps" in kernels[k]]
     dom = max(single, key=lambda k: kernels[k]["ms"])
     hbm, how = peaks()
@@ -451,8 +451,9 @@ def gpu_bench(args):
     if ncu and not use_tf:
         roofline["ncu"] = ncu
     if dom == "riccati" and not use_tf:
-        roofline["note"] = ("the recursion is bound by fp32 instruction issue / the FMA pipe, not by HBM (SURVEY 8d asks for "
-                            "both figures): see ncu.fma_pipe_pct and ncu.issue_active_pct")
+        roofline["note"] = ("one thread per trajectory, 50 dependent steps: at 16 384 trajectories there is one warp per scheduler "
+                            "and the kernel runs at its fp32 latency floor (SURVEY 8d asks for both figures: ncu.fma_pipe_pct, "
+                            "ncu.issue_active_pct); from 32 768 trajectories on it is HBM-bound")
     if world == 1:      # the CPU leg runs at N = 1 only (at N > 1 the other ranks' host threads share the cores)
         cpu_val, cores, _, sample = cpu_reference(system, steps=2, warmup=1, iters_per_step=2)
         cpu_baseline = {"value": cpu_val, "unit": "trajectory-iterations/s", "cores": cores, "kind": "port", "sample": sample}
@@ -469,8 +470,8 @@ def gpu_bench(args):
                    "global_batch": world * B, "parallelism": f"dp{world} (independent trajectory shards)",
                    "backward_pass": "block records (64 floats per step)" if eng.exp_layout == 2 else "dense records",
                    "launch": "two iterations per CUDA-graph replay" if (tf is None and args.graph) else "one launch per kernel",
-                   "l2": "working set per iteration (x, u ping-pong 0.21 GB + expansion 0.21 GB + gains 0.17 GB + "
-                         "line-search scratch up to 0.53 GB at 16 384 trajectories) larger than the 126 MB L2"},
+                   "l2": "working set per iteration (x, u ping-pong 0.21 GB + expansion 0.21 GB + gains 0.17 GB at 16 384 "
+                         "trajectories) larger than the 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "trajectory-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "pipeline": f"{chunks} slices on {chunks} streams, consecutive batches overlap" if chunks > 1 else "single stream",
                 "host_numa_bound": numa_bound},

@@ -47,6 +47,21 @@ struct Rec {
 
 __host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// One-time launch setup (cudaFuncSetAttribute, SM count) is PER DEVICE and a process may drive several: the caches
+// that remember it are arrays indexed by the current device.
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d < 0 || d >= kMaxDevices) ? 0 : d;
+}
+inline int device_sm_count() {
+  static int sms[kMaxDevices] = {};
+  const int d = current_device_slot();
+  if (sms[d] == 0) cudaDeviceGetAttribute(&sms[d], cudaDevAttrMultiProcessorCount, d);
+  return sms[d];
+}
+
 // Gains are stored with the trajectory index fastest, so that a warp of consecutive trajectories touches whole lines:
 //   QX_LAYOUT_SOA (cart-pole)  float  [N][G][B]
 //   QX_LAYOUT_REC (quadrotor)  float4 [N][G/4][B]   G = 52: float4 #0 = k, #1..#12 = K row-major, four entries each

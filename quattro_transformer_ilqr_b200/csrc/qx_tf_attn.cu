@@ -169,10 +169,10 @@ int tf_attention_tc(const float* qkv, float* out, int B, int L, int d, int nhead
   if (d != nhead * kHd || L > 8 * kMaxKt || L < 1) return QX_EUNSUPPORTED;
   const int Lp = (L + 7) & ~7, nq = (L + 15) >> 4;
   const size_t smem = (size_t)2 * Lp * kPitch * sizeof(float);
-  static bool cfg = false;
-  if (!cfg) {
+  static bool cfg[kMaxDevices] = {};
+  if (!cfg[current_device_slot()]) {
     cudaFuncSetAttribute(tf_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * kMaxKt * kPitch * 4);
-    cfg = true;
+    cfg[current_device_slot()] = true;
   }
   tf_attention_mma_kernel<<<dim3(nhead, B), 32 * ((nq + 1) / 2), smem, st>>>(qkv, out, L, d);
   QX_CHECK_LAUNCH("tf_attention_mma_kernel");

@@ -550,16 +550,13 @@ int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhe
     const int rc = make_map_nd(&mo, out, 3, dims, strides, box);
     if (rc) return rc;
   }
-  static bool cfg = false;
-  static int num_sms = 0;
-  if (!cfg) {
+  static bool cfg[kMaxDevices] = {};
+  if (!cfg[current_device_slot()]) {
     cudaFuncSetAttribute(tf_attention_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmem));
     cudaFuncSetAttribute(tf_attention_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmem));
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cfg = true;
+    cfg[current_device_slot()] = true;
   }
+  const int num_sms = device_sm_count();
   const int n_items = (pair ? (B + 1) / 2 : B) * nhead;
   // QX_TF_ATTN_DBG (timing experiments only, results are then wrong on purpose): bit 1 no P V MMAs, bit 2 no softmax
   const char* env_dbg = getenv("QX_TF_ATTN_DBG");

@@ -408,13 +408,7 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
   dim3 ge(L, B);
   const bool per_traj = (d == 128) && lay.n <= QX_MAX_N && lay.c <= 64 && cfg->horizon + 1 <= 128;
   if (per_traj) {
-    static int embed_ctas = 0;
-    if (embed_ctas == 0) {
-      int dev = 0, sms = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      embed_ctas = 5 * sms;          // 45 KB of shared memory per CTA: five fit an SM
-    }
+    const int embed_ctas = 5 * device_sm_count();          // 45 KB of shared memory per CTA: five fit an SM
     const int ge128 = B < embed_ctas ? B : embed_ctas;
     if (layout == QX_LAYOUT_REC) tf_embed128_kernel<QX_LAYOUT_REC><<<ge128, 128, 0, st>>>(*cfg, w, x, x_shift, gains, h, B);
     else tf_embed128_kernel<QX_LAYOUT_SOA><<<ge128, 128, 0, st>>>(*cfg, w, x, x_shift, gains, h, B);
@@ -425,10 +419,10 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
   QX_CHECK_LAUNCH("tf_embed_kernel");
   const int hd = d / cfg->nhead;
   const size_t att_smem = (size_t)2 * L * hd * sizeof(float);
-  static bool att_cfg = false;
-  if (!att_cfg) {
+  static bool att_cfg[kMaxDevices] = {};
+  if (!att_cfg[current_device_slot()]) {
     cudaFuncSetAttribute(tf_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    att_cfg = true;
+    att_cfg[current_device_slot()] = true;
   }
   const SplitLayout sp(lay);
   // dense contraction: tcgen05 3xTF32 when split weights are supplied, exact-fp32 CUDA cores otherwise
@@ -629,10 +623,10 @@ extern "C" int qx_tf_attention(const float* qkv, float* out, int B, int L, int d
   if (impl == 0) return qx::tf_attention_umma(qkv, out, B, L, d, nhead, 0, st);
   if (impl == 1) return qx::tf_attention_tc(qkv, out, B, L, d, nhead, st);
   QX_CHECK_ARG(impl == 2, "impl must be 0, 1 or 2");
-  static bool att_cfg = false;
-  if (!att_cfg) {
+  static bool att_cfg[qx::kMaxDevices] = {};
+  if (!att_cfg[qx::current_device_slot()]) {
     cudaFuncSetAttribute(qx::tf_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    att_cfg = true;
+    att_cfg[qx::current_device_slot()] = true;
   }
   qx::tf_attention_kernel<32><<<dim3(nhead, B), 128, (size_t)2 * L * 32 * sizeof(float), st>>>(qkv, out, L, d);
   QX_CHECK_LAUNCH("tf_attention_kernel");

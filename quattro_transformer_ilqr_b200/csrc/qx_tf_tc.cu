@@ -593,18 +593,14 @@ int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* 
   CUtensorMap ma, mh, ml;
   int rc;
   if ((rc = make_map(&ma, A, M, K)) || (rc = make_map(&mh, Whi, N, K)) || (rc = make_map(&ml, Wlo, N, K))) return rc;
-  static bool configured = false;
-  if (!configured) {
+  const int dslot = current_device_slot();
+  static bool configured[kMaxDevices] = {};
+  if (!configured[dslot]) {
     cudaFuncSetAttribute(tf_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes);
     cudaFuncSetAttribute(tf_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes);
-    configured = true;
+    configured[dslot] = true;
   }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int num_sms = device_sm_count();
   // QX_TF_GEMM_STREAM=1: the first-generation streaming kernel (A/B measurements and the bitwise-equality test; read
   // per call).  QX_TF_GEMM_VARIANT=1: two splitter warp sets.  QX_TF_GEMM_DBG: timing experiments, see the kernel.
   const char* env_stream = getenv("QX_TF_GEMM_STREAM");
@@ -623,11 +619,11 @@ int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* 
     if ((rc = make_map(&mc, C, M, N, 32, 32))) return rc;
 #define QX_TA_LAUNCH(RELU_, STREAM_, SETS)                                                                              \
   do {                                                                                                                  \
-    static bool cfgd = false;                                                                                           \
-    if (!cfgd) {                                                                                                        \
+    static bool cfgd[kMaxDevices] = {};                                                                                 \
+    if (!cfgd[dslot]) {                                                                                                 \
       cudaFuncSetAttribute(tf_gemm_ta_kernel<RELU_, STREAM_, SETS>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                            (int)kTaSmemBytes);                                                                          \
-      cfgd = true;                                                                                                      \
+      cfgd[dslot] = true;                                                                                               \
     }                                                                                                                   \
     tf_gemm_ta_kernel<RELU_, STREAM_, SETS><<<grid, ta_threads(SETS), kTaSmemBytes, st>>>(ma, mh, ml, mc, bias, M, N, K, dbg, mc, LnArgs{}); \
   } while (0)
@@ -667,20 +663,15 @@ int tf_gemm_ln_tc(const float* A, const float* Whi, const float* Wlo, const floa
   if ((rc = make_map(&ma, A, M, K)) || (rc = make_map(&mh, Whi, N, K)) || (rc = make_map(&ml, Wlo, N, K)) ||
       (rc = make_map(&mc, C, M, N, 32, 32)) || (rc = make_map(&mr, res, M, N, 32, 32)))
     return rc;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int num_sms = device_sm_count();
   const int m_tiles = ceil_div(M, kBM);
   const int grid = num_sms < m_tiles ? num_sms : m_tiles;
   const LnArgs ln{gamma, beta};
-  static bool cfgd = false;
-  if (!cfgd) {
+  static bool cfgd[kMaxDevices] = {};
+  if (!cfgd[current_device_slot()]) {
     cudaFuncSetAttribute(tf_gemm_ta_kernel<false, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTaSmemBytes);
     cudaFuncSetAttribute(tf_gemm_ta_kernel<false, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTaSmemBytes);
-    cfgd = true;
+    cfgd[current_device_slot()] = true;
   }
   if (K != kTaW * kBK)
     tf_gemm_ta_kernel<false, true, 1, true><<<grid, ta_threads(1), kTaSmemBytes, st>>>(ma, mh, ml, mc, bias, M, N, K, 0, mr, ln);

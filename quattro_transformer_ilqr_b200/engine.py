@@ -16,6 +16,7 @@ Device layouts are documented in include/quattro_b200.h.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 
 import numpy as np
 import torch
@@ -28,6 +29,18 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+def _on_device(fn):
+    """Run a method with the engine's device current: kernels and cudaMemsetAsync are issued on a stream of
+    ``self.device``, which is an error if another device is current (the caller need not have called set_device)."""
+    @functools.wraps(fn)
+    def wrapper(self, *a, **kw):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *a, **kw)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **kw)
+    return wrapper
+
+
 class BatchedILQR:
     def __init__(self, model: DeviceModel, B: int, N: int, device=None, tf=None, two_phase_linesearch=True,
                  block_path=True):
@@ -37,6 +50,10 @@ class BatchedILQR:
         self.model, self.B, self.N = model, int(B), int(N)
         self.n, self.m = model.n, model.m
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise RuntimeError("quattro_transformer_ilqr_b200 needs a CUDA device (B200, sm_100a); no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device(f"cuda:{torch.cuda.current_device()}")
         self.tf = tf
         n, m, mid = self.n, self.m, model.model_id
         dev, f64, f32, i32 = self.device, torch.float64, torch.float32, torch.int32
@@ -82,11 +99,15 @@ class BatchedILQR:
             return
         self.exp_layout = layout
         self.expansion = self.terminal = None           # release before allocating the other layout
+        # captured graphs (iterate_pair) and the compaction sub-engines bake these buffers' addresses in
+        self.__dict__.pop("_pair_graphs", None)
+        self.__dict__.pop("_sub_engines", None)
         eb = self.lib.qx_blk_expansion_bytes(B, N) if blk else self.lib.qx_expansion_bytes(mid, B, N)
         tb = self.lib.qx_blk_terminal_bytes(B) if blk else self.lib.qx_terminal_bytes(mid, B)
         self.expansion = torch.zeros(eb // 4, dtype=torch.float32, device=self.device)
         self.terminal = torch.zeros(tb // 4, dtype=torch.float32, device=self.device)
 
+    @_on_device
     def set_problem(self, x0, u_init, rollout=True):
         """x0 (B, n), u_init (B, N, m): host arrays or tensors (any device); resets the solver state."""
         B, N, n, m = self.B, self.N, self.n, self.m
@@ -104,12 +125,14 @@ class BatchedILQR:
             self.rollout()
 
     # ------------------------------------------------------------------ kernels
+    @_on_device
     def rollout(self):
         c = self.cur
         _lib.check(self.lib.qx_rollout_cost(C.byref(self.params), _ptr(self.x0), _ptr(self.u[c]), _ptr(self.x[c]),
                                             _ptr(self.cost), None, self.B, self.N, self.stream), "qx_rollout_cost")
         self.launches += 1
 
+    @_on_device
     def linearize(self, t_start=0):
         c = self.cur
         fn = self.lib.qx_linearize_blk if self.exp_layout == _lib.QX_LAYOUT_BLK else self.lib.qx_linearize
@@ -117,6 +140,7 @@ class BatchedILQR:
                       _ptr(self.terminal), _ptr(self.status), self.B, self.N, t_start, self.stream), "qx_linearize")
         self.launches += 1
 
+    @_on_device
     def riccati(self, t_start=0, reg=1e-6):
         if self.exp_layout == _lib.QX_LAYOUT_BLK:
             _lib.check(self.lib.qx_riccati_blk(C.byref(self.params), _ptr(self.expansion), _ptr(self.terminal),
@@ -128,6 +152,7 @@ class BatchedILQR:
                                            self.stream), "qx_riccati")
         self.launches += 1
 
+    @_on_device
     def linesearch(self, tol, force=False):
         c = self.cur
         self.n_active.zero_()
@@ -145,18 +170,26 @@ class BatchedILQR:
         self.launches += (3 if force else 4) if staged else (2 if par else 1)
         self.cur = 1 - c
 
+    @_on_device
     def forward_pass(self, alpha):
         """Candidate rollout with step size `alpha` from the current nominal and gains; returns
-        (x (B,N+1,n), u (B,N,m), cost (B,)) tensors without touching the solver state."""
+        (x (B,N+1,n), u (B,N,m), cost (B,)) tensors.  The candidate goes to scratch tensors of its own: the solver
+        state - including the copy of a finished trajectory's final iterate in the other ping-pong buffer - is
+        not touched."""
         c = self.cur
+        scratch = self.__dict__.get("_fp_scratch")
+        if scratch is None:
+            scratch = self._fp_scratch = (torch.empty_like(self.x[0]), torch.empty_like(self.u[0]))
+        xs, us = scratch
         cost = torch.empty_like(self.cost)
         _lib.check(self.lib.qx_forward_pass(C.byref(self.params), _ptr(self.x[c]), _ptr(self.u[c]), _ptr(self.gains),
-                                            float(alpha), _ptr(self.x[1 - c]), _ptr(self.u[1 - c]), _ptr(cost),
+                                            float(alpha), _ptr(xs), _ptr(us), _ptr(cost),
                                             self.B, self.N, self.stream), "qx_forward_pass")
         self.launches += 1
-        return (self.x[1 - c].permute(2, 0, 1).clone(memory_format=torch.contiguous_format),
-                self.u[1 - c].permute(2, 0, 1).clone(memory_format=torch.contiguous_format), cost)
+        return (xs.permute(2, 0, 1).clone(memory_format=torch.contiguous_format),
+                us.permute(2, 0, 1).clone(memory_format=torch.contiguous_format), cost)
 
+    @_on_device
     def backward(self):
         """Gains for the whole horizon: Riccati, or Riccati tail + transformer head."""
         if self.tf is None:
@@ -172,6 +205,7 @@ class BatchedILQR:
         self.backward()
         self.linesearch(tol, force)
 
+    @_on_device
     def iterate_pair(self, tol=1e-3, force=False):
         """Two iterations replayed as ONE CUDA graph (classic mode): the 14 launches of a pair - linearise, Riccati and
         the five line-search stages, twice - go out in one call, which removes ~2 % of launch gaps at 16 384
@@ -263,6 +297,7 @@ class BatchedILQR:
         return done
 
     # ------------------------------------------------------------------ receding horizon, device resident
+    @_on_device
     def advance_receding_horizon(self, x_next=None):
         """One MPC shift without leaving the device: what ``control_step`` does on the host after ``optimize``
         (cartpole_mpc.py:326-332, quadrotor_mpc.py:115-122) - x0 <- the next plant state, u <- u[1:] + [u[-1]] -

@@ -35,7 +35,17 @@ class StreamedILQR:
             # transformer mode: the slices share the wrapper's device weights (uploaded and split here, once, before any
             # slice stream can ask for them) and its state shift; each engine owns its activations workspace
             tf._device_weights(self.device)
+            self.set_shift(tf._shift.cpu().numpy() if tf._shift is not None else None)
             torch.cuda.current_stream(self.device).synchronize()
+
+    def set_shift(self, shift=None):
+        """State shift of the transformer input (x_seq_err = x_seq + shift, quattro_ilqr_tf.py:504/:532), one private
+        copy per slice engine, created on the current stream: call it before ``run`` (which makes every slice stream
+        wait for the current one), never concurrently with it."""
+        import numpy as np
+        v = np.zeros(self.n) if shift is None else np.asarray(shift, dtype=np.float64).reshape(-1)
+        for eng in self.engines:
+            eng._tf_shift = torch.as_tensor(v, dtype=torch.float64).to(self.device)
 
     @property
     def launches(self):

@@ -150,7 +150,7 @@ class iLQR_TF:
         if tf is not None:
             self._check_tf_shapes()
             shift = np.asarray(self.state_offset, dtype=np.float64).reshape(-1) - np.asarray(x_ref, dtype=np.float64).reshape(-1)
-            tf.set_shift(shift, e.device)
+            e._tf_shift = torch.as_tensor(shift, dtype=torch.float64).to(e.device)     # per engine, not on the shared wrapper
         e.set_problem(x0, u0)
         start = 0 if tf is None else self.horizon - self.tf_window
         log = self.enable_log

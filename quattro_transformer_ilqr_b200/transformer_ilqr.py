@@ -47,7 +47,8 @@ class TransformerILQR:
                                     self.target_len, self.prompt_len)
 
     def load(self, model_path):
-        data = np.load(os.path.join(model_path, "tf_model_normalizer.npz"), allow_pickle=True)
+        # every field is a plain array or scalar: nothing in a checkpoint needs the pickle machinery
+        data = np.load(os.path.join(model_path, "tf_model_normalizer.npz"), allow_pickle=False)
         nz = self.normalizer
         nz.x_mean, nz.x_std, nz.u_mean, nz.u_std = data["x_mean"], data["x_std"], data["u_mean"], data["u_std"]
         for key in ("target_len", "prompt_len", "state_dim", "control_dim", "d_model", "nhead",
@@ -58,7 +59,7 @@ class TransformerILQR:
         if self.quant_mode == "int8":
             raise NotImplementedError("int8 dynamically-quantised checkpoints are not supported by the CUDA path")
         self.model = self._build_model()
-        sd = torch.load(os.path.join(model_path, "tf_model.pt"), map_location="cpu")
+        sd = torch.load(os.path.join(model_path, "tf_model.pt"), map_location="cpu", weights_only=True)
         self.model.load_state_dict({k: v.float() for k, v in sd.items()})
         self.model.eval()
         self._packed = None
@@ -133,8 +134,9 @@ class TransformerILQR:
             cfg = self.config()
             w = self.pack_weights().to(device)
             split = torch.empty(lib.qx_tf_split_floats(C.byref(cfg)), dtype=torch.float32, device=device)
-            _lib.check(lib.qx_tf_prepare(C.byref(cfg), C.c_void_p(w.data_ptr()), C.c_void_p(split.data_ptr()),
-                                         C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "qx_tf_prepare")
+            with torch.cuda.device(device):      # the launch needs `device` current, whatever the caller has set
+                _lib.check(lib.qx_tf_prepare(C.byref(cfg), C.c_void_p(w.data_ptr()), C.c_void_p(split.data_ptr()),
+                                             C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "qx_tf_prepare")
             self._packed = (device, w, split)
         return self._packed[1], self._packed[2]
 
@@ -152,6 +154,13 @@ class TransformerILQR:
         lib = _lib.load()
         cfg = self.config()
         dev = engine.device
+        # The kernels index the trajectories and the gain records with the CHECKPOINT's horizon and dimensions
+        # (a-Q(12): the reference silently mis-aligns the gains when they differ): an engine of another shape would be
+        # read and written out of bounds.
+        if (engine.N, engine.n, engine.m) != (cfg.horizon, self.state_dim, cfg.m):
+            raise ValueError(f"engine shape (N, n, m) = {(engine.N, engine.n, engine.m)} does not match the checkpoint: "
+                             f"horizon = target_len + prompt_len = {cfg.horizon}, state_dim = {self.state_dim}, "
+                             f"m = control_dim / (1 + state_dim) = {cfg.m}")
         w, split = self._device_weights(dev)
         need = lib.qx_tf_workspace_bytes(C.byref(cfg), engine.B)
         # the activations live with the ENGINE, not with the wrapper: slices of a batch that run on their own streams
@@ -159,15 +168,21 @@ class TransformerILQR:
         ws = getattr(engine, "_tf_ws", None)
         if ws is None or ws.device != dev or ws.numel() * 4 < need:
             ws = engine._tf_ws = torch.empty(need // 4, dtype=torch.float32, device=dev)
-        if self._shift is None or self._shift.device != dev:
-            self.set_shift(np.zeros(self.state_dim), dev)
+        # the state shift belongs to the engine (StreamedILQR gives every slice its own before any stream work starts);
+        # the wrapper's own is the default for engines that never set one
+        shift = getattr(engine, "_tf_shift", None)
+        if shift is None:
+            if self._shift is None or self._shift.device != dev:
+                self.set_shift(np.zeros(self.state_dim), dev)
+            shift = self._shift
         c = engine.cur
-        _lib.check(lib.qx_tf_forward(C.byref(cfg), C.c_void_p(w.data_ptr()),
-                                     C.c_void_p(split.data_ptr() if self.tensor_cores else 0),
-                                     C.c_void_p(engine.x[c].data_ptr()),
-                                     C.c_void_p(self._shift.data_ptr()), C.c_void_p(engine.gains.data_ptr()),
-                                     engine.model.model_id, C.c_void_p(engine.status.data_ptr()),
-                                     C.c_void_p(ws.data_ptr()), engine.B, engine.stream), "qx_tf_forward")
+        with torch.cuda.device(dev):
+            _lib.check(lib.qx_tf_forward(C.byref(cfg), C.c_void_p(w.data_ptr()),
+                                         C.c_void_p(split.data_ptr() if self.tensor_cores else 0),
+                                         C.c_void_p(engine.x[c].data_ptr()),
+                                         C.c_void_p(shift.data_ptr()), C.c_void_p(engine.gains.data_ptr()),
+                                         engine.model.model_id, C.c_void_p(engine.status.data_ptr()),
+                                         C.c_void_p(ws.data_ptr()), engine.B, engine.stream), "qx_tf_forward")
         # embed, head, unpack + per layer QKV, attention, out-proj, add+LN, linear1, linear2, add+LN; on the tensor-core
         # path the two add+LN ride in the GEMM epilogues (QX_TF_FUSE_LN, qx_tf_simt.cu), except norm1 of the pruned last layer
         fuse = int(os.environ.get("QX_TF_FUSE_LN", "3")) if self.tensor_cores else 0
@@ -189,6 +204,12 @@ class TransformerILQR:
         name = {(4, 1): "cartpole", (12, 4): "quadrotor"}.get((n, m))
         if name is None:
             raise ValueError("predict needs a built-in system shape (4x1 or 12x4)")
+        if x.ndim != 3 or x.shape[2] != n or N != self.target_len + P:
+            raise ValueError(f"x_seq must be (horizon + 1, state_dim) = ({self.target_len + P + 1}, {n}) "
+                             f"[optionally batched], got {tuple(np.shape(x_seq))}")
+        if kK.ndim != 3 or kK.shape[0] != B or kK.shape[1] < P or kK.shape[2] != m * (1 + n):
+            raise ValueError(f"kK_seq must be (>= prompt_len, control_dim) = (>= {P}, {m * (1 + n)}) "
+                             f"[optionally batched like x_seq], got {tuple(np.shape(kK_seq))}")
         solo = self._solo
         if solo is None or solo.B != B or solo.N != N or solo.model.name != name:
             solo = self._solo = BatchedILQR(DeviceModel(name), B, N)
@@ -201,7 +222,10 @@ class TransformerILQR:
         K_full[:, N - P:] = tail[..., m:].reshape(B, P, m, n)
         solo.load_gains(K_full, k_full)
         solo.status.zero_()
-        self.set_shift(np.zeros(n), solo.device)
+        # predict() takes x_seq_err as is (transformer_ilqr.py:311-316): zero shift, on the scratch engine only - a
+        # shift the caller installed for its own solver stays untouched
+        if getattr(solo, "_tf_shift", None) is None:
+            solo._tf_shift = torch.zeros(n, dtype=torch.float64, device=solo.device)
         self.forward_device(solo)
         K, k = solo.gains_batch()
         T = self.target_len

@@ -45,11 +45,11 @@ def test_layout_queries(lib):
     assert lib.qx_expansion_bytes(1, 1, 50) + lib.qx_terminal_bytes(1, 1) == 83824
     assert lib.qx_gains_bytes(1, 1, 50) == 10400
     assert lib.qx_layout(7) < 0 and b"unknown model_id" in lib.qx_last_error()
-    # line-search workspaces: one int32 winner hint per cart-pole trajectory (128-B granules); the quadrotor parks the
-    # candidates of the five smaller alphas (fp64 trajectories) plus queues and flags
+    # line-search workspaces: one int32 winner hint per cart-pole trajectory (128-B granules); the quadrotor keeps a
+    # queue, two flag arrays, the nominal's cost and the five probe costs per trajectory (no candidate is parked)
     assert lib.qx_linesearch_workspace_bytes(_lib.QX_MODEL_CARTPOLE, 4096, 30) == 4096 * 4
     assert lib.qx_linesearch_workspace_bytes(_lib.QX_MODEL_CARTPOLE, 1, 30) == 128
-    assert lib.qx_linesearch_workspace_bytes(_lib.QX_MODEL_QUADROTOR, 1024, 50) >= 5 * (51 * 12 + 50 * 4) * 8 * 1024
+    assert lib.qx_linesearch_workspace_bytes(_lib.QX_MODEL_QUADROTOR, 1024, 50) == 32 + 3 * 4096 + 6 * 8192
     assert lib.qx_linesearch_workspace_bytes(_lib.QX_MODEL_CARTPOLE, 0, 30) == 0
 
 

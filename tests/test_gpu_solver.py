@@ -556,3 +556,111 @@ def test_transformer_mode_matches_golden_runs(system, mode):
             assert relmax(np.array(u), r["u_final"]) < 2e-3
         assert len(il.get_time()) == 4 and len(il.inference_time) == len(L)
     assert n_ok >= 3, f"line-search decisions differ from the reference in {4 - n_ok}/4 runs"
+
+
+# ---------------------------------------------------------------------------- host-side guards (round-1 review)
+def test_transformer_rejects_an_engine_of_another_shape():
+    """forward_device indexes trajectories and gain records with the checkpoint's horizon / dimensions: an engine of
+    another shape must raise instead of reading out of bounds (the reference silently mis-aligns, a-Q(12))."""
+    from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel
+    w = _wrapper("cartpole", "fp32")
+    good = BatchedILQR(DeviceModel("cartpole"), 8, HORIZON["cartpole"], tf=w)
+    good.set_problem(sample_x0("cartpole", 8, seed=3), np.zeros((8, HORIZON["cartpole"], 1)))
+    good.backward()                                     # the matching shape runs
+    for eng in (BatchedILQR(DeviceModel("cartpole"), 8, HORIZON["cartpole"] - 5, tf=w),
+                BatchedILQR(DeviceModel("quadrotor"), 8, HORIZON["cartpole"], tf=w)):
+        eng.set_problem(sample_x0(eng.model.name, 8, seed=3), np.zeros((8, eng.N, eng.m)))
+        with pytest.raises(ValueError, match="does not match the checkpoint"):
+            eng.backward()
+    torch.cuda.synchronize()
+
+
+def test_predict_validates_shapes_and_keeps_the_callers_shift(golden_dir):
+    g = np.load(f"{golden_dir}/tf_forward_cartpole.npz")
+    w = _wrapper("cartpole", "fp32")
+    x, kK = g["x_err"][0], g["kK"][0]
+    ref = w.predict(x, kK)
+    with pytest.raises(ValueError, match="x_seq must be"):
+        w.predict(x[:-3], kK)
+    with pytest.raises(ValueError, match="x_seq must be"):
+        w.predict(x[:, :3], kK)
+    with pytest.raises(ValueError, match="kK_seq must be"):
+        w.predict(x, kK[:, :4])
+    with pytest.raises(ValueError, match="kK_seq must be"):
+        w.predict(x, kK[-2:])
+    shift = np.array([0.25, 0.0, -0.5, 0.0])
+    w.set_shift(shift, torch.device("cuda:0"))
+    again = w.predict(x, kK)                            # predict takes x_seq_err as is: zero shift, on its own engine
+    assert np.array_equal(ref, again)
+    assert np.array_equal(w._shift.cpu().numpy(), shift)
+
+
+def test_forward_pass_probe_leaves_the_solver_state_alone():
+    """A mid-solve forward_pass() must not disturb anything: finished trajectories keep their final iterate in BOTH
+    ping-pong buffers, and continuing the solve gives the bits of an undisturbed solve."""
+    from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel
+    B, N = 256, HORIZON["cartpole"]
+    x0 = sample_x0("cartpole", B, seed=8)
+    u0 = np.zeros((B, N, 1))
+    a = BatchedILQR(DeviceModel("cartpole"), B, N)
+    b = BatchedILQR(DeviceModel("cartpole"), B, N)
+    for e in (a, b):
+        e.set_problem(x0, u0)
+        for _ in range(2):
+            e.iterate(TOL["cartpole"])
+    assert int((a.status != 0).sum()) > 0               # some trajectories are finished by now
+    before = [t.clone() for t in (a.x[0], a.x[1], a.u[0], a.u[1], a.cost)]
+    xs, us, cs = a.forward_pass(0.5)
+    assert xs.shape == (B, N + 1, 4) and us.shape == (B, N, 1) and cs.shape == (B,)
+    for t0, t1 in zip(before, (a.x[0], a.x[1], a.u[0], a.u[1], a.cost)):
+        assert torch.equal(t0, t1)
+    for e in (a, b):
+        for _ in range(3):
+            e.iterate(TOL["cartpole"])
+    torch.cuda.synchronize()
+    assert torch.equal(a.u_batch(), b.u_batch()) and torch.equal(a.x_batch(), b.x_batch()) and torch.equal(a.cost, b.cost)
+
+
+def test_graph_cache_follows_a_layout_change():
+    """iterate_pair graphs bake buffer addresses in; a parameter change that switches the expansion layout frees and
+    reallocates those buffers, so the cached graphs must go with them (and come back correct after switching back)."""
+    from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel
+    B, N = 512, HORIZON["quadrotor"]
+    x0 = sample_x0("quadrotor", B, seed=5)
+    u0 = np.zeros((B, N, 4))
+    model = DeviceModel("quadrotor")
+    e, ref = BatchedILQR(model, B, N), BatchedILQR(DeviceModel("quadrotor"), B, N)
+    e.set_problem(x0, u0)
+    for _ in range(3):
+        e.iterate_pair(1e-3, force=True)                # plain, capture, replay
+    assert e.__dict__.get("_pair_graphs")
+    model.integration_method = "rk4"                    # generic records: the block buffers are released
+    e.set_problem(x0, u0)
+    assert not e.__dict__.get("_pair_graphs")
+    e.iterate_pair(1e-3, force=True)
+    model.integration_method = "euler"                  # back on the block path, new buffers
+    e.set_problem(x0, u0)
+    ref.set_problem(x0, u0)
+    for _ in range(3):
+        e.iterate_pair(1e-3, force=True)
+    for _ in range(6):
+        ref.iterate(1e-3, force=True)
+    torch.cuda.synchronize()
+    assert torch.equal(e.cost, ref.cost) and torch.equal(e.u[e.cur], ref.u[ref.cur])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_engine_on_a_device_that_is_not_current():
+    """BatchedILQR(device='cuda:1') while cuda:0 is current: every launch runs under a device guard."""
+    from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel
+    B, N = 64, HORIZON["quadrotor"]
+    x0 = sample_x0("quadrotor", B, seed=4)
+    u0 = np.zeros((B, N, 4))
+    torch.cuda.set_device(0)
+    a = BatchedILQR(DeviceModel("quadrotor"), B, N, device="cuda:0")
+    b = BatchedILQR(DeviceModel("quadrotor"), B, N, device="cuda:1")
+    for e in (a, b):
+        e.set_problem(x0, u0)
+        e.solve(fixed_iters=3)
+    torch.cuda.synchronize(0); torch.cuda.synchronize(1)
+    assert torch.equal(a.cost.cpu(), b.cost.cpu()) and torch.equal(a.u_batch().cpu(), b.u_batch().cpu())
