@@ -27,21 +27,13 @@
 // lane-contiguous: conflict free).  The record of the next step is copied global -> shared with cp.async
 // (LDGSTS, 15 x 16 B per thread) while the current step is computed: no staging registers, no barrier - a thread
 // only ever reads what it copied itself.
-#include "qx_models.cuh"
+#include "qx_blk.cuh"
 
 namespace qx {
 
-struct BlkConst {       // same as qx_blk.cu
-  float dt, reg;
-  float tr[3];
-  float lq[12];
-  float lqf[12];
-};
-
 namespace {
 
-constexpr int kThrOct = 8 * 64;          // floats per octet record group (qx_blk.cu kBlkOct)
-constexpr int kThrTerm = 16;
+constexpr int kThrTerm = kBlkTerm;
 
 __host__ __device__ constexpr int TRI(int i, int j) {
   return i <= j ? (i * 12 - (i * (i - 1)) / 2 + (j - i)) : (j * 12 - (j * (j - 1)) / 2 + (i - j));
