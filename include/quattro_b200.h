@@ -24,11 +24,12 @@
  *   iters  int32  [B]              iterations executed so far
  *   alpha  int32  [B]              index into {1,.5,.25,.1,.05,.01} accepted last, -1 = none
  *   expansion / terminal / gains: float, layout depends on the model's "record" kind:
- *     QX_LAYOUT_REC (quadrotor; warp-per-trajectory Riccati, one contiguous record per (t,b))
+ *     QX_LAYOUT_REC (quadrotor; generic dense records, one contiguous record per (t,b))
  *        expansion float [N][B][REC]   REC = [F n*(n+m) | lx n | lu m | lxx n*n | luu m*m | lux m*n],
  *                                      F = [A | B] interleaved: row i = A[i][0..n) then B[i][0..m)
  *        terminal  float [B][n + n*n]  [Vx | Vxx]
- *        gains     float [N][B][m + m*n]  [k | K row-major]
+ *        gains     float4 [N][(m + m*n)/4][B]  (b fastest): float4 #0 = k, #1.. = K row-major, four entries each;
+ *                  element (t, ch, b) at (((t * 13 + ch / 4) * B + b) * 4 + ch % 4 floats (m + m*n = 52)
  *     QX_LAYOUT_SOA (cart-pole; thread-per-trajectory Riccati, b fastest)
  *        expansion float [N][REC][B], terminal float [n + n*n][B], gains float [N][m + m*n][B]
  */
@@ -129,7 +130,7 @@ int qx_riccati(int model_id, const float* expansion, const float* terminal, floa
  *              6-8 rows of E = dt deta'/domega with l_u[3], l_uu[0], l_uu[1], 9-11 rows of
  *              Sp = I + dt domega'/domega with l_uu[2], l_uu[3], 12-14 l_x, 15 unused)
  *   terminal  float [B][16]  = [V_x(12) | pad]   (V_xx(N) = 2 Qf comes from the parameters)
- *   gains     as QX_LAYOUT_REC: float [N][B][52] = [k | K row-major]
+ *   gains     as QX_LAYOUT_REC: float4 [N][13][B], [k | K row-major] in groups of four
  * qx_blk_supported() tells whether the parameter block qualifies; the generic entry points serve the rest. */
 int qx_blk_supported(const QxParams* p);
 size_t qx_blk_expansion_bytes(int B, int N);
@@ -148,10 +149,15 @@ int qx_riccati_blk(const QxParams* p, const float* expansion, const float* termi
  * caller can ping-pong the buffers.  n_active (device int32, may be NULL) is incremented by the
  * number of trajectories still active afterwards.
  * workspace (qx_linesearch_workspace_bytes(), may be NULL): with it the candidates are evaluated concurrently
- * instead of one alpha after the other - quadrotor (diagonal weights): alpha = 1 for every trajectory, then the
- * remaining alphas of the rejected ones in two stages (candidates parked in the workspace); cart-pole: the six
- * alphas side by side (costs only; alpha = 1 also stored), then the winners other than alpha = 1 re-rolled and
- * stored (the workspace holds one int32 hint per trajectory).  Results are bit-identical with and without it. */
+ * instead of one alpha after the other - quadrotor (diagonal weights): alpha = 1 for every trajectory (stage A, the
+ * candidate goes straight into x_out/u_out), then the five smaller alphas of the rejected ones side by side, costs
+ * only (stage B), then the first accepted one rolled out again into x_out/u_out (stage W; a trajectory without an
+ * accepted alpha rolls alpha = 0, i.e. its nominal), then the final iterates of the finished trajectories mirrored
+ * into x_in/u_in; the workspace holds the queue, two int32 flags, the nominal's cost and five probe costs per
+ * trajectory.  Cart-pole: the six alphas side by side (costs only; alpha = 1 also stored), then the winners other
+ * than alpha = 1 re-rolled and stored (the workspace holds one int32 hint per trajectory).  Results are bit-identical
+ * with and without it.  A candidate whose partial cost already exceeds cost[b] is abandoned early (quadrotor, when
+ * Q, R, Qf and the barrier weight are non-negative: the costs are then sums of non-negative terms). */
 size_t qx_linesearch_workspace_bytes(int model_id, int B, int N);
 int qx_linesearch(const QxParams* p, double* x_in, double* u_in, const float* gains, double* cost,
                   int32_t* status, int32_t* iters, int32_t* alpha, double* x_out, double* u_out,
