@@ -9,6 +9,8 @@ encoder layers -> output head -> de-normalise -> unpack, with no PyTorch operato
 Checkpoints saved with ``quant_mode="float16"`` (both shipped ones) are loaded as the same fp16
 values widened to fp32: the kernels compute in fp32, which is MORE accurate than the reference's
 fp16 CPU inference (measured gap of the reference's own two modes: ~3e-4 relative).
+``quant_mode="int8"`` checkpoints (torch dynamic quantisation of the nn.Linear modules) are read and
+written in the reference's format; on load the int8 weights are de-quantised to fp32.
 """
 from __future__ import annotations
 
@@ -21,6 +23,28 @@ import torch
 
 from . import _lib
 from .transformer_model import DataNormalizer, TransformerPredictor
+
+
+def _dequantize_dynamic_state_dict(sd):
+    """state_dict of ``torch.quantization.quantize_dynamic(model, {nn.Linear}, qint8)`` (the reference's
+    ``quant_mode="int8"`` checkpoints, transformer_ilqr.py:226-227 / :297-298) -> plain fp32 state_dict.
+    Every quantised Linear stores ``<name>._packed_params._packed_params = (qint8 weight, bias)`` plus ``scale``,
+    ``zero_point`` and ``dtype`` entries of its (unused, dynamic) output quantiser; the attention in_proj / out_proj and
+    the LayerNorms are not nn.Linear modules and stay fp32.  The CUDA path then computes with the de-quantised int8
+    weights and fp32 activations - the reference additionally quantises the activations of each Linear per call."""
+    out = {}
+    for key, val in sd.items():
+        if key.endswith("._packed_params._packed_params"):
+            prefix = key[: -len("._packed_params._packed_params")]
+            qw, bias = val
+            out[prefix + ".weight"] = qw.dequantize() if qw.is_quantized else qw
+            if bias is not None:
+                out[prefix + ".bias"] = bias
+        elif key.endswith((".scale", ".zero_point", "._packed_params.dtype")):
+            continue
+        else:
+            out[key] = val
+    return out
 
 
 class TransformerILQR:
@@ -56,10 +80,10 @@ class TransformerILQR:
             setattr(self, key, int(data[key]))
         self.dropout = float(data["dropout"])
         self.quant_mode = str(data["quant_mode"])
-        if self.quant_mode == "int8":
-            raise NotImplementedError("int8 dynamically-quantised checkpoints are not supported by the CUDA path")
         self.model = self._build_model()
         sd = torch.load(os.path.join(model_path, "tf_model.pt"), map_location="cpu", weights_only=True)
+        if self.quant_mode == "int8":
+            sd = _dequantize_dynamic_state_dict(sd)
         self.model.load_state_dict({k: v.float() for k, v in sd.items()})
         self.model.eval()
         self._packed = None
@@ -78,7 +102,12 @@ class TransformerILQR:
         if self.quant_mode == "float16":
             sd = {k: v.half() for k, v in sd.items()}
         elif self.quant_mode == "int8":
-            raise NotImplementedError("int8 export is not supported")
+            # the reference's wire format (transformer_ilqr.py:226-227): torch's dynamic quantisation of the nn.Linear
+            # modules, applied to a CPU copy (the live fp32 module stays as it is)
+            import copy
+            q = torch.quantization.quantize_dynamic(copy.deepcopy(self.model).cpu().float(), {torch.nn.Linear},
+                                                    dtype=torch.qint8)
+            sd = q.state_dict()
         torch.save(sd, os.path.join(dir_name, "tf_model.pt"))
         nz = self.normalizer
         np.savez(os.path.join(dir_name, "tf_model_normalizer.npz"), x_mean=nz.x_mean, x_std=nz.x_std,

@@ -178,3 +178,41 @@ def test_tf_mode_port_matches_reference(system):
     alphas = [(-1 if l["alpha"] is None else ob.ALPHAS.tolist().index(l["alpha"])) for l in p.logs]
     assert alphas == list(r["alpha_idx"])
     assert relmax([l["current_cost"] for l in p.logs], r["cost"]) < 1e-5
+
+
+def test_int8_checkpoint_round_trip(tmp_path, monkeypatch):
+    """quant_mode="int8" (transformer_ilqr.py:226-227, :297-298): save writes torch's dynamically-quantised state_dict,
+    load de-quantises it; the loaded fp32 module must carry exactly the de-quantised int8 weights of the nn.Linear
+    modules and the untouched fp32 tensors of everything else.  Host logic only (no GPU)."""
+    import copy
+    import os
+    import torch
+    from quattro_transformer_ilqr_b200 import TransformerILQR
+    from quattro_transformer_ilqr_b200.transformer_model import TransformerPredictor
+    w = TransformerILQR(4, 5, prompt_len=5, d_model=128, nhead=4, num_decoder_layers=3, dim_feedforward=256,
+                        max_seq_len=100, quant_mode="int8")
+    w.target_len = 25
+    torch.manual_seed(3)
+    w.model = TransformerPredictor(4, 5, 128, 4, 3, 256, 0.1, 100, 25, 5).eval()
+    nz = w.normalizer
+    nz.x_mean, nz.x_std = np.zeros(4, np.float32), np.ones(4, np.float32)
+    nz.u_mean, nz.u_std = np.zeros(5, np.float32), np.ones(5, np.float32)
+    monkeypatch.chdir(tmp_path)
+    d = w.save("int8test")
+    sd_file = torch.load(os.path.join(d, "tf_model.pt"), weights_only=True)
+    assert any(k.endswith("._packed_params._packed_params") for k in sd_file)          # the reference's wire format
+    r = TransformerILQR(1, 1).load(d)
+    assert r.quant_mode == "int8" and r.target_len == 25 and r.prompt_len == 5
+    ref_q = torch.quantization.quantize_dynamic(copy.deepcopy(w.model), {torch.nn.Linear}, dtype=torch.qint8)
+    got, orig = r.model.state_dict(), w.model.state_dict()
+    for name in ("state_embed", "control_embed", "output_linear", "transformer_decoder.layers.1.linear1",
+                 "transformer_decoder.layers.2.linear2"):
+        mod = ref_q
+        for part in name.split("."):
+            mod = getattr(mod, part)
+        assert torch.equal(got[name + ".weight"], mod.weight().dequantize())
+        assert torch.equal(got[name + ".bias"], mod.bias())
+        assert not torch.equal(got[name + ".weight"], orig[name + ".weight"])           # really quantised
+    for name in ("transformer_decoder.layers.0.self_attn.in_proj_weight", "transformer_decoder.layers.0.norm1.weight",
+                 "target_embedding", "transformer_decoder.layers.2.self_attn.out_proj.weight"):
+        assert torch.equal(got[name], orig[name])                                       # not nn.Linear: stays fp32
