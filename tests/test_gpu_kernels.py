@@ -440,3 +440,84 @@ def test_dense_layer_with_layernorm_epilogue(K):
                             128, 96, st)
     assert rc != 0 and b"K" in lib.qx_last_error()
 
+
+
+# ---------------------------------------------------------------------------- round 2: thread-per-candidate search
+def _spoiled_search(B, seed, forced, ws=True, **model_kw):
+    """One line search of the staged quadrotor kernels on the oracle's gains with some of them spoiled, so that every
+    outcome occurs: alpha = 1, smaller alphas, no alpha at all."""
+    x0, u = _problem("quadrotor", B, seed, 0.75)
+    model = make_model("quadrotor", **model_kw)
+    x_ref, c_ref = ob.rollout(model, x0, u)
+    K, k = ob.riccati(ob.linearize(model, x_ref, u))
+    rng = np.random.default_rng(seed)
+    scale = rng.choice([1.0, 3.0, 8.0, -1.0], size=B, p=[0.4, 0.25, 0.2, 0.15])
+    k = (k * scale[:, None, None]).astype(np.float32)
+    K = K.astype(np.float32)
+    e = _engine("quadrotor", B, **model_kw)
+    if not ws:
+        e.ls_workspace = None
+    e.set_problem(x0, u)
+    e.load_gains(K, k)
+    nominal = (e.x[e.cur].clone(), e.u[e.cur].clone(), e.cost.clone())
+    e.linesearch(tol=1e-3, force=forced)
+    ref = ob.line_search(model, x_ref, u, K.astype(np.float64), k.astype(np.float64), c_ref)
+    return e, nominal, ref
+
+
+@pytest.mark.parametrize("forced", [False, True])
+def test_no_accepted_alpha_keeps_the_nominal_bit_for_bit(forced):
+    """Stage W gives a trajectory without an accepted alpha its nominal by rolling out alpha = 0 (no copy pass): the
+    next iterate must be the nominal's exact bits - x, u and cost - forced mode or not, and in non-forced mode the
+    trajectory is finished with that iterate in both buffers."""
+    e, (xn, un, cn), (_, _, _, idx, _) = _spoiled_search(203, 31, forced)
+    none = torch.as_tensor(idx < 0, device=e.device)
+    assert int(none.sum()) >= 10
+    assert np.array_equal(e.alpha.cpu().numpy(), idx)
+    c = e.cur
+    assert torch.equal(e.x[c][:, :, none], xn[:, :, none]) and torch.equal(e.u[c][:, :, none], un[:, :, none])
+    assert torch.equal(e.cost[none], cn[none])
+    assert torch.equal(e.x[1 - c][:, :, none], xn[:, :, none])           # the input buffer still holds it too
+    st = e.status.cpu().numpy()
+    assert (st[idx < 0] == (0 if forced else 1)).all()
+
+
+def test_early_rejection_is_switched_off_for_negative_weights():
+    """Partial costs only prove a rejection when every cost term is non-negative.  With a negative weight the kernels
+    must run every candidate to the end - and still agree with the oracle on every decision and candidate."""
+    Q = np.diag([10.0, 10, 50, 1, 1, 1, 10, 10, 50, -40.0, -40.0, 1])      # rewards body rates: costs are not monotone in t
+    e, _, (xn, un, cn, idx, _) = _spoiled_search(160, 41, False, Q=Q)
+    assert len(set(idx.tolist())) >= 3
+    assert np.array_equal(e.alpha.cpu().numpy(), idx)
+    assert relmax(e.cost.cpu().numpy(), cn) < 1e-12
+    assert relmax(e.u_batch().cpu().numpy(), un) < 1e-11 and relmax(e.x_batch().cpu().numpy(), xn) < 1e-11
+    # and the staged search equals the single-launch sequential search bit for bit there as well
+    s, _, _ = _spoiled_search(160, 41, False, ws=False, Q=Q)
+    assert torch.equal(e.cost, s.cost) and torch.equal(e.alpha, s.alpha) and torch.equal(e.u[e.cur], s.u[s.cur])
+
+
+def test_staged_search_equals_sequential_search_bitwise():
+    """Stages A / B / W (early rejection, costs-only probes, winner rolled out again) against the single-launch kernel
+    that walks the alpha list in order: same bits in costs, alphas, iterates, status and both ping-pong buffers."""
+    a, _, _ = _spoiled_search(333, 51, False)
+    b, _, _ = _spoiled_search(333, 51, False, ws=False)
+    assert torch.equal(a.alpha, b.alpha) and torch.equal(a.cost, b.cost) and torch.equal(a.status, b.status)
+    for buf in (0, 1):
+        assert torch.equal(a.x[buf], b.x[buf]) and torch.equal(a.u[buf], b.u[buf])
+
+
+def test_gain_record_layout_round_trip():
+    """float4 [N][13][B] gains of the quadrotor: load_gains / gains_batch are inverse, and element (t, ch, b) sits where
+    include/quattro_b200.h says."""
+    B, N = 37, 50
+    e = _engine("quadrotor", B)
+    rng = np.random.default_rng(0)
+    K = rng.standard_normal((B, N, 4, 12)).astype(np.float32)
+    k = rng.standard_normal((B, N, 4)).astype(np.float32)
+    e.load_gains(K, k)
+    K2, k2 = e.gains_batch()
+    assert np.array_equal(K2.cpu().numpy(), K) and np.array_equal(k2.cpu().numpy(), k)
+    flat = e.gains.cpu().numpy()
+    for (t, ch, b) in [(0, 0, 0), (3, 2, 5), (49, 51, 36), (17, 4, 1), (17, 7, 1)]:
+        want = k[b, t, ch] if ch < 4 else K[b, t].reshape(-1)[ch - 4]
+        assert flat[((t * 13 + ch // 4) * B + b) * 4 + ch % 4] == want
