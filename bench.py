@@ -51,9 +51,9 @@ FP64_EXTRA = {"quadrotor": {"linearize": 3248, "riccati": 0, "linesearch": 3248 
               "cartpole": {"linearize": 616, "riccati": 0, "linesearch": 616 + 620, "rollout": 636}}
 # Block path (quadrotor, Euler, diagonal weights; include/quattro_b200.h QX_LAYOUT_BLK): the expansion is 64
 # floats per (t, b) instead of 416 and the terminal 16 floats, so the algorithmic traffic of the backward pass is
-#   linearise: read x,u fp64 6 496 B + write 50 x 256 + 64 B            = 19 360 B per trajectory
-#   Riccati  : read 50 x 256 + 64 B      + write gains 50 x 208 B       = 23 264 B per trajectory
-BLK_BYTES = {"linearize": 6496 + 50 * 256 + 64, "riccati": 50 * 256 + 64 + 50 * 208}
+#   linearise: read x,u fp64 6 496 B + write 50 x 192 + 64 B            = 16 160 B per trajectory
+#   Riccati  : read 50 x 192 + 64 B      + write gains 50 x 208 B       = 20 064 B per trajectory
+BLK_BYTES = {"linearize": 6496 + 50 * 192 + 64, "riccati": 50 * 192 + 64 + 50 * 208}
 
 
 def peaks():
@@ -494,7 +494,7 @@ def gpu_bench(args):
         "config": {"workload": f"{args.workload}: {system} n={n} m={m} horizon={N}, {B} trajectories per GPU, "
                                f"fixed-iteration mode, problem reset every {RESET_EVERY} steps",
                    "global_batch": world * B, "parallelism": f"dp{world} (independent trajectory shards)",
-                   "backward_pass": "block records (64 floats per step)" if eng.exp_layout == 2 else "dense records",
+                   "backward_pass": "block records (48 floats per step)" if eng.exp_layout == 2 else "dense records",
                    "launch": "two iterations per CUDA-graph replay" if (tf is None and args.graph) else "one launch per kernel",
                    "l2": "working set per iteration (x, u ping-pong 0.21 GB + expansion 0.21 GB + gains 0.17 GB at 16 384 "
                          "trajectories) larger than the 126 MB L2"},

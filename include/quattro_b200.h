@@ -123,12 +123,14 @@ int qx_riccati(int model_id, const float* expansion, const float* terminal, floa
 /* ---- Block fast path of the backward pass: quadrotor + Euler map + diagonal Q, R, Qf (what every driver
  * of the reference runs: quadrotor_sim.py:100, quadrotor_mpc.py:40-46).  There A_t is block bidiagonal in
  * x = [p | v | eta | omega], B_t has two non-zero row blocks, l_xx / l_uu are diagonal and l_ux = 0, so
- * linearise emits 64 floats per (t, b) instead of 416 and the Riccati step works on 3x3 blocks with four
- * lanes per trajectory (qx_blk.cu).  Same results as qx_linearize + qx_riccati (quattro_ilqr_tf.py:182-366).
- *   expansion float [N][ceil(B/8)][16 slots][8 trajectories][4]   (QX_LAYOUT_BLK; float4 slots: 0-2 rows of
- *              G = dt dv'/deta with d = dt/m dir in .w, 3-5 rows of Hp = I + dt deta'/deta with l_u[0..2],
- *              6-8 rows of E = dt deta'/domega with l_u[3], l_uu[0], l_uu[1], 9-11 rows of
- *              Sp = I + dt domega'/domega with l_uu[2], l_uu[3], 12-14 l_x, 15 unused)
+ * linearise emits 48 floats per (t, b) instead of 416 and the Riccati step works on 3x3 blocks with one
+ * thread per trajectory (qx_blk.cu, qx_blk_riccati.cu).  Same results as qx_linearize + qx_riccati (quattro_ilqr_tf.py:182-366).
+ *   expansion float [N][ceil(B/8)][12 slots][8 trajectories][4]   (QX_LAYOUT_BLK, 48 floats = 192 B per (t, b)):
+ *              only the entries that vary are stored.  With G = dt dv'/deta, Hp = I + dt deta'/deta,
+ *              E = dt deta'/domega, Sp = I + dt domega'/domega (G[2][2] = 0; Hp[:,2] = e3, Hp[1][1] = 1;
+ *              E[:,0] = dt e1; diag(Sp) = 1) and d = dt/m * thrust direction, the float4 slots are
+ *              0: g00 g01 g02 d0 | 1: g10 g11 g12 d1 | 2: g20 g21 d2 h00 | 3: h01 h10 h20 h21 | 4: e01 e02 e11 e12
+ *              5: e21 e22 s01 s02 | 6: s10 s12 s20 s21 | 7: l_u | 8: diag(l_uu) | 9-11: l_x
  *   terminal  float [B][16]  = [V_x(12) | pad]   (V_xx(N) = 2 Qf comes from the parameters)
  *   gains     as QX_LAYOUT_REC: float4 [N][13][B], [k | K row-major] in groups of four
  * qx_blk_supported() tells whether the parameter block qualifies; the generic entry points serve the rest. */

@@ -14,10 +14,11 @@
 //        | 0   0    0   Sp |          | T      |      T  = dt * (constant torque map, +-tr[r])
 //
 // and l_xx = 2Q, l_uu = 2R + barrier'' are diagonal, l_ux = 0.  So instead of the dense 416-float
-// record (1 664 B per step and trajectory through HBM, twice) linearise emits the 36 block entries
-// plus d, l_x, l_u, diag(l_uu): 64 floats = 256 B, and the Riccati step works on 3x3 blocks.
-// Records are stored float4-interleaved over eight trajectories ([t][b/8][16 slots][8][4 floats]), so that
-// linearise writes whole 128-B lines without staging and the Riccati thread of trajectory b copies its sixteen
+// record (1 664 B per step and trajectory through HBM, twice) linearise emits the 25 block entries that vary
+// (the blocks also hold fixed 0 / 1 / dt entries, qx_blk.cuh) plus d, l_x, l_u, diag(l_uu): 48 floats = 192 B,
+// and the Riccati step works on 3x3 blocks.
+// Records are stored float4-interleaved over eight trajectories ([t][b/8][12 slots][8][4 floats]), so that
+// linearise writes whole 128-B lines without staging and the Riccati thread of trajectory b copies its twelve
 // 16-B slots with a warp touching four full lines per slot.
 #include "qx_blk.cuh"
 
@@ -48,13 +49,13 @@ linearize_quad_blk_kernel(const __grid_constant__ LinConst k, const double* __re
   float us[m];
 #pragma unroll
   for (int j = 0; j < m; ++j) us[j] = float(u[((size_t)t * m + j) * B + b]);
-  float4 rec[16];
+  float4 rec[15], pk[kBlkSlots];
   quad_blk_record(k, xs, us, rec);
-  rec[15] = make_float4(0.f, 0.f, 0.f, 0.f);
+  quad_blk_pack(rec, pk);
   const int n_oct = ceil_div(B, 8);
   float4* out = reinterpret_cast<float4*>(expansion + ((size_t)t * n_oct + (b >> 3)) * kBlkOct) + (b & 7);
 #pragma unroll
-  for (int qd = 0; qd < 16; ++qd) out[qd * 8] = rec[qd];     // a warp writes 4 full 128-B lines per slot
+  for (int qd = 0; qd < kBlkSlots; ++qd) out[qd * 8] = pk[qd];     // a warp writes 4 full 128-B lines per slot
 }
 
 }  // namespace qx

@@ -8,11 +8,17 @@
 
 namespace qx {
 
-constexpr int kBlkRec = 64;              // floats per (t, b) record
-constexpr int kBlkOct = 8 * kBlkRec;     // floats per octet of trajectories
+constexpr int kBlkSlots = 12;            // float4 slots per (t, b) record
+constexpr int kBlkRec = 4 * kBlkSlots;   // 48 floats = 192 B: exactly the entries of the expansion that vary
+constexpr int kBlkOct = 8 * kBlkRec;     // floats per octet of trajectories (twelve 128-B lines)
 constexpr int kBlkTerm = 16;             // floats per trajectory: [V_x(12) | pad]
-// float4 slots of a record: 0-2 G rows (.w = d), 3-5 Hp rows (.w = l_u[0..2]),
-// 6-8 E rows (.w = l_u[3], l_uu[0], l_uu[1]), 9-11 Sp rows (.w = l_uu[2], l_uu[3], 0), 12-14 l_x, 15 pad
+// The blocks have fixed entries besides the variable ones,
+//   G = |g00 g01 g02|  Hp = |h00 h01 0|  E = |dt e01 e02|  Sp = |1   s01 s02|
+//       |g10 g11 g12|       |h10 1   0|      |0  e11 e12|       |s10 1   s12|
+//       |g20 g21 0  |       |h20 h21 1|      |0  e21 e22|       |s20 s21 1  |
+// and only the variable ones are stored.  float4 slots of a record:
+//   0: g00 g01 g02 d0 | 1: g10 g11 g12 d1 | 2: g20 g21 d2 h00 | 3: h01 h10 h20 h21 | 4: e01 e02 e11 e12
+//   5: e21 e22 s01 s02 | 6: s10 s12 s20 s21 | 7: l_u | 8: diag(l_uu) | 9-11: l_x
 
 // constants of the Riccati recursion
 struct BlkConst {
@@ -121,6 +127,22 @@ __device__ __forceinline__ void quad_blk_record(const LinConst& k, const float* 
   rec[12] = make_float4(gx[0], gx[1], gx[2], gx[3]);
   rec[13] = make_float4(gx[4], gx[5], gx[6], gx[7]);
   rec[14] = make_float4(gx[8], gx[9], gx[10], gx[11]);
+}
+
+// the 15 logical slots of quad_blk_record -> the 12 stored slots (drops the entries that are 0, 1 or dt by construction)
+__device__ __forceinline__ void quad_blk_pack(const float4* r, float4* p) {
+  p[0] = r[0];
+  p[1] = r[1];
+  p[2] = make_float4(r[2].x, r[2].y, r[2].w, r[3].x);
+  p[3] = make_float4(r[3].y, r[4].x, r[5].x, r[5].y);
+  p[4] = make_float4(r[6].y, r[6].z, r[7].y, r[7].z);
+  p[5] = make_float4(r[8].y, r[8].z, r[9].y, r[9].z);
+  p[6] = make_float4(r[10].x, r[10].z, r[11].x, r[11].y);
+  p[7] = make_float4(r[3].w, r[4].w, r[5].w, r[6].w);
+  p[8] = make_float4(r[7].w, r[8].w, r[9].w, r[10].w);
+  p[9] = r[12];
+  p[10] = r[13];
+  p[11] = r[14];
 }
 
 // terminal gradient V_x(N) = 2 Qf (x_N - x_ref); V_xx(N) = 2 Qf is constant

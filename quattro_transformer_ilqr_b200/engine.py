@@ -385,24 +385,34 @@ class BatchedILQR:
         B, N, n, m = self.B, self.N, self.n, self.m
         p, dev, f32 = self.params, self.device, torch.float32
         noct = (B + 7) // 8
-        r = self.expansion.view(N, noct, 16, 8, 4).permute(1, 3, 0, 2, 4).reshape(noct * 8, N, 16, 4)[:B]   # (B,N,slot,4)
+        r = self.expansion.view(N, noct, 12, 8, 4).permute(1, 3, 0, 2, 4).reshape(noct * 8, N, 12, 4)[:B]   # (B,N,slot,4)
         dt = float(p.dt)
+        one, zero = torch.ones((B, N), dtype=f32, device=dev), torch.zeros((B, N), dtype=f32, device=dev)
+
+        def mat(rows):
+            return torch.stack([torch.stack(row, dim=-1) for row in rows], dim=-2)
+        # stored: the entries of the four blocks that vary; the others are 0, 1 or dt by construction (qx_blk.cuh)
+        G = mat([[r[..., 0, 0], r[..., 0, 1], r[..., 0, 2]], [r[..., 1, 0], r[..., 1, 1], r[..., 1, 2]],
+                 [r[..., 2, 0], r[..., 2, 1], zero]])
+        Hp = mat([[r[..., 2, 3], r[..., 3, 0], zero], [r[..., 3, 1], one, zero], [r[..., 3, 2], r[..., 3, 3], one]])
+        E = mat([[dt * one, r[..., 4, 0], r[..., 4, 1]], [zero, r[..., 4, 2], r[..., 4, 3]], [zero, r[..., 5, 0], r[..., 5, 1]]])
+        Sp = mat([[one, r[..., 5, 2], r[..., 5, 3]], [r[..., 6, 0], one, r[..., 6, 1]], [r[..., 6, 2], r[..., 6, 3], one]])
+        d = torch.stack([r[..., 0, 3], r[..., 1, 3], r[..., 2, 2]], dim=-1)
         A = torch.eye(n, dtype=f32, device=dev).repeat(B, N, 1, 1)
         A[..., 0:3, 3:6] = dt * torch.eye(3, dtype=f32, device=dev)
-        A[..., 3:6, 6:9] = r[..., 0:3, 0:3]
-        A[..., 6:9, 6:9] = r[..., 3:6, 0:3]
-        A[..., 6:9, 9:12] = r[..., 6:9, 0:3]
-        A[..., 9:12, 9:12] = r[..., 9:12, 0:3]
+        A[..., 3:6, 6:9] = G
+        A[..., 6:9, 6:9] = Hp
+        A[..., 6:9, 9:12] = E
+        A[..., 9:12, 9:12] = Sp
         Bm = torch.zeros((B, N, n, m), dtype=f32, device=dev)
-        Bm[..., 3:6, :] = r[..., 0:3, 3:4]
+        Bm[..., 3:6, :] = d[..., None]
         tr = [dt * p.phys[4] / p.phys[1], dt * p.phys[4] / p.phys[2], dt * p.phys[6] / p.phys[3]]
         sg = torch.tensor([[-1, 1, 1, -1], [1, 1, -1, -1], [1, -1, 1, -1]], dtype=f32, device=dev)
         Bm[..., 9:12, :] = sg * torch.tensor(tr, dtype=f32, device=dev)[:, None]
-        lu = torch.stack([r[..., 3, 3], r[..., 4, 3], r[..., 5, 3], r[..., 6, 3]], dim=-1)
-        luu_d = torch.stack([r[..., 7, 3], r[..., 8, 3], r[..., 9, 3], r[..., 10, 3]], dim=-1)
+        lu, luu_d = r[..., 7, :], r[..., 8, :]
         Q = torch.tensor(list(p.Q), dtype=torch.float64).view(12, 12).diagonal().to(dev, f32)
         Qf = torch.tensor(list(p.Qf), dtype=torch.float64).view(12, 12).diagonal().to(dev, f32)
-        return {"A": A, "B": Bm, "lx": r[..., 12:15, :].reshape(B, N, 12), "lu": lu,
+        return {"A": A, "B": Bm, "lx": r[..., 9:12, :].reshape(B, N, 12), "lu": lu,
                 "lxx": torch.diag(2 * Q).repeat(B, N, 1, 1), "luu": torch.diag_embed(luu_d),
                 "lux": torch.zeros((B, N, m, n), dtype=f32, device=dev),
                 "VxN": self.terminal.view(B, 16)[:, :12], "VxxN": torch.diag(2 * Qf).repeat(B, 1, 1)}
