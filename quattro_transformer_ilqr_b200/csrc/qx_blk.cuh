@@ -2,7 +2,11 @@
 // and the per-(t, b) linearisation.
 // (Tried and dropped in round 2: building the record inside the Riccati thread instead of a separate linearise launch.
 // The fused loop body is 2 500 instructions = 40 KB, past the 32 KB instruction cache: ncu showed 1.2 cycles of
-// "no instruction" stall per issued instruction and 230 us instead of 65 + 89 us for the two launches.)
+// "no instruction" stall per issued instruction and 230 us instead of 65 + 89 us for the two launches.
+// Also tried and dropped: emitting the records from the line-search rollouts (stages A and W call quad_blk_record on
+// the iterate they produce, so the next backward pass needs no linearise launch).  Bit-identical records, but the
+// rollout threads run alone on their scheduler and every instruction added to them is serial time: +73 us per
+// rollout pass against the 59 us of the stand-alone kernel, which spreads the same work over 50 x more threads.)
 #pragma once
 #include "qx_models.cuh"
 

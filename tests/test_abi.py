@@ -54,11 +54,11 @@ def test_layout_queries(lib):
 
 
 def test_block_path_queries(lib):
-    """The compact block records (QX_LAYOUT_BLK): 256 B per (t, b) in octets of trajectories, 64-B terminal; only
+    """The compact block records (QX_LAYOUT_BLK): 192 B per (t, b) in octets of trajectories, 64-B terminal; only
     the quadrotor with the Euler map and diagonal weights qualifies."""
     from quattro_transformer_ilqr_b200 import DeviceModel
-    assert lib.qx_blk_expansion_bytes(16384, 50) == 16384 * 50 * 256
-    assert lib.qx_blk_expansion_bytes(9, 50) == 16 * 50 * 256          # ragged batch: padded to whole octets
+    assert lib.qx_blk_expansion_bytes(16384, 50) == 16384 * 50 * 192
+    assert lib.qx_blk_expansion_bytes(9, 50) == 16 * 50 * 192          # ragged batch: padded to whole octets
     assert lib.qx_blk_terminal_bytes(97) == 97 * 64
     assert lib.qx_blk_expansion_bytes(0, 50) == 0
     ok = DeviceModel("quadrotor").params()
