@@ -16,12 +16,171 @@
 
 namespace qx {
 
+// ---- quadrotor, RK4: the chain rule through the four stages on 3x3 BLOCKS --------------------------------------------
+// With x = [p | v | eta | omega] the continuous Jacobian is block upper triangular,
+//        | 0  I  0   0  |           | 0      |
+//    J = | 0  0  Gc  0  |     Gu =  | dc 1^T |      (Gc, Hc, Ec, Sc, dc: the non-zero blocks of Quadrotor::fc_jac)
+//        | 0  0  Hc  Ec |           | 0      |
+//        | 0  0  0   Sc |           | Tc     |
+// and so is every D_s = d k_s / d x = J_s (I + h D_{s-1}): eight blocks, of which D_pv = I always.  The dense
+// formulation below (12x12 products on arrays that live in local memory) took 2.5 ms per launch at 16 384 trajectories
+// (50 x the Euler kernel); on blocks the same chain rule is ~1 200 FMAs per (t, b) in registers.
+__device__ __forceinline__ void quad_fc_blocks(const float* x, const float* u, const QxParams& p, float Gc[3][3],
+                                               float Hc[3][3], float Ec[3][3], float Sc[3][3], float* dc) {
+  const float mass = float(p.phys[0]), Ix = float(p.phys[1]), Iy = float(p.phys[2]), Iz = float(p.phys[3]);
+  float sphi, cphi, sth, cth, spsi, cpsi;
+  sincosf(x[6], &sphi, &cphi);
+  sincosf(x[7], &sth, &cth);
+  sincosf(x[8], &spsi, &cpsi);
+  const float pp = x[9], q = x[10], r = x[11];
+  const float Tm = (u[0] + u[1] + u[2] + u[3]) / mass, im = 1.f / mass;
+  const float sec = 1.f / cth, tth = sth * sec;
+  const float dirx = spsi * sphi + cpsi * sth * cphi;
+  const float diry = cpsi * sphi - spsi * sth * cphi;
+  const float dirz = cth * cphi;
+  Gc[0][0] = Tm * (spsi * cphi - cpsi * sth * sphi); Gc[0][1] = Tm * (cpsi * cth * cphi); Gc[0][2] = Tm * diry;
+  Gc[1][0] = Tm * (cpsi * cphi + spsi * sth * sphi); Gc[1][1] = Tm * (-spsi * cth * cphi); Gc[1][2] = -Tm * dirx;
+  Gc[2][0] = -Tm * cth * sphi; Gc[2][1] = -Tm * sth * cphi; Gc[2][2] = 0.f;
+  dc[0] = im * dirx; dc[1] = im * diry; dc[2] = im * dirz;
+  const float w = q * sphi + r * cphi, v = q * cphi - r * sphi;
+  Hc[0][0] = v * tth; Hc[0][1] = w * sec * sec; Hc[0][2] = 0.f;
+  Hc[1][0] = -w; Hc[1][1] = 0.f; Hc[1][2] = 0.f;
+  Hc[2][0] = v * sec; Hc[2][1] = w * sth * sec * sec; Hc[2][2] = 0.f;
+  Ec[0][0] = 1.f; Ec[0][1] = sphi * tth; Ec[0][2] = cphi * tth;
+  Ec[1][0] = 0.f; Ec[1][1] = cphi; Ec[1][2] = -sphi;
+  Ec[2][0] = 0.f; Ec[2][1] = sphi * sec; Ec[2][2] = cphi * sec;
+  const float c1 = (Iy - Iz) / Ix, c2 = (Iz - Ix) / Iy, c3 = (Ix - Iy) / Iz;
+  Sc[0][0] = 0.f; Sc[0][1] = c1 * r; Sc[0][2] = c1 * q;
+  Sc[1][0] = c2 * r; Sc[1][1] = 0.f; Sc[1][2] = c2 * pp;
+  Sc[2][0] = c3 * q; Sc[2][1] = c3 * pp; Sc[2][2] = 0.f;
+}
+
+// Z = X Y (3x3 times 3xC)
+template <int C>
+__device__ __forceinline__ void mul3(const float X[3][3], const float (*Y)[C], float (*Z)[C]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < C; ++j) Z[i][j] = fmaf(X[i][2], Y[2][j], fmaf(X[i][1], Y[1][j], X[i][0] * Y[0][j]));
+}
+
+__device__ __forceinline__ void quad_rk4_jacobians(const float* x, const float* u, const QxParams& p, float* A, float* Bm) {
+  constexpr int n = 12, m = 4;
+  const float dt = float(p.dt);
+  const float aix = float(p.phys[4]) / float(p.phys[1]), aiy = float(p.phys[4]) / float(p.phys[2]);
+  const float kiz = float(p.phys[6]) / float(p.phys[3]);
+  const float Tc[3][4] = {{-aix, aix, aix, -aix}, {aiy, aiy, -aiy, -aiy}, {kiz, -kiz, kiz, -kiz}};
+  // D blocks (d k_s / d x) and their weighted sums; Du blocks (d k_s / d u, 3x4 each) and theirs
+  float Dpe[3][3] = {}, Dpw[3][3] = {}, Dve[3][3] = {}, Dvw[3][3] = {}, Dee[3][3] = {}, Dew[3][3] = {}, Dww[3][3] = {};
+  float Ape[3][3] = {}, Apw[3][3] = {}, Ave[3][3] = {}, Avw[3][3] = {}, Aee[3][3] = {}, Aew[3][3] = {}, Aww[3][3] = {};
+  float Dup[3][4] = {}, Duv[3][4] = {}, Due[3][4] = {}, Duw[3][4] = {};
+  float Bp[3][4] = {}, Bv[3][4] = {}, Be[3][4] = {}, Bw[3][4] = {};
+  float k[n], xs[n];
+#pragma unroll
+  for (int i = 0; i < n; ++i) k[i] = 0.f;
+  const float wgt[4] = {1.f, 2.f, 2.f, 1.f}, cs[4] = {0.f, 0.5f, 0.5f, 1.f};
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const float h = cs[s] * dt, w = wgt[s];
+#pragma unroll
+    for (int i = 0; i < n; ++i) xs[i] = x[i] + h * k[i];
+    float Gc[3][3], Hc[3][3], Ec[3][3], Sc[3][3], dc[3];
+    quad_fc_blocks(xs, u, p, Gc, Hc, Ec, Sc, dc);
+    // rows of M = I + h D_{s-1} that J touches
+    float Tee[3][3], Tew[3][3], Tww[3][3], Npe[3][3], Npw[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        Npe[i][j] = h * Dve[i][j];
+        Npw[i][j] = h * Dvw[i][j];
+        Tee[i][j] = (i == j ? 1.f : 0.f) + h * Dee[i][j];
+        Tew[i][j] = h * Dew[i][j];
+        Tww[i][j] = (i == j ? 1.f : 0.f) + h * Dww[i][j];
+      }
+    float t1[3][3], t2[3][3];
+    mul3<3>(Gc, Tee, Dve);
+    mul3<3>(Gc, Tew, Dvw);
+    mul3<3>(Hc, Tew, t1);
+    mul3<3>(Ec, Tww, t2);
+    mul3<3>(Hc, Tee, Dee);
+    mul3<3>(Sc, Tww, Dww);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        Dew[i][j] = t1[i][j] + t2[i][j];
+        Dpe[i][j] = Npe[i][j];
+        Dpw[i][j] = Npw[i][j];
+        Ape[i][j] += w * Dpe[i][j]; Apw[i][j] += w * Dpw[i][j];
+        Ave[i][j] += w * Dve[i][j]; Avw[i][j] += w * Dvw[i][j];
+        Aee[i][j] += w * Dee[i][j]; Aew[i][j] += w * Dew[i][j];
+        Aww[i][j] += w * Dww[i][j];
+      }
+    // d k_s / d u = J_s (h D_{s-1,u}) + Gu
+    float He[3][4], Hw[3][4], u1[3][4], u2[3][4], u3[3][4], u4[3][4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        He[i][j] = h * Due[i][j];
+        Hw[i][j] = h * Duw[i][j];
+        Dup[i][j] = h * Duv[i][j];
+      }
+    mul3<4>(Gc, He, u1);
+    mul3<4>(Hc, He, u2);
+    mul3<4>(Ec, Hw, u3);
+    mul3<4>(Sc, Hw, u4);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        Duv[i][j] = u1[i][j] + dc[i];
+        Due[i][j] = u2[i][j] + u3[i][j];
+        Duw[i][j] = u4[i][j] + Tc[i][j];
+        Bp[i][j] += w * Dup[i][j]; Bv[i][j] += w * Duv[i][j];
+        Be[i][j] += w * Due[i][j]; Bw[i][j] += w * Duw[i][j];
+      }
+    Quadrotor::fc<float>(xs, u, p, k);
+  }
+  const float s6 = dt / 6.f;
+#pragma unroll
+  for (int i = 0; i < n * n; ++i) A[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < n; ++i) A[i * n + i] = 1.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    A[i * n + 3 + i] = s6 * 6.f;                        // D_pv = I in every stage
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      A[i * n + 6 + j] = s6 * Ape[i][j];
+      A[i * n + 9 + j] = s6 * Apw[i][j];
+      A[(3 + i) * n + 6 + j] = s6 * Ave[i][j];
+      A[(3 + i) * n + 9 + j] = s6 * Avw[i][j];
+      A[(6 + i) * n + 6 + j] = (i == j ? 1.f : 0.f) + s6 * Aee[i][j];
+      A[(6 + i) * n + 9 + j] = s6 * Aew[i][j];
+      A[(9 + i) * n + 9 + j] = (i == j ? 1.f : 0.f) + s6 * Aww[i][j];
+    }
+#pragma unroll
+    for (int j = 0; j < m; ++j) {
+      Bm[i * m + j] = s6 * Bp[i][j];
+      Bm[(3 + i) * m + j] = s6 * Bv[i][j];
+      Bm[(6 + i) * m + j] = s6 * Be[i][j];
+      Bm[(9 + i) * m + j] = s6 * Bw[i][j];
+    }
+  }
+}
+
 // A = d f / d x, Bm = d f / d u of the DISCRETE map, row-major, in float.
 template <class Mdl, int INTEG>
 __device__ __forceinline__ void discrete_jacobians(const float* x, const float* u, const QxParams& p, float* A,
                                                    float* Bm) {
   constexpr int n = Mdl::n, m = Mdl::m;
   const float dt = float(p.dt);
+  if (INTEG == QX_RK4 && Mdl::id == QX_MODEL_QUADROTOR) {
+    quad_rk4_jacobians(x, u, p, A, Bm);
+    return;
+  }
   if (INTEG == QX_EULER) {
     Mdl::template fc_jac<float>(x, u, p, A, Bm);
 #pragma unroll
