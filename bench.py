@@ -266,8 +266,8 @@ def gpu_bench(args):
         while done < k:
             if state["i"] % RESET_EVERY == 0:
                 eng.set_problem(x0_d, u0_d)
-            # classic mode: two iterations per CUDA-graph replay where the step count and the reset cadence allow it
-            if tf is None and args.graph and done + 2 <= k and state["i"] % RESET_EVERY <= RESET_EVERY - 2:
+            # two iterations per CUDA-graph replay where the step count and the reset cadence allow it
+            if args.graph and done + 2 <= k and state["i"] % RESET_EVERY <= RESET_EVERY - 2:
                 eng.iterate_pair(tol, force=True)
                 state["i"] += 2
                 done += 2
@@ -283,7 +283,7 @@ def gpu_bench(args):
 
     state = {"i": 0}
     run_steps(args.warmup, state)
-    if tf is None and args.graph:
+    if args.graph:
         # capture the iteration-pair graphs for both buffer parities now, whatever W was: a capture costs milliseconds
         # and must not land inside the timed region
         for parity in (0, 1):
@@ -495,7 +495,7 @@ def gpu_bench(args):
                                f"fixed-iteration mode, problem reset every {RESET_EVERY} steps",
                    "global_batch": world * B, "parallelism": f"dp{world} (independent trajectory shards)",
                    "backward_pass": "block records (48 floats per step)" if eng.exp_layout == 2 else "dense records",
-                   "launch": "two iterations per CUDA-graph replay" if (tf is None and args.graph) else "one launch per kernel",
+                   "launch": "two iterations per CUDA-graph replay" if args.graph else "one launch per kernel",
                    "l2": "working set per iteration (x, u ping-pong 0.21 GB + expansion 0.21 GB + gains 0.17 GB at 16 384 "
                          "trajectories) larger than the 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "trajectory-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -207,18 +207,16 @@ class BatchedILQR:
 
     @_on_device
     def iterate_pair(self, tol=1e-3, force=False):
-        """Two iterations replayed as ONE CUDA graph (classic mode): the 14 launches of a pair - linearise, Riccati and
-        the five line-search stages, twice - go out in one call, which removes ~2 % of launch gaps at 16 384
-        trajectories (tools/graph_probe.py).  A pair, because the iterate ping-pongs between two buffer sets and a
+        """Two iterations replayed as ONE CUDA graph: the launches of a pair - linearise, Riccati, [the transformer
+        forward,] the line-search stages, twice - go out in one call, which removes the launch gaps (~2 % of the classic
+        iteration at 16 384 trajectories, tools/graph_probe.py; 1-3 % in transformer mode, tools/tf_graph_probe.py).  A pair, because the iterate ping-pongs between two buffer sets and a
         graph bakes the pointers in: after two iterations the roles are back where the capture found them.  Graphs
         are cached per (buffer parity, tol, force, model parameters); the first call with a new key runs plainly
         (and warms the kernels up), the second captures.  Results are those of two ``iterate`` calls, bit for bit."""
-        if self.tf is not None:
-            self.iterate(tol, force)
-            self.iterate(tol, force)
-            return
         graphs = self.__dict__.setdefault("_pair_graphs", {})
-        key = (self.cur, float(tol), bool(force), bytes(self.params), self.exp_layout)
+        # transformer mode: the forward's launches bake in the weight, shift and workspace buffers and the path switches
+        tf_key = None if self.tf is None else self.tf.graph_key(self)
+        key = (self.cur, float(tol), bool(force), bytes(self.params), self.exp_layout, tf_key)
         state = graphs.get(key)
         if state is None:
             graphs[key] = False

@@ -177,6 +177,20 @@ class TransformerILQR:
         """x_seq_err = x_seq + shift, shift = state_offset - x_ref (quattro_ilqr_tf.py:504/:532)."""
         self._shift = torch.as_tensor(np.asarray(shift, dtype=np.float64), device=device)
 
+    def graph_key(self, engine):
+        """What a captured ``forward_device`` launch sequence depends on besides the engine's own buffers: the weight
+        and split buffers, the state shift, the activations workspace and the kernel-path switches (read from the
+        environment per call).  ``BatchedILQR.iterate_pair`` keys its CUDA graphs on it."""
+        packed = self._packed
+        shift = getattr(engine, "_tf_shift", None)
+        if shift is None:
+            shift = self._shift
+        ws = getattr(engine, "_tf_ws", None)
+        env = tuple(os.environ.get(k, "") for k in ("QX_TF_FUSE_LN", "QX_TF_NO_PRUNE", "QX_TF_GEMM_STREAM", "QX_TF_GEMM_VARIANT",
+                                                     "QX_TF_ATTN_PAIR", "QX_TF_ATTN_MMA", "QX_TF_ATTN_DBG", "QX_TF_GEMM_DBG"))
+        return (id(self), bool(self.tensor_cores), None if packed is None else (packed[1].data_ptr(), packed[2].data_ptr()),
+                None if shift is None else shift.data_ptr(), None if ws is None else ws.data_ptr(), env)
+
     def forward_device(self, engine):
         """Predict gains for t < target_len from the engine's current trajectories and the Riccati
         tail already in ``engine.gains``; writes the predicted records into ``engine.gains``."""

@@ -664,3 +664,34 @@ def test_engine_on_a_device_that_is_not_current():
         e.solve(fixed_iters=3)
     torch.cuda.synchronize(0); torch.cuda.synchronize(1)
     assert torch.equal(a.cost.cpu(), b.cost.cpu()) and torch.equal(a.u_batch().cpu(), b.u_batch().cpu())
+
+
+@pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
+def test_graph_replayed_pairs_in_transformer_mode(system):
+    """iterate_pair with a transformer wrapper: the forward's launches (tensor maps passed by value) are captured with the
+    rest of the iteration; replays must equal plain iterations bit for bit, and a changed state shift must not replay a
+    graph that baked the old one in."""
+    from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel
+    B, N = 96, HORIZON[system]
+    m = 4 if system == "quadrotor" else 1
+    tf = _wrapper(system, "rand")
+    x0 = sample_x0(system, B, seed=33)
+    u0 = np.zeros((B, N, m))
+    a = BatchedILQR(DeviceModel(system), B, N, tf=tf)
+    b = BatchedILQR(DeviceModel(system), B, N, tf=tf)
+    for e in (a, b):
+        e.set_problem(x0, u0)
+    for _ in range(3):                  # plain, capture, replay
+        a.iterate_pair(TOL[system], force=True)
+    for _ in range(6):
+        b.iterate(TOL[system], force=True)
+    torch.cuda.synchronize()
+    assert a.launches == b.launches and torch.equal(a.cost, b.cost) and torch.equal(a.u[a.cur], b.u[b.cur])
+    shift = torch.full((a.n,), 0.01, dtype=torch.float64, device=a.device)
+    a._tf_shift, b._tf_shift = shift, shift.clone()
+    for _ in range(3):
+        a.iterate_pair(TOL[system], force=True)
+    for _ in range(6):
+        b.iterate(TOL[system], force=True)
+    torch.cuda.synchronize()
+    assert torch.equal(a.cost, b.cost) and torch.equal(a.u[a.cur], b.u[b.cur])
