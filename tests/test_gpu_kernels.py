@@ -521,3 +521,34 @@ def test_gain_record_layout_round_trip():
     for (t, ch, b) in [(0, 0, 0), (3, 2, 5), (49, 51, 36), (17, 4, 1), (17, 7, 1)]:
         want = k[b, t, ch] if ch < 4 else K[b, t].reshape(-1)[ch - 4]
         assert flat[((t * 13 + ch // 4) * B + b) * 4 + ch % 4] == want
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 5, 64])
+@pytest.mark.parametrize("system", ["quadrotor", "cartpole"])
+def test_short_and_long_horizons(system, N):
+    """Horizon edge cases of the staged kernels (two-deep cp.async staging, one record in flight in the Riccati
+    thread): N = 1, 2, 3 leave the prefetch pipelines partly empty; N = 64 is longer than any shipped configuration.
+    Every kernel against the oracle on the same inputs (a whole solve is no test here: with two or three steps the
+    problem is solved after one iteration and the next accept tests are decided by fp32 round-off of the gains)."""
+    from quattro_transformer_ilqr_b200 import BatchedILQR, DeviceModel
+    B = 67
+    model = make_model(system)
+    rng = np.random.default_rng(N)
+    x0 = sample_x0(system, B, seed=N)
+    u = (0.3 * rng.standard_normal((B, N, model.m)) + (2.45 if system == "quadrotor" else 0.0))
+    e = BatchedILQR(DeviceModel(system), B, N)
+    e.set_problem(x0, u)
+    x_ref, c_ref = ob.rollout(model, x0, u)
+    assert relmax(e.cost.cpu().numpy(), c_ref) < 1e-12 and relmax(e.x_batch().cpu().numpy(), x_ref) < 1e-12
+    K_ref, k_ref = ob.riccati(ob.linearize(model, x_ref, u))
+    e.backward()
+    K, k = (t.cpu().numpy() for t in e.gains_batch())
+    assert relmax(K, K_ref) < 1e-5 and relmax(k, k_ref) < 1e-5
+    scale = rng.choice([1.0, 4.0, -1.0], size=B, p=[0.5, 0.3, 0.2])      # some spoiled gains: smaller alphas, rejections
+    Kf, kf = K_ref.astype(np.float32), (k_ref * scale[:, None, None]).astype(np.float32)
+    e.load_gains(Kf, kf)
+    e.linesearch(tol=1e-3)
+    xn, un, cn, idx, _ = ob.line_search(model, x_ref, u, Kf.astype(np.float64), kf.astype(np.float64), c_ref)
+    assert np.array_equal(e.alpha.cpu().numpy(), idx)
+    assert relmax(e.cost.cpu().numpy(), cn) < 1e-12 and relmax(e.u_batch().cpu().numpy(), un) < 1e-11
+    assert relmax(e.x_batch().cpu().numpy(), xn) < 1e-11
