@@ -4,7 +4,7 @@ set -euo pipefail
 cd "$(dirname "$0")"
 OUT=../libquattro_sm100a.so
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr ${QX_EXTRA_NVCC_FLAGS:-}"      # e.g. -DQX_ATTN_TRACE for the phase timer of qx_tf_attn05.cu
 SRCS=$(ls *.cu)
 mkdir -p build
 rm -f build/*.o          # stale objects of deleted sources must not be linked

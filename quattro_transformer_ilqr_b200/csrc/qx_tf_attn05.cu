@@ -21,6 +21,7 @@
 // The steps of one item are serial inside a CTA (two __syncthreads and four mbarriers), so TWO CTAs share an SM
 // (112 KB of shared memory and 256 TMEM columns each): one does its softmax on the CUDA cores while the other's
 // MMAs run.  The next item's Q/K tiles are requested as soon as S is done, its V tile as soon as O is done.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "qx_tc05.cuh"
@@ -35,12 +36,26 @@ constexpr int kMaxKeys = 112;              // TMEM budget: S/P_hi [0,112) | P_lo
 constexpr int kTile = kRows * kHd;         // floats per tile (16 KB)
 constexpr uint32_t kColPlo = kMaxKeys, kColO = 2 * kMaxKeys;
 
-struct AttnSmem {
-  float q_hi[kTile], q_lo[kTile], k_hi[kTile], k_lo[kTile], v_hi[kTile], v_lo[kTile];
-  float4 stage[4][32][8];                  // per warp: 32 rows x 32 dims in the TMA 128-B swizzle layout
-  uint64_t bar_qk, bar_v, bar_s, bar_o;
+// One trajectory per tile: K and V are boxes of kMaxKeys = 112 token rows, which buys a landing tile of its own for V:
+// the next item's V is requested as soon as this item's has been split, a whole item ahead of its use.  (With V landing
+// in v_hi its request had to wait for the item's P V product, and the TMA latency sat on every item's critical path.)
+// The epilogue's staging chunks (quarter w: 32 rows x 128 B in the TMA swizzle layout) then no longer fit next to the
+// tiles: they ARE rows 32 w .. 32 w + 31 of v_hi, free between the item's P V product and the next item's V split -
+// which the same two warps perform on exactly these rows, after the lane that issued the store has seen it read (v_hi
+// keeps 128 rows for that: rows 112-127 are staging only).
+// PAIR: 128-row tiles, V lands in v_hi and the staging chunks are their own.
+template <bool PAIR>
+struct AttnSmemT {
+  static constexpr int kKeyRows = PAIR ? kRows : kMaxKeys;
+  float q_hi[kTile], q_lo[kTile], k_hi[kKeyRows * kHd], k_lo[kKeyRows * kHd], v_hi[kTile], v_lo[kKeyRows * kHd];
+  float4 stage[PAIR ? 4 : 1][32][8];       // PAIR: per quarter 32 rows x 32 dims in the TMA 128-B swizzle layout
+  float v_raw[PAIR ? 4 : kKeyRows * kHd];
+  float pmax[PAIR ? 4 : 256], psum[PAIR ? 4 : 256];   // the two threads of a row exchange their partial maximum / sum
+  uint64_t bar_qk, bar_v, bar_s, bar_o, bar_vfree;
   uint32_t tmem_base;
 };
+static_assert(2 * (sizeof(AttnSmemT<false>) + 1024) <= 228 * 1024 && 2 * (sizeof(AttnSmemT<true>) + 1024) <= 228 * 1024,
+              "two attention CTAs must fit the shared memory of an SM");
 
 // instruction descriptors: D = F32, A = B = TF32, M = 128; N and the B major differ
 constexpr uint32_t idesc_tf32(int n, bool b_mn_major) {
@@ -108,6 +123,25 @@ __device__ __forceinline__ void split_tile_row(float* hi_tile, float* lo_tile, i
   for (int jj = 0; jj < 4; ++jj) {
     const int c = (4 * half + jj) ^ (row & 7);
     const float4 v = hi4[c];
+    float4 h, l;
+    tf32_split(v.x, h.x, l.x);
+    tf32_split(v.y, h.y, l.y);
+    tf32_split(v.z, h.z, l.z);
+    tf32_split(v.w, h.w, l.w);
+    hi4[c] = h;
+    lo4[c] = l;
+  }
+}
+
+// The same from a landing tile of its own: raw -> (hi, lo)
+__device__ __forceinline__ void split_raw_row(const float* raw_tile, float* hi_tile, float* lo_tile, int row, int half) {
+  const float4* raw4 = reinterpret_cast<const float4*>(raw_tile) + row * 8;
+  float4* hi4 = reinterpret_cast<float4*>(hi_tile) + row * 8;
+  float4* lo4 = reinterpret_cast<float4*>(lo_tile) + row * 8;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const int c = (4 * half + jj) ^ (row & 7);
+    const float4 v = raw4[c];
     float4 h, l;
     tf32_split(v.x, h.x, l.x);
     tf32_split(v.y, h.y, l.y);
@@ -274,20 +308,37 @@ __device__ __forceinline__ void chunk_zero(uint32_t tmem_row, int col0) {
   TmemRow<HW>::st(tmem_row + kColPlo + col0, z);
 }
 
+// -DQX_ATTN_TRACE (experiments only; QX_EXTRA_NVCC_FLAGS of build.sh): CTA 0 sums the cycles each phase of an item takes
+// as seen by warp 0 (MMA / TMA issuer, quarter 0) and warp 7 (quarter 3, the longest causal rows); the launcher prints
+// them to stderr.
+#ifdef QX_ATTN_TRACE
+__device__ long long g_attn_trace[2][16];
+#define QX_TRACE_DECL long long tr_t = clock64(), tr_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define QX_TRACE(i) do { const long long tr_n = clock64(); tr_acc[i] += tr_n - tr_t; tr_t = tr_n; } while (0)
+#define QX_TRACE_DUMP do { if (blockIdx.x == 0 && (tid == 0 || tid == 224)) { for (int i = 0; i < 16; ++i) g_attn_trace[tid ? 1 : 0][i] = tr_acc[i]; } } while (0)
+#else
+#define QX_TRACE_DECL
+#define QX_TRACE(i)
+#define QX_TRACE_DUMP
+#endif
+
 }  // namespace
 
 // grid: min(B * nhead, 2 * SMs) persistent CTAs of 256 threads; item = trajectory * nhead + head.
 // Two threads per query row (warps w and w + 4 share TMEM lane quarter w % 4 and split every chunk's columns), so an
 // SM holds 16 warps: the softmax and the operand splits are latency-bound CUDA-core work and need the occupancy.
-// (Tried and dropped: reversing the row order in every second CTA so that the long causal rows of two co-resident
-// CTAs land on different schedulers - 0.65 ms against 0.59 ms without.)
+// (Tried and dropped, twice: token quarters in reverse lane order in every second CTA / in the second CTA to arrive on
+// an SM, so that the long causal rows of two co-resident CTAs do not share a lane quarter - 0.63 ms against 0.57 ms.
+// The hardware already spreads the warps of the two CTAs evenly: smsp__inst_executed differs by 3 % across the
+// schedulers (profiles/r2_ncu_full_attention_summary.txt).)
 template <bool PAIR>
 __global__ void __launch_bounds__(256, 2)
-tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmV,
-                         const __grid_constant__ CUtensorMap tmOut, float* __restrict__ out_rows, int n_items, int n_traj, int nhead, int L,
+tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmK,
+                         const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmOut, float* __restrict__ out_rows, int n_items, int n_traj, int nhead, int L,
                          int d, int row_lo, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  AttnSmem& s = *reinterpret_cast<AttnSmem*>(smem_raw);
+  using Smem = AttnSmemT<PAIR>;
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wq = warp & 3, half = warp >> 2;        // TMEM lane quarter; which half of the row's columns
   const int row = wq * 32 + lane;                   // tile row / TMEM lane of this thread
@@ -303,6 +354,7 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     mbar_init(&s.bar_v, 1);
     mbar_init(&s.bar_s, 1);
     mbar_init(&s.bar_o, 1);
+    mbar_init(&s.bar_vfree, 8);
     mbar_fence_init();
   }
   if (warp == 0) {
@@ -317,25 +369,27 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
   const uint32_t tmem_row = tmem + ((uint32_t)(wq * 32) << 16);       // this warp's lane quarter
   const float scale_log2 = rsqrtf((float)kHd) * 1.4426950408889634f;  // softmax in base 2: exp(x) = 2^(x log2 e)
 
+  QX_TRACE_DECL;
   auto load_qk = [&](int item) {
     const int b = (PAIR ? 2 : 1) * (item / nhead), h = item % nhead;
-    mbar_arrive_expect_tx(&s.bar_qk, 2 * kTile * 4);
+    mbar_arrive_expect_tx(&s.bar_qk, (kTile + Smem::kKeyRows * kHd) * 4);
     tma_load_3d(&tmQkv, &s.bar_qk, s.q_hi, h * kHd, 0, b);
-    tma_load_3d(&tmQkv, &s.bar_qk, s.k_hi, d + h * kHd, 0, b);
+    tma_load_3d(&tmK, &s.bar_qk, s.k_hi, d + h * kHd, 0, b);
   };
   auto load_v = [&](int item) {
     const int b = (PAIR ? 2 : 1) * (item / nhead), h = item % nhead;
-    mbar_arrive_expect_tx(&s.bar_v, kTile * 4);
-    tma_load_3d(&tmV, &s.bar_v, s.v_hi, 2 * d + h * kHd, 0, b);
+    mbar_arrive_expect_tx(&s.bar_v, Smem::kKeyRows * kHd * 4);
+    tma_load_3d(&tmV, &s.bar_v, PAIR ? s.v_hi : s.v_raw, 2 * d + h * kHd, 0, b);
   };
-  // The two threads of a row exchange their partial maximum / sum through the last 16 rows of the K_lo tile: the
-  // first product reads N <= 112 key rows, so those 2 KB are never an operand (and the K split leaves them alone).
-  float* const pmax = s.k_lo + kMaxKeys * kHd;
-  float* const psum = pmax + 256;
+  float* const pmax = s.pmax;
+  float* const psum = s.psum;
   auto split_qk = [&](uint32_t ph) {
     mbar_wait(&s.bar_qk, ph);
-    if (PAIR || row < kMaxKeys) split_tile_row(s.k_hi, s.k_lo, row, half);
-    split_q_row(s.q_hi, s.q_lo, row, half, scale_log2);
+    QX_TRACE(11);    // wait Q, K
+    if (!(dbg & 8)) {
+      if (PAIR || row < kMaxKeys) split_tile_row(s.k_hi, s.k_lo, row, half);
+      split_q_row(s.q_hi, s.q_lo, row, half, scale_log2);
+    }
     fence_proxy_async();
   };
   if ((int)blockIdx.x < n_items) {
@@ -354,6 +408,7 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     const int h = item % nhead;
     const int b = PAIR ? 2 * (item / nhead) + th : item / nhead;      // this row's trajectory
     const int next = item + gridDim.x;
+    QX_TRACE(10);    // loop top
 
     // ---- S = (scaled Q) K^T ---------------------------------------------------------------------------------------
     if (warp == 0) {
@@ -372,12 +427,31 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
       }
       __syncwarp();
     }
+    QX_TRACE(0);     // S issue
     // V is split while the tensor core works on S
     mbar_wait(&s.bar_v, ph);
-    split_tile_row(s.v_hi, s.v_lo, row, half);
+    QX_TRACE(1);     // wait V
+    if (PAIR) {
+      if (!(dbg & 8)) split_tile_row(s.v_hi, s.v_lo, row, half);
+    } else {
+      // v_hi / v_lo are free (every thread saw the previous item's P V complete before its epilogue) once the output
+      // store that staged in this pair's v_hi rows has read them.  The landing tile goes back to TMA when all eight warps
+      // have consumed their rows: the stores of the split depend on every load.
+      if (half == 0 && lane == 0) bulk_wait_read<0>();
+      pair_sync(wq);
+      if (row < kMaxKeys && !(dbg & 8)) split_raw_row(s.v_raw, s.v_hi, s.v_lo, row, half);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.bar_vfree);
+      if (tid == 0 && next < n_items) {
+        mbar_wait(&s.bar_vfree, ph);
+        load_v(next);
+      }
+    }
     fence_proxy_async();
+    QX_TRACE(2);     // V split (+ request of the next V)
 
     mbar_wait(&s.bar_s, ph);
+    QX_TRACE(3);     // wait S
     tcgen05_fence_after();
     if (tid == 0 && next < n_items) load_qk(next);          // Q, K tiles are free: request the next item's
     __syncwarp();                // reconverge (per-lane spins, thread 0's detour): the tcgen05.ld / st below are .sync.aligned
@@ -416,8 +490,10 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
       }
       tmem_wait_st();
     }
+    QX_TRACE(4);     // softmax
     tcgen05_fence_before();
     __syncthreads();
+    QX_TRACE(5);     // CTA barrier
     // ---- O = P V ----------------------------------------------------------------------------------------------------
     if (warp == 0) {
       tcgen05_fence_after();
@@ -450,11 +526,14 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
       }
       __syncwarp();
     }
+    QX_TRACE(12);    // O issue
     // the next item's Q, K are split while the tensor core works on O
     if (next < n_items) split_qk(ph ^ 1u);
+    QX_TRACE(6);     // split of the next Q, K
     mbar_wait(&s.bar_o, ph);
+    QX_TRACE(7);     // wait O
     tcgen05_fence_after();
-    if (tid == 0 && next < n_items) load_v(next);
+    if (PAIR && tid == 0 && next < n_items) load_v(next);
     __syncwarp();
     // ---- epilogue: each thread 16 of the row's 32 output dims -----------------------------------------------------
     const uint32_t col_o = PAIR ? kPairO + 32 * th : kColO;
@@ -465,14 +544,16 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
       }
       return psum[tid & 127] + psum[(tid & 127) + 128];
     };
-    if (active && row_lo == 0) {
+    if (active && row_lo == 0 && !(dbg & 16)) {
       uint32_t r[16];
       TmemRow<16>::ld(tmem_row + col_o + 16 * half, r);
-      if (half == 0 && lane == 0) bulk_wait_read<0>();       // the previous item's store has read the staging chunk
-      pair_sync(wq);
+      if (PAIR) {
+        if (half == 0 && lane == 0) bulk_wait_read<0>();     // the previous item's store has read the staging chunk
+        pair_sync(wq);
+      }
       tmem_wait_ld();
       const float inv = 1.f / row_sum();
-      float4 (*stg)[8] = s.stage[wq];
+      float4 (*stg)[8] = PAIR ? s.stage[wq] : reinterpret_cast<float4 (*)[8]>(s.v_hi + wq * 32 * kHd);
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         float4 o;
@@ -511,9 +592,12 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
         }
       }
     }
+    QX_TRACE(8);     // epilogue
     tcgen05_fence_before();      // the next item's MMAs overwrite S and O; its Q / K halves must be visible to them
     __syncthreads();
+    QX_TRACE(9);     // CTA barrier
   }
+  QX_TRACE_DUMP;
   if (half == 0 && lane == 0) bulk_wait_read<0>();
   tcgen05_fence_before();
   __syncthreads();
@@ -530,16 +614,18 @@ int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhe
   // QX_TF_ATTN_PAIR=0 keeps one trajectory per tile whatever L is (A/B runs and the equality test)
   const char* env_pair = getenv("QX_TF_ATTN_PAIR");
   const bool pair = L <= 64 && !(env_pair != nullptr && env_pair[0] == '0');
-  CUtensorMap mq, mv, mo;
+  CUtensorMap mq, mk, mv, mo;
   {
     const cuuint64_t dims[3] = {(cuuint64_t)(3 * d), (cuuint64_t)L, (cuuint64_t)B};
     const cuuint64_t strides[2] = {(cuuint64_t)(3 * d) * 4, (cuuint64_t)L * 3 * d * 4};
     const cuuint32_t box1[3] = {(cuuint32_t)kHd, (cuuint32_t)kRows, 1}, box2[3] = {(cuuint32_t)kHd, 64, 2};
-    const cuuint32_t* box = pair ? box2 : box1;
-    int rc = make_map_nd(&mq, qkv, 3, dims, strides, box);
+    const cuuint32_t boxk[3] = {(cuuint32_t)kHd, (cuuint32_t)kMaxKeys, 1};       // key / value rows of a single-trajectory tile
+    int rc = make_map_nd(&mq, qkv, 3, dims, strides, pair ? box2 : box1);
+    if (rc) return rc;
+    rc = make_map_nd(&mk, qkv, 3, dims, strides, pair ? box2 : boxk);
     if (rc) return rc;
     // V is an MN-major operand of the second product: 32-B swizzle atoms (see umma_desc_mn_sw128_32b)
-    rc = make_map_nd(&mv, qkv, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    rc = make_map_nd(&mv, qkv, 3, dims, strides, pair ? box2 : boxk, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   }
   {
@@ -552,19 +638,32 @@ int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhe
   }
   static bool cfg[kMaxDevices] = {};
   if (!cfg[current_device_slot()]) {
-    cudaFuncSetAttribute(tf_attention_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmem));
-    cudaFuncSetAttribute(tf_attention_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmem));
+    cudaFuncSetAttribute(tf_attention_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmemT<false>));
+    cudaFuncSetAttribute(tf_attention_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmemT<true>));
     cfg[current_device_slot()] = true;
   }
   const int num_sms = device_sm_count();
   const int n_items = (pair ? (B + 1) / 2 : B) * nhead;
-  // QX_TF_ATTN_DBG (timing experiments only, results are then wrong on purpose): bit 1 no P V MMAs, bit 2 no softmax
+  // QX_TF_ATTN_DBG (timing experiments only, results are then wrong on purpose): bit 1 no P V MMAs, bit 2 no softmax,
+  // bit 3 no operand splits, bit 4 no epilogue
   const char* env_dbg = getenv("QX_TF_ATTN_DBG");
   const int dbg = env_dbg ? atoi(env_dbg) : 0;
   const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;
-  if (pair) tf_attention_umma_kernel<true><<<grid, 256, sizeof(AttnSmem), st>>>(mq, mv, mo, out, n_items, B, nhead, L, d, row_lo, dbg);
-  else tf_attention_umma_kernel<false><<<grid, 256, sizeof(AttnSmem), st>>>(mq, mv, mo, out, n_items, B, nhead, L, d, row_lo, dbg);
+  if (pair) tf_attention_umma_kernel<true><<<grid, 256, sizeof(AttnSmemT<true>), st>>>(mq, mk, mv, mo, out, n_items, B, nhead, L, d, row_lo, dbg);
+  else tf_attention_umma_kernel<false><<<grid, 256, sizeof(AttnSmemT<false>), st>>>(mq, mk, mv, mo, out, n_items, B, nhead, L, d, row_lo, dbg);
   QX_CHECK_LAUNCH("tf_attention_umma_kernel");
+#ifdef QX_ATTN_TRACE
+  {
+    static const char* names[13] = {"S issue", "wait V", "V split", "wait S", "softmax", "barrier", "next Q,K split", "wait O", "epilogue", "barrier",
+                                    "loop top", "wait next Q,K", "O issue"};
+    long long h[2][16];
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(h, g_attn_trace, sizeof(h));
+    const int per_cta = (n_items + grid - 1) / grid;
+    for (int i = 0; i < 13; ++i)
+      fprintf(stderr, "attn trace %-20s warp 0: %8.1f  warp 7: %8.1f cycles / item\n", names[i], (double)h[0][i] / per_cta, (double)h[1][i] / per_cta);
+  }
+#endif
   return QX_OK;
 }
 

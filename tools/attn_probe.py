@@ -70,7 +70,7 @@ def main():
             got = out[: args.check * L].double()
             err = (got - ref).abs()
         print(f"impl {impl}: max abs err {err.max().item():.3e} (ref max {ref.abs().max().item():.3f}), nan count {int(torch.isnan(out).sum())}")
-        if err.max().item() > 1e-4 or torch.isnan(out).any():
+        if not dbg and (err.max().item() > 1e-4 or torch.isnan(out).any()):
             e = err.view(args.check, L, H, 32)
             print("  err by head       :", [f"{e[:, :, h].max().item():.2e}" for h in range(H)])
             print("  err by row block  :", [f"{e[:, r:r + 16].max().item():.2e}" for r in range(0, L, 16)])
