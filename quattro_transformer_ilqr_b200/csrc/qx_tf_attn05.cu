@@ -35,6 +35,7 @@ constexpr int kRows = 128;                 // UMMA M: query rows (and key rows o
 constexpr int kMaxKeys = 112;              // TMEM budget: S/P_hi [0,112) | P_lo [112,224) | O [224,256)
 constexpr int kTile = kRows * kHd;         // floats per tile (16 KB)
 constexpr uint32_t kColPlo = kMaxKeys, kColO = 2 * kMaxKeys;
+constexpr uint32_t kColQ = kColPlo;            // Q_hi [112,144) | Q_lo [144,176) while S is computed: P_lo is written after it
 
 // One trajectory per tile: K and V are boxes of kMaxKeys = 112 token rows, which buys a landing tile of its own for V:
 // the next item's V is requested as soon as this item's has been split, a whole item ahead of its use.  (With V landing
@@ -47,7 +48,8 @@ constexpr uint32_t kColPlo = kMaxKeys, kColO = 2 * kMaxKeys;
 template <bool PAIR>
 struct AttnSmemT {
   static constexpr int kKeyRows = PAIR ? kRows : kMaxKeys;
-  float q_hi[kTile], q_lo[kTile], k_hi[kKeyRows * kHd], k_lo[kKeyRows * kHd], v_hi[kTile], v_lo[kKeyRows * kHd];
+  float q_hi[kTile], q_lo[PAIR ? kTile : 256];   // single trajectory: q_hi is the landing tile only, the halves of Q live in TMEM
+  float k_hi[kKeyRows * kHd], k_lo[kKeyRows * kHd], v_hi[kTile], v_lo[kKeyRows * kHd];
   float4 stage[PAIR ? 4 : 1][32][8];       // PAIR: per quarter 32 rows x 32 dims in the TMA 128-B swizzle layout
   float v_raw[PAIR ? 4 : kKeyRows * kHd];
   float pmax[PAIR ? 4 : 256], psum[PAIR ? 4 : 256];   // the two threads of a row exchange their partial maximum / sum
@@ -388,9 +390,30 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     QX_TRACE(11);    // wait Q, K
     if (!(dbg & 8)) {
       if (PAIR || row < kMaxKeys) split_tile_row(s.k_hi, s.k_lo, row, half);
-      split_q_row(s.q_hi, s.q_lo, row, half, scale_log2);
+      if (PAIR) split_q_row(s.q_hi, s.q_lo, row, half, scale_log2);
     }
     fence_proxy_async();
+  };
+  // Single trajectory: Q is the A operand of the first product FROM TENSOR MEMORY (lane = query row, column = dim): an
+  // M128 N112 K8 product with both operands in shared memory reads 7.5 KB in its 56 cycles - more than the 128 B/clk an
+  // SM has, while the V split of this CTA and whatever the other CTA does want the same banks.  The halves sit in the
+  // columns of P_lo, which is dead from the end of one item's P V product to the end of the next item's S.
+  auto split_q_tmem = [&]() {
+    const float4* src = reinterpret_cast<const float4*>(s.q_hi) + row * 8;
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const float4 v = src[(4 * half + jj) ^ (row & 7)];
+      float h, l;
+      tf32_split(v.x * scale_log2, h, l); hi[4 * jj + 0] = __float_as_uint(h); lo[4 * jj + 0] = __float_as_uint(l);
+      tf32_split(v.y * scale_log2, h, l); hi[4 * jj + 1] = __float_as_uint(h); lo[4 * jj + 1] = __float_as_uint(l);
+      tf32_split(v.z * scale_log2, h, l); hi[4 * jj + 2] = __float_as_uint(h); lo[4 * jj + 2] = __float_as_uint(l);
+      tf32_split(v.w * scale_log2, h, l); hi[4 * jj + 3] = __float_as_uint(h); lo[4 * jj + 3] = __float_as_uint(l);
+    }
+    __syncwarp();        // reconverge after the per-lane spins: tcgen05.st / wait::st are .sync.aligned
+    TmemRow<16>::st(tmem_row + kColQ + 16 * half, hi);
+    TmemRow<16>::st(tmem_row + kColQ + kHd + 16 * half, lo);
+    tmem_wait_st();
   };
   if ((int)blockIdx.x < n_items) {
     if (tid == 0) {
@@ -398,6 +421,7 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
       load_v(blockIdx.x);
     }
     split_qk(0);
+    if (!PAIR) split_q_tmem();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -415,13 +439,20 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
       tcgen05_fence_after();
       const uint64_t dq_hi = umma_desc_sw128(s.q_hi), dq_lo = umma_desc_sw128(s.q_lo);
       const uint64_t dk_hi = umma_desc_sw128(s.k_hi), dk_lo = umma_desc_sw128(s.k_lo);
+      const uint32_t aq_hi = tmem + kColQ, aq_lo = aq_hi + kHd;
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < kHd / 8; ++k) {
           const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
-          mma_tf32(tmem, dq_lo + adv, dk_hi + adv, idesc_s, k ? 1u : 0u);
-          mma_tf32(tmem, dq_hi + adv, dk_lo + adv, idesc_s, 1u);
-          mma_tf32(tmem, dq_hi + adv, dk_hi + adv, idesc_s, 1u);
+          if (PAIR) {
+            mma_tf32(tmem, dq_lo + adv, dk_hi + adv, idesc_s, k ? 1u : 0u);
+            mma_tf32(tmem, dq_hi + adv, dk_lo + adv, idesc_s, 1u);
+            mma_tf32(tmem, dq_hi + adv, dk_hi + adv, idesc_s, 1u);
+          } else {
+            mma_tf32_ta(tmem, aq_lo + 8 * k, dk_hi + adv, idesc_s, k ? 1u : 0u);
+            mma_tf32_ta(tmem, aq_hi + 8 * k, dk_lo + adv, idesc_s, 1u);
+            mma_tf32_ta(tmem, aq_hi + 8 * k, dk_hi + adv, idesc_s, 1u);
+          }
         }
         tcgen05_commit(&s.bar_s);
       }
@@ -533,6 +564,7 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     mbar_wait(&s.bar_o, ph);
     QX_TRACE(7);     // wait O
     tcgen05_fence_after();
+    if (!PAIR && next < n_items && !(dbg & 8)) split_q_tmem();     // P_lo is dead: the next item's Q halves move in
     if (PAIR && tid == 0 && next < n_items) load_v(next);
     __syncwarp();
     // ---- epilogue: each thread 16 of the row's 32 output dims -----------------------------------------------------
