@@ -373,15 +373,16 @@ static int gemm(const float* A, const float* W, const float* bias, float* C, int
 int tf_attention_tc(const float* qkv, float* out, int B, int L, int d, int nhead, cudaStream_t st);   // qx_tf_attn.cu
 int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhead, int row_lo, cudaStream_t st); // qx_tf_attn05.cu
 int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* bias, float* C, int M, int N, int K,
-               bool relu, cudaStream_t st);
-int tf_split_weights(const float* w, float* hi, float* lo, size_t count, cudaStream_t st);
+               bool relu, cudaStream_t st, bool f16);
+int tf_split_weights(const float* w, float* hi, float* lo, size_t count, cudaStream_t st, bool f16);
 int tf_gemm_ln_tc(const float* A, const float* Whi, const float* Wlo, const float* bias, const float* res, const float* gamma,
-                  const float* beta, float* C, int M, int K, cudaStream_t st);
+                  const float* beta, float* C, int M, int K, cudaStream_t st, bool f16);
 
 // offsets of the (hi, lo) copies of the four GEMM weights of one layer inside the split buffer
 struct SplitLayout {
   size_t in_hi, in_lo, out_hi, out_lo, w1_hi, w1_lo, w2_hi, w2_lo, stride;
-  size_t head_pad, head_hi, head_lo, head_bias, total;     // after the per-layer blocks
+  size_t head_pad, head_hi, head_lo, head_bias, total32;   // after the per-layer blocks
+  size_t total;        // the fp16 halves of the weight at float offset X sit at float offset total32 + X / 2
   explicit SplitLayout(const TfLayout& l) {
     const size_t d = l.d, ff = l.ff;
     size_t o = 0;
@@ -392,9 +393,22 @@ struct SplitLayout {
     stride = o;
     size_t g = stride * l.layers;
     head_pad = g; g += 128 * d; head_hi = g; g += 128 * d; head_lo = g; g += 128 * d; head_bias = g; g += 128;
-    total = g;
+    total32 = g;
+    total = total32 + (total32 + 1) / 2;
   }
 };
+// QX_TF_GEMM_F16=0: the dense layers of the forward pass run on the TF32 split (the standalone operators always do);
+// so does QX_TF_GEMM_STREAM=1, the first-generation kernel has no fp16 variant.  Read per call, like the other switches.
+// QX_TF_DENSE_F16=1 (experiments, tools/gemm_probe.py): the standalone operators use the fp16 split as well
+static bool tf_ops_f16() {
+  const char* e = getenv("QX_TF_DENSE_F16");
+  return e != nullptr && e[0] == '1';
+}
+static bool tf_use_f16() {
+  const char* e = getenv("QX_TF_GEMM_F16");
+  const char* s1 = getenv("QX_TF_GEMM_STREAM");
+  return !(e != nullptr && e[0] == '0') && !(s1 != nullptr && s1[0] == '1');
+}
 
 int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, const double* x, const double* x_shift,
                     float* gains, int layout, const int32_t* status, float* ws, int B, cudaStream_t st) {
@@ -425,12 +439,15 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
     att_cfg[current_device_slot()] = true;
   }
   const SplitLayout sp(lay);
-  // dense contraction: tcgen05 3xTF32 when split weights are supplied, exact-fp32 CUDA cores otherwise
+  const bool f16 = tf_use_f16();
+  // the (hi, lo) halves the tensor-core kernels read for the weight whose TF32 halves sit at p: p itself, or its fp16 twin
+  auto wh = [&](const float* p) -> const float* { return f16 ? wsplit + sp.total32 + (size_t)(p - wsplit) / 2 : p; };
+  // dense contraction: tcgen05 three-term split when split weights are supplied, exact-fp32 CUDA cores otherwise
   auto dense = [&](const float* A, const float* lw, size_t w_off, size_t b_off, size_t hi_off, size_t lo_off, int l,
                    float* C, int N, int K, bool relu) -> int {
     if (wsplit != nullptr) {
       const float* sw = wsplit + (size_t)l * sp.stride;
-      return tf_gemm_tc(A, sw + hi_off, sw + lo_off, lw + b_off, C, rows, N, K, relu, st);
+      return tf_gemm_tc(A, wh(sw + hi_off), wh(sw + lo_off), lw + b_off, C, rows, N, K, relu, st, f16);
     }
     return gemm(A, lw + w_off, lw + b_off, C, rows, N, K, relu, st);
   };
@@ -479,9 +496,9 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
                         size_t g_off, size_t be_off, float* out, int m_rows, int per, int src_per, int src_off) -> int {
       int rc = QX_EUNSUPPORTED;
       if (fused && per == m_rows && src_off == 0)      // gathered residual rows (pruned norm1) are not a TMA box
-        rc = tf_gemm_ln_tc(A, sw + hi_off, sw + lo_off, lw + b_off, res, lw + g_off, lw + be_off, out, m_rows, K, st);
+        rc = tf_gemm_ln_tc(A, wh(sw + hi_off), wh(sw + lo_off), lw + b_off, res, lw + g_off, lw + be_off, out, m_rows, K, st, f16);
       if (rc != QX_EUNSUPPORTED) return rc;
-      if (wsplit != nullptr) rc = tf_gemm_tc(A, sw + hi_off, sw + lo_off, lw + b_off, y, m_rows, d, K, false, st);
+      if (wsplit != nullptr) rc = tf_gemm_tc(A, wh(sw + hi_off), wh(sw + lo_off), lw + b_off, y, m_rows, d, K, false, st, f16);
       else rc = gemm(A, lw + w_off, lw + b_off, y, m_rows, d, K, false, st);
       if (rc) return rc;
       tf_add_ln_kernel<<<ceil_div(m_rows, 8), 256, 0, st>>>(out, res, y, lw + g_off, lw + be_off, m_rows, per, src_per, src_off);
@@ -495,7 +512,7 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
       if ((rc = dense_ln(fuse & 1, att, lay.l_outw, lay.l_outb, sp.out_hi, sp.out_lo, d, h, lay.l_n1w, lay.l_n1b, hc, rows_c, lay.T, L,
                          L - lay.T)))
         return rc;
-      if ((rc = tf_gemm_tc(hc, sw + sp.w1_hi, sw + sp.w1_lo, lw + lay.l_b1, ffh, rows_c, ff, d, true, st))) return rc;
+      if ((rc = tf_gemm_tc(hc, wh(sw + sp.w1_hi), wh(sw + sp.w1_lo), lw + lay.l_b1, ffh, rows_c, ff, d, true, st, f16))) return rc;
       if ((rc = dense_ln(fuse & 2, ffh, lay.l_w2, lay.l_b2, sp.w2_hi, sp.w2_lo, ff, hc, lay.l_n2w, lay.l_n2b, hc, rows_c, rows_c, rows_c, 0)))
         return rc;
       hfinal = hc;
@@ -509,8 +526,8 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
   }
   dim3 go(lay.T, B);
   if (wsplit != nullptr) {      // output head as one more tensor-core GEMM (N padded to 128) over the rows that are left
-    int rc = tf_gemm_tc(hfinal, wsplit + sp.head_hi, wsplit + sp.head_lo, wsplit + sp.head_bias, y, pruned ? rows_c : rows, 128, d,
-                        false, st);
+    int rc = tf_gemm_tc(hfinal, wh(wsplit + sp.head_hi), wh(wsplit + sp.head_lo), wsplit + sp.head_bias, y, pruned ? rows_c : rows, 128, d,
+                        false, st, f16);
     if (rc) return rc;
     if (per_traj) {
       if (layout == QX_LAYOUT_REC) tf_unpack128_kernel<QX_LAYOUT_REC><<<B, 128, 0, st>>>(*cfg, w, y, gains, status, B, pruned ? 1 : 0);
@@ -553,20 +570,27 @@ extern "C" int qx_tf_prepare(const QxTfConfig* cfg, const float* weights, float*
   const qx::SplitLayout sp(lay);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t d = lay.d, ff = lay.ff;
+  // every weight in both formats: TF32 halves at (hi, lo), fp16 halves at total32 + offset / 2
+  auto both = [&](const float* w, float* hi, float* lo, size_t count) -> int {
+    const int rc = qx::tf_split_weights(w, hi, lo, count, st, false);
+    if (rc) return rc;
+    return qx::tf_split_weights(w, wsplit + sp.total32 + (size_t)(hi - wsplit) / 2, wsplit + sp.total32 + (size_t)(lo - wsplit) / 2,
+                                count, st, true);
+  };
   for (int l = 0; l < lay.layers; ++l) {
     const float* lw = weights + lay.layer0 + (size_t)l * lay.layer_stride;
     float* sw = wsplit + (size_t)l * sp.stride;
     int rc;
-    if ((rc = qx::tf_split_weights(lw + lay.l_inw, sw + sp.in_hi, sw + sp.in_lo, 3 * d * d, st))) return rc;
-    if ((rc = qx::tf_split_weights(lw + lay.l_outw, sw + sp.out_hi, sw + sp.out_lo, d * d, st))) return rc;
-    if ((rc = qx::tf_split_weights(lw + lay.l_w1, sw + sp.w1_hi, sw + sp.w1_lo, ff * d, st))) return rc;
-    if ((rc = qx::tf_split_weights(lw + lay.l_w2, sw + sp.w2_hi, sw + sp.w2_lo, d * ff, st))) return rc;
+    if ((rc = both(lw + lay.l_inw, sw + sp.in_hi, sw + sp.in_lo, 3 * d * d))) return rc;
+    if ((rc = both(lw + lay.l_outw, sw + sp.out_hi, sw + sp.out_lo, d * d))) return rc;
+    if ((rc = both(lw + lay.l_w1, sw + sp.w1_hi, sw + sp.w1_lo, ff * d))) return rc;
+    if ((rc = both(lw + lay.l_w2, sw + sp.w2_hi, sw + sp.w2_lo, d * ff))) return rc;
   }
   qx::tf_pad_head_kernel<<<(unsigned)((128 * d + 255) / 256), 256, 0, st>>>(weights + lay.wo, weights + lay.bo,
                                                                           wsplit + sp.head_pad, wsplit + sp.head_bias,
                                                                           lay.c, (int)d);
   QX_CHECK_LAUNCH("tf_pad_head_kernel");
-  return qx::tf_split_weights(wsplit + sp.head_pad, wsplit + sp.head_hi, wsplit + sp.head_lo, 128 * d, st);
+  return both(wsplit + sp.head_pad, wsplit + sp.head_hi, wsplit + sp.head_lo, 128 * d);
 }
 
 extern "C" int qx_tf_forward(const QxTfConfig* cfg, const float* weights, const float* wsplit, const double* x,
@@ -590,7 +614,7 @@ extern "C" int qx_tf_forward(const QxTfConfig* cfg, const float* weights, const 
 extern "C" int qx_tf_split(const float* w, float* hi, float* lo, size_t count, void* stream) {
   QX_CHECK_ARG(w && hi && lo, "null pointer");
   if (count == 0) return QX_OK;
-  return qx::tf_split_weights(w, hi, lo, count, static_cast<cudaStream_t>(stream));
+  return qx::tf_split_weights(w, hi, lo, count, static_cast<cudaStream_t>(stream), qx::tf_ops_f16());
 }
 
 extern "C" int qx_tf_dense(const float* A, const float* w_hi, const float* w_lo, const float* bias, float* C, int M,
@@ -598,7 +622,7 @@ extern "C" int qx_tf_dense(const float* A, const float* w_hi, const float* w_lo,
   QX_CHECK_ARG(A && w_hi && w_lo && bias && C, "null pointer");
   QX_CHECK_ARG(M >= 0 && N > 0 && K > 0, "bad shape");
   if (M == 0) return QX_OK;
-  return qx::tf_gemm_tc(A, w_hi, w_lo, bias, C, M, N, K, relu != 0, static_cast<cudaStream_t>(stream));
+  return qx::tf_gemm_tc(A, w_hi, w_lo, bias, C, M, N, K, relu != 0, static_cast<cudaStream_t>(stream), qx::tf_ops_f16());
 }
 
 extern "C" int qx_tf_dense_ln(const float* A, const float* w_hi, const float* w_lo, const float* bias, const float* res,
@@ -607,7 +631,7 @@ extern "C" int qx_tf_dense_ln(const float* A, const float* w_hi, const float* w_
   QX_CHECK_ARG(M >= 0 && K > 0, "bad shape");
   QX_CHECK_ARG(C != A, "the output may alias the residual, not the A operand");
   if (M == 0) return QX_OK;
-  const int rc = qx::tf_gemm_ln_tc(A, w_hi, w_lo, bias, res, gamma, beta, C, M, K, static_cast<cudaStream_t>(stream));
+  const int rc = qx::tf_gemm_ln_tc(A, w_hi, w_lo, bias, res, gamma, beta, C, M, K, static_cast<cudaStream_t>(stream), qx::tf_ops_f16());
   if (rc == QX_EUNSUPPORTED) qx::set_error("qx_tf_dense_ln needs K %% 128 == 0 (got K=%d)", K);
   return rc;
 }

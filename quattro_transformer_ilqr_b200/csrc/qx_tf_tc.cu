@@ -20,6 +20,7 @@
 //   warps 6-9 epilogue: tcgen05.ld (32x32b.x32) TMEM -> registers, + bias, optional ReLU, 16-B
 //             stores; runs concurrently with the next tile's MMAs (double-buffered TMEM)
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "qx_tc05.cuh"
@@ -239,6 +240,36 @@ tf_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // TMEM: columns 0-255 two accumulators (the epilogue of tile i overlaps the MMAs of tile i+1), 256-511 four A stages
 // of (32 hi + 32 lo) columns.  Results are bit-identical to the streaming kernel (same MMAs, same order).
 constexpr int kTaW = 4, kTaRaw = 4, kTaA = 4;
+
+// (a, b) -> packed fp16 (hi, hi) and (lo, lo), a in the low halves
+__device__ __forceinline__ void f16_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// accumulator -> product: the fp16 weights carry a factor 2^8 (exact to undo)
+template <bool F16>
+__device__ __forceinline__ float unscale(uint32_t acc) {
+  return F16 ? __fmul_rn(__uint_as_float(acc), 1.f / 256.f) : __uint_as_float(acc);
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void mma_f16_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 constexpr int ta_threads(int sets) { return 64 + 128 * sets + 128; }
 
 struct TaSmem {
@@ -266,7 +297,16 @@ struct LnArgs {
   const float* beta;
 };
 
-template <bool RELU, bool STREAM_W, int kSets, bool LN = false>
+// F16: the operands are split into fp16 halves instead of TF32 ones.  x = hi + lo with hi = rn16(x), lo = rn16(x - hi)
+// carries the same 22 significant bits (the weights are pre-scaled by 2^8, undone exactly in the epilogue, so that their
+// lo halves stay out of the fp16 subnormals; activations need |x| < 65 504), the three products hi hi + hi lo + lo hi
+// are exact in the fp32 accumulator like the TF32 ones - but kind::f16 covers K = 16 per MMA where kind::tf32 covers 8:
+// half the tensor-pipe time, half the weight bytes in shared memory, half the tensor-memory columns for A.  A weight
+// block (128 rows x 128 B) then spans 64 k: two A blocks.
+constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);   // D = F32, A = B = F16
+constexpr float kW16Scale = 256.f;
+
+template <bool RELU, bool STREAM_W, int kSets, bool LN = false, bool F16 = false>
 __global__ void __launch_bounds__(ta_threads(kSets), 1)
 tf_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
                   const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmC,
@@ -324,7 +364,17 @@ tf_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t it = 0;
       for (int mt = g0; mt < m_tiles; mt += groups) {
         for (int kb = 0; kb < KB; ++kb, ++it) {
-          if (STREAM_W || it < (uint32_t)kTaW) {
+          if (F16) {
+            // weight block wit = it / 2 (the maps see the fp16 rows as K / 2 floats); resident: the first tile's only
+            if ((kb & 1) == 0 && (STREAM_W || it < (uint32_t)KB)) {
+              const uint32_t wit = it >> 1;
+              const int sw = wit % kTaW;
+              mbar_wait(&s.w_empty[sw], ((wit / kTaW) & 1u) ^ 1u);
+              mbar_arrive_expect_tx(&s.w_full[sw], 2 * kTileBytes);
+              tma_load_2d(&tmWhi, &s.w_full[sw], s.w_hi[sw], (kb >> 1) * kBK, n0);
+              tma_load_2d(&tmWlo, &s.w_full[sw], s.w_lo[sw], (kb >> 1) * kBK, n0);
+            }
+          } else if (STREAM_W || it < (uint32_t)kTaW) {
             const int sw = it % kTaW;
             mbar_wait(&s.w_empty[sw], ((it / kTaW) & 1u) ^ 1u);
             mbar_arrive_expect_tx(&s.w_full[sw], 2 * kTileBytes);
@@ -347,23 +397,36 @@ tf_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tcgen05_fence_after();
       const uint32_t acc = tmem + buf * kBN;
       for (int kb = 0; kb < KB; ++kb, ++it) {
-        const uint32_t sa = it % kTaA, sw = it % kTaW;
+        const uint32_t wit = F16 ? it >> 1 : it;                    // weight block of this A block
+        const uint32_t sa = it % kTaA;
+        const uint32_t sw = STREAM_W ? wit % kTaW : (uint32_t)(F16 ? kb >> 1 : kb);    // resident: block kb's own slot
         // resident weights: phase 0 of w_full[sw] completes once and the wait stays satisfied
-        mbar_wait(&s.w_full[sw], STREAM_W ? ((it / kTaW) & 1u) : 0u);
+        mbar_wait(&s.w_full[sw], STREAM_W ? ((wit / kTaW) & 1u) : 0u);
         mbar_wait(&s.a_ready[sa], (it / kTaA) & 1u);
         tcgen05_fence_after();
-        const uint32_t a_hi = tmem_a0 + sa * (2 * kBK), a_lo = a_hi + kBK;
+        const uint32_t a_hi = tmem_a0 + sa * (2 * kBK), a_lo = a_hi + (F16 ? kBK / 2 : kBK);
         const uint64_t dw_hi = umma_desc_sw128(s.w_hi[sw]), dw_lo = umma_desc_sw128(s.w_lo[sw]);
         if (elect_one()) {
+          if (F16) {
 #pragma unroll
-          for (int k = 0; k < kBK / 8; ++k) {
-            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);       // 32 bytes per K = 8 slice
-            mma_tf32_ta(acc, a_lo + 8 * k, dw_hi + adv, kIdescTf32, (kb | k) ? 1u : 0u);
-            mma_tf32_ta(acc, a_hi + 8 * k, dw_lo + adv, kIdescTf32, 1u);
-            mma_tf32_ta(acc, a_hi + 8 * k, dw_hi + adv, kIdescTf32, 1u);
+            for (int k = 0; k < kBK / 16; ++k) {
+              // 32 bytes per K = 16 slice, the odd A block in the upper half of the 128-B weight rows; 8 columns of A
+              const uint64_t adv = (uint64_t)((((kb & 1) * kBK + k * 16) * 2) >> 4);
+              mma_f16_ta(acc, a_lo + 8 * k, dw_hi + adv, kIdescF16, (kb | k) ? 1u : 0u);
+              mma_f16_ta(acc, a_hi + 8 * k, dw_lo + adv, kIdescF16, 1u);
+              mma_f16_ta(acc, a_hi + 8 * k, dw_hi + adv, kIdescF16, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < kBK / 8; ++k) {
+              const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);       // 32 bytes per K = 8 slice
+              mma_tf32_ta(acc, a_lo + 8 * k, dw_hi + adv, kIdescTf32, (kb | k) ? 1u : 0u);
+              mma_tf32_ta(acc, a_hi + 8 * k, dw_lo + adv, kIdescTf32, 1u);
+              mma_tf32_ta(acc, a_hi + 8 * k, dw_hi + adv, kIdescTf32, 1u);
+            }
           }
           tcgen05_commit(&s.a_empty[sa]);
-          if (STREAM_W) tcgen05_commit(&s.w_empty[sw]);
+          if (STREAM_W && (!F16 || (kb & 1))) tcgen05_commit(&s.w_empty[sw]);
           if (kb == KB - 1) tcgen05_commit(&s.acc_full[buf]);
         }
         __syncwarp();
@@ -379,22 +442,33 @@ tf_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t sa = it % kTaA;
       mbar_wait(&s.full[st], (it / kTaRaw) & 1u);
       const float4* src = reinterpret_cast<const float4*>(s.raw[st]) + row * 8;
-      uint32_t hi[32], lo[32];
+      uint32_t hi[F16 ? 16 : 32], lo[F16 ? 16 : 32];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 v = src[j ^ (row & 7)];           // 128-B swizzle: 16-B chunk j of row r sits at j ^ (r % 8)
-        float h, l;
-        tf32_split(v.x, h, l); hi[4 * j + 0] = __float_as_uint(h); lo[4 * j + 0] = __float_as_uint(l);
-        tf32_split(v.y, h, l); hi[4 * j + 1] = __float_as_uint(h); lo[4 * j + 1] = __float_as_uint(l);
-        tf32_split(v.z, h, l); hi[4 * j + 2] = __float_as_uint(h); lo[4 * j + 2] = __float_as_uint(l);
-        tf32_split(v.w, h, l); hi[4 * j + 3] = __float_as_uint(h); lo[4 * j + 3] = __float_as_uint(l);
+        if constexpr (F16) {
+          // a tensor-memory column holds two consecutive k (the lower one in the low half)
+          f16_split2(v.x, v.y, hi[2 * j + 0], lo[2 * j + 0]);
+          f16_split2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+        } else {
+          float h, l;
+          tf32_split(v.x, h, l); hi[4 * j + 0] = __float_as_uint(h); lo[4 * j + 0] = __float_as_uint(l);
+          tf32_split(v.y, h, l); hi[4 * j + 1] = __float_as_uint(h); lo[4 * j + 1] = __float_as_uint(l);
+          tf32_split(v.z, h, l); hi[4 * j + 2] = __float_as_uint(h); lo[4 * j + 2] = __float_as_uint(l);
+          tf32_split(v.w, h, l); hi[4 * j + 3] = __float_as_uint(h); lo[4 * j + 3] = __float_as_uint(l);
+        }
       }
       mbar_wait(&s.a_empty[sa], ((it / kTaA) & 1u) ^ 1u);
       __syncwarp();        // the lanes leave the spin loop one by one; tcgen05.st / wait::st are .sync.aligned
       tcgen05_fence_after();
       const uint32_t taddr = tmem_a0 + sa * (2 * kBK) + ((uint32_t)(q * 32) << 16);
-      tmem_st_32x32b_x32(taddr, hi);
-      tmem_st_32x32b_x32(taddr + kBK, lo);
+      if constexpr (F16) {
+        tmem_st_32x32b_x16(taddr, hi);
+        tmem_st_32x32b_x16(taddr + kBK / 2, lo);
+      } else {
+        tmem_st_32x32b_x32(taddr, hi);
+        tmem_st_32x32b_x32(taddr + kBK, lo);
+      }
       // Hand the raw block back to the producer only now: the stores above consume every loaded value, so the LDS have
       // returned.  (An arrive placed right after the loads is issued while they are in flight - nothing orders a
       // pending shared-memory read against the TMA write the arrive unblocks; that cost a few rows every ~100th launch.)
@@ -446,10 +520,10 @@ tf_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int j = 0; j < 8; ++j) {
             const float4 bb = b4[j];
             const float4 hh = stg[lane][j ^ (lane & 7)];
-            const float a0 = __fadd_rn(hh.x, __fadd_rn(__uint_as_float(r[c][4 * j + 0]), bb.x));
-            const float a1 = __fadd_rn(hh.y, __fadd_rn(__uint_as_float(r[c][4 * j + 1]), bb.y));
-            const float a2 = __fadd_rn(hh.z, __fadd_rn(__uint_as_float(r[c][4 * j + 2]), bb.z));
-            const float a3 = __fadd_rn(hh.w, __fadd_rn(__uint_as_float(r[c][4 * j + 3]), bb.w));
+            const float a0 = __fadd_rn(hh.x, __fadd_rn(unscale<F16>(r[c][4 * j + 0]), bb.x));
+            const float a1 = __fadd_rn(hh.y, __fadd_rn(unscale<F16>(r[c][4 * j + 1]), bb.y));
+            const float a2 = __fadd_rn(hh.z, __fadd_rn(unscale<F16>(r[c][4 * j + 2]), bb.z));
+            const float a3 = __fadd_rn(hh.w, __fadd_rn(unscale<F16>(r[c][4 * j + 3]), bb.w));
             t[j] = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
             r[c][4 * j + 0] = __float_as_uint(a0); r[c][4 * j + 1] = __float_as_uint(a1);
             r[c][4 * j + 2] = __float_as_uint(a2); r[c][4 * j + 3] = __float_as_uint(a3);
@@ -539,10 +613,10 @@ tf_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int j = 0; j < 8; ++j) {
             const float4 bb = b4[j];
             float4 o;
-            o.x = __uint_as_float(r[4 * j + 0]) + bb.x;
-            o.y = __uint_as_float(r[4 * j + 1]) + bb.y;
-            o.z = __uint_as_float(r[4 * j + 2]) + bb.z;
-            o.w = __uint_as_float(r[4 * j + 3]) + bb.w;
+            o.x = __fadd_rn(unscale<F16>(r[4 * j + 0]), bb.x);
+            o.y = __fadd_rn(unscale<F16>(r[4 * j + 1]), bb.y);
+            o.z = __fadd_rn(unscale<F16>(r[4 * j + 2]), bb.z);
+            o.w = __fadd_rn(unscale<F16>(r[4 * j + 3]), bb.w);
             if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
             stg[lane][j ^ (lane & 7)] = o;
           }
@@ -576,6 +650,16 @@ __global__ void tf_split_kernel(const float* __restrict__ w, float* __restrict__
   lo[i] = l;
 }
 
+// W -> fp16 (hi, lo) halves of 2^8 W (see tf_gemm_ta_kernel<F16>); hi / lo hold `count` halves each
+__global__ void tf_split16_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, size_t count) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float v = w[i] * kW16Scale;
+  const __half h = __float2half_rn(v);
+  hi[i] = h;
+  lo[i] = __float2half_rn(v - __half2float(h));
+}
+
 // row-major fp32 matrix [rows][cols] -> tiled map with a (32 x 128) box and 128-B swizzle
 static int make_map(CUtensorMap* map, const float* base, int rows, int cols, int box_cols = kBK, int box_rows = kBM) {
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -584,15 +668,17 @@ static int make_map(CUtensorMap* map, const float* base, int rows, int cols, int
   return make_map_nd(map, base, 2, dims, strides, box);
 }
 
+// f16: Whi / Wlo hold the fp16 halves tf_split_weights(.., true) wrote (N x K halves each; the maps see K / 2 floats a row)
 int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* bias, float* C, int M, int N, int K,
-               bool relu, cudaStream_t st) {
+               bool relu, cudaStream_t st, bool f16) {
   if (N % kBN != 0 || K % kBK != 0) {
     set_error("tensor-core GEMM needs N %% 128 == 0 and K %% 32 == 0 (got N=%d K=%d)", N, K);
     return QX_EINVAL;
   }
   CUtensorMap ma, mh, ml;
   int rc;
-  if ((rc = make_map(&ma, A, M, K)) || (rc = make_map(&mh, Whi, N, K)) || (rc = make_map(&ml, Wlo, N, K))) return rc;
+  const int Kw = f16 ? K / 2 : K;
+  if ((rc = make_map(&ma, A, M, K)) || (rc = make_map(&mh, Whi, N, Kw)) || (rc = make_map(&ml, Wlo, N, Kw))) return rc;
   const int dslot = current_device_slot();
   static bool configured[kMaxDevices] = {};
   if (!configured[dslot]) {
@@ -605,6 +691,10 @@ int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* 
   // per call).  QX_TF_GEMM_VARIANT=1: two splitter warp sets.  QX_TF_GEMM_DBG: timing experiments, see the kernel.
   const char* env_stream = getenv("QX_TF_GEMM_STREAM");
   const bool stream_only = env_stream != nullptr && env_stream[0] == '1';
+  if (f16 && (K % (kTaW * kBK) != 0 || N / kBN > num_sms || stream_only)) {
+    set_error("fp16-split GEMM needs K %% 128 == 0 and the tensor-memory kernel (got N=%d K=%d)", N, K);
+    return QX_EINVAL;
+  }
   if (K % (kTaW * kBK) == 0 && N / kBN <= num_sms && !stream_only) {
     // groups of N/128 CTAs (one per n tile) walk the m tiles together
     const int n_tiles_n = N / kBN, m_tiles = ceil_div(M, kBM);
@@ -617,18 +707,24 @@ int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* 
     const int variant = env_var ? atoi(env_var) : 0;
     CUtensorMap mc;
     if ((rc = make_map(&mc, C, M, N, 32, 32))) return rc;
-#define QX_TA_LAUNCH(RELU_, STREAM_, SETS)                                                                              \
+#define QX_TA_LAUNCH(RELU_, STREAM_, SETS, ...)                                                                         \
   do {                                                                                                                  \
     static bool cfgd[kMaxDevices] = {};                                                                                 \
     if (!cfgd[dslot]) {                                                                                                 \
-      cudaFuncSetAttribute(tf_gemm_ta_kernel<RELU_, STREAM_, SETS>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+      cudaFuncSetAttribute(tf_gemm_ta_kernel<RELU_, STREAM_, SETS __VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                            (int)kTaSmemBytes);                                                                          \
       cfgd[dslot] = true;                                                                                               \
     }                                                                                                                   \
-    tf_gemm_ta_kernel<RELU_, STREAM_, SETS><<<grid, ta_threads(SETS), kTaSmemBytes, st>>>(ma, mh, ml, mc, bias, M, N, K, dbg, mc, LnArgs{}); \
+    tf_gemm_ta_kernel<RELU_, STREAM_, SETS __VA_ARGS__><<<grid, ta_threads(SETS), kTaSmemBytes, st>>>(ma, mh, ml, mc, bias, M, N, K, dbg, mc, LnArgs{}); \
   } while (0)
+#define QX_COMMA ,
     const bool stream_w = K != kTaW * kBK;
-    if (variant == 1) {
+    if (f16) {
+      if (relu && stream_w) QX_TA_LAUNCH(true, true, 1, QX_COMMA false QX_COMMA true);
+      else if (relu) QX_TA_LAUNCH(true, false, 1, QX_COMMA false QX_COMMA true);
+      else if (stream_w) QX_TA_LAUNCH(false, true, 1, QX_COMMA false QX_COMMA true);
+      else QX_TA_LAUNCH(false, false, 1, QX_COMMA false QX_COMMA true);
+    } else if (variant == 1) {
       if (relu && stream_w) QX_TA_LAUNCH(true, true, 2);
       else if (relu) QX_TA_LAUNCH(true, false, 2);
       else if (stream_w) QX_TA_LAUNCH(false, true, 2);
@@ -640,6 +736,7 @@ int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* 
       else QX_TA_LAUNCH(false, false, 1);
     }
 #undef QX_TA_LAUNCH
+#undef QX_COMMA
     QX_CHECK_LAUNCH("tf_gemm_ta_kernel");
     return QX_OK;
   }
@@ -655,12 +752,13 @@ int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* 
 // kernel).  C may be res itself (a tile's residual rows are consumed before its stores are issued, and no other CTA
 // touches them) but must not be A.  QX_EUNSUPPORTED when the shape does not fit.
 int tf_gemm_ln_tc(const float* A, const float* Whi, const float* Wlo, const float* bias, const float* res, const float* gamma,
-                  const float* beta, float* C, int M, int K, cudaStream_t st) {
+                  const float* beta, float* C, int M, int K, cudaStream_t st, bool f16) {
   const int N = kBN;
   if (K % (kTaW * kBK) != 0) return QX_EUNSUPPORTED;
   CUtensorMap ma, mh, ml, mc, mr;
   int rc;
-  if ((rc = make_map(&ma, A, M, K)) || (rc = make_map(&mh, Whi, N, K)) || (rc = make_map(&ml, Wlo, N, K)) ||
+  const int Kw = f16 ? K / 2 : K;
+  if ((rc = make_map(&ma, A, M, K)) || (rc = make_map(&mh, Whi, N, Kw)) || (rc = make_map(&ml, Wlo, N, Kw)) ||
       (rc = make_map(&mc, C, M, N, 32, 32)) || (rc = make_map(&mr, res, M, N, 32, 32)))
     return rc;
   const int num_sms = device_sm_count();
@@ -671,9 +769,15 @@ int tf_gemm_ln_tc(const float* A, const float* Whi, const float* Wlo, const floa
   if (!cfgd[current_device_slot()]) {
     cudaFuncSetAttribute(tf_gemm_ta_kernel<false, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTaSmemBytes);
     cudaFuncSetAttribute(tf_gemm_ta_kernel<false, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTaSmemBytes);
+    cudaFuncSetAttribute(tf_gemm_ta_kernel<false, false, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTaSmemBytes);
+    cudaFuncSetAttribute(tf_gemm_ta_kernel<false, true, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTaSmemBytes);
     cfgd[current_device_slot()] = true;
   }
-  if (K != kTaW * kBK)
+  if (f16 && K != kTaW * kBK)
+    tf_gemm_ta_kernel<false, true, 1, true, true><<<grid, ta_threads(1), kTaSmemBytes, st>>>(ma, mh, ml, mc, bias, M, N, K, 0, mr, ln);
+  else if (f16)
+    tf_gemm_ta_kernel<false, false, 1, true, true><<<grid, ta_threads(1), kTaSmemBytes, st>>>(ma, mh, ml, mc, bias, M, N, K, 0, mr, ln);
+  else if (K != kTaW * kBK)
     tf_gemm_ta_kernel<false, true, 1, true><<<grid, ta_threads(1), kTaSmemBytes, st>>>(ma, mh, ml, mc, bias, M, N, K, 0, mr, ln);
   else
     tf_gemm_ta_kernel<false, false, 1, true><<<grid, ta_threads(1), kTaSmemBytes, st>>>(ma, mh, ml, mc, bias, M, N, K, 0, mr, ln);
@@ -681,8 +785,9 @@ int tf_gemm_ln_tc(const float* A, const float* Whi, const float* Wlo, const floa
   return QX_OK;
 }
 
-int tf_split_weights(const float* w, float* hi, float* lo, size_t count, cudaStream_t st) {
-  tf_split_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(w, hi, lo, count);
+int tf_split_weights(const float* w, float* hi, float* lo, size_t count, cudaStream_t st, bool f16) {
+  if (f16) tf_split16_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(w, reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), count);
+  else tf_split_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(w, hi, lo, count);
   QX_CHECK_LAUNCH("tf_split_kernel");
   return QX_OK;
 }

@@ -403,6 +403,32 @@ def test_tensor_core_path_matches_exact_fp32_path(system, golden_dir):
 
 
 @pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
+def test_fp16_split_dense_layers_match_tf32_split_and_exact_path(system, golden_dir, monkeypatch):
+    """The dense layers of the forward pass run as three kind::f16 products of fp16 (hi, lo) halves (weights pre-scaled by
+    2^8) - the default - or as three kind::tf32 products of TF32 halves (QX_TF_GEMM_F16=0): both carry 22 significant
+    bits per operand, so both sit within 5e-6 of the exact fp32 CUDA-core path, and within that of each other.  1 200
+    trajectories: many tiles per CTA, both weight-ring modes (K = 128 resident, K = ff streamed)."""
+    g = np.load(f"{golden_dir}/tf_forward_{system}.npz")
+    w = _wrapper(system, "rand")
+    rng = np.random.default_rng(11)
+    reps = 1200 // len(g["x_err"])
+    x = np.concatenate([g["x_err"] * (1.0 + 0.05 * rng.standard_normal(g["x_err"].shape)) for _ in range(reps)])
+    kK = np.concatenate([g["kK"] * (1.0 + 0.05 * rng.standard_normal(g["kK"].shape)) for _ in range(reps)])
+    monkeypatch.setenv("QX_TF_GEMM_F16", "1")
+    f16 = w.predict(x, kK)
+    again = w.predict(x, kK)
+    monkeypatch.setenv("QX_TF_GEMM_F16", "0")
+    tf32 = w.predict(x, kK)
+    assert np.isfinite(f16).all() and np.array_equal(f16, again)
+    assert not np.array_equal(f16, tf32)           # the switch does select another kernel
+    w.tensor_cores = False
+    exact = w.predict(x, kK)
+    e16, e32 = relmax(f16, exact), relmax(tf32, exact)
+    print(f"{system}: fp16 split {e16:.2e}, TF32 split {e32:.2e} from the exact fp32 path")
+    assert e16 < 5e-6 and e32 < 5e-6 and relmax(f16, tf32) < 5e-6
+
+
+@pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
 def test_resident_weight_gemm_equals_streaming_gemm_bitwise(system, golden_dir, monkeypatch):
     """The K = 128 layers run on the resident-weight tcgen05 kernel (weights parked in shared memory, A streamed
     through a 3 + 2 block ring); it issues the same MMAs in the same order as the streaming kernel, so the
@@ -415,6 +441,7 @@ def test_resident_weight_gemm_equals_streaming_gemm_bitwise(system, golden_dir, 
     x = np.concatenate([g["x_err"] * (1.0 + 0.05 * rng.standard_normal(g["x_err"].shape)) for _ in range(reps)])
     kK = np.concatenate([g["kK"] * (1.0 + 0.05 * rng.standard_normal(g["kK"].shape)) for _ in range(reps)])
     monkeypatch.setenv("QX_TF_FUSE_LN", "0")       # plain epilogues on both sides: all four GEMMs of a layer are compared
+    monkeypatch.setenv("QX_TF_GEMM_F16", "0")      # both kernels on the TF32 split (the streaming one has no fp16 variant)
     monkeypatch.setenv("QX_TF_GEMM_STREAM", "1")
     streamed = w.predict(x, kK)
     monkeypatch.setenv("QX_TF_GEMM_STREAM", "0")
