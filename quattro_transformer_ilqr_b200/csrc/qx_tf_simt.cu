@@ -377,6 +377,8 @@ int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* 
 int tf_split_weights(const float* w, float* hi, float* lo, size_t count, cudaStream_t st, bool f16);
 int tf_gemm_ln_tc(const float* A, const float* Whi, const float* Wlo, const float* bias, const float* res, const float* gamma,
                   const float* beta, float* C, int M, int K, cudaStream_t st, bool f16);
+int tf_ffn_fused(const float* x, const float* W1hi, const float* W1lo, const float* b1, const float* W2hi, const float* W2lo,
+                 const float* b2, const float* gamma, const float* beta, float* out, int M, int ff, cudaStream_t st);
 
 // offsets of the (hi, lo) copies of the four GEMM weights of one layer inside the split buffer
 struct SplitLayout {
@@ -505,6 +507,15 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
       QX_CHECK_LAUNCH("tf_add_ln_kernel");
       return QX_OK;
     };
+    // The whole feed-forward block in one launch (tf_ffn_kernel: the ff-wide intermediate never leaves the SM) when the
+    // fp16 split and the fused norm2 are on; QX_TF_FFN_FUSE=0 brings the two launches back (A/B runs, equality test).
+    const char* env_ff = getenv("QX_TF_FFN_FUSE");
+    const bool fuse_ffn = f16 && (fuse & 2) && !(env_ff != nullptr && env_ff[0] == '0');
+    auto ffn = [&](float* xs, int m_rows) -> int {
+      if (!fuse_ffn) return QX_EUNSUPPORTED;
+      return tf_ffn_fused(xs, wh(sw + sp.w1_hi), wh(sw + sp.w1_lo), lw + lay.l_b1, wh(sw + sp.w2_hi), wh(sw + sp.w2_lo), lw + lay.l_b2,
+                          lw + lay.l_n2w, lw + lay.l_n2b, xs, m_rows, ff, st);
+    };
     if (pruned) {
       // compact stream: att -> out-proj -> y; hc = LN(h[query rows] + y) lands in att (its input is consumed);
       // FFN (+ hc, norm2) -> hc
@@ -512,17 +523,21 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
       if ((rc = dense_ln(fuse & 1, att, lay.l_outw, lay.l_outb, sp.out_hi, sp.out_lo, d, h, lay.l_n1w, lay.l_n1b, hc, rows_c, lay.T, L,
                          L - lay.T)))
         return rc;
-      if ((rc = tf_gemm_tc(hc, wh(sw + sp.w1_hi), wh(sw + sp.w1_lo), lw + lay.l_b1, ffh, rows_c, ff, d, true, st, f16))) return rc;
-      if ((rc = dense_ln(fuse & 2, ffh, lay.l_w2, lay.l_b2, sp.w2_hi, sp.w2_lo, ff, hc, lay.l_n2w, lay.l_n2b, hc, rows_c, rows_c, rows_c, 0)))
-        return rc;
+      if ((rc = ffn(hc, rows_c)) == QX_EUNSUPPORTED) {
+        if ((rc = tf_gemm_tc(hc, wh(sw + sp.w1_hi), wh(sw + sp.w1_lo), lw + lay.l_b1, ffh, rows_c, ff, d, true, st, f16))) return rc;
+        rc = dense_ln(fuse & 2, ffh, lay.l_w2, lay.l_b2, sp.w2_hi, sp.w2_lo, ff, hc, lay.l_n2w, lay.l_n2b, hc, rows_c, rows_c, rows_c, 0);
+      }
+      if (rc) return rc;
       hfinal = hc;
       break;
     }
     if ((rc = dense_ln(fuse & 1, att, lay.l_outw, lay.l_outb, sp.out_hi, sp.out_lo, d, h, lay.l_n1w, lay.l_n1b, h, rows, rows, rows, 0)))
       return rc;
-    if ((rc = dense(h, lw, lay.l_w1, lay.l_b1, sp.w1_hi, sp.w1_lo, l, ffh, ff, d, true))) return rc;
-    if ((rc = dense_ln(fuse & 2, ffh, lay.l_w2, lay.l_b2, sp.w2_hi, sp.w2_lo, ff, h, lay.l_n2w, lay.l_n2b, h, rows, rows, rows, 0)))
-      return rc;
+    if ((rc = ffn(h, rows)) == QX_EUNSUPPORTED) {
+      if ((rc = dense(h, lw, lay.l_w1, lay.l_b1, sp.w1_hi, sp.w1_lo, l, ffh, ff, d, true))) return rc;
+      rc = dense_ln(fuse & 2, ffh, lay.l_w2, lay.l_b2, sp.w2_hi, sp.w2_lo, ff, h, lay.l_n2w, lay.l_n2b, h, rows, rows, rows, 0);
+    }
+    if (rc) return rc;
   }
   dim3 go(lay.T, B);
   if (wsplit != nullptr) {      // output head as one more tensor-core GEMM (N padded to 128) over the rows that are left

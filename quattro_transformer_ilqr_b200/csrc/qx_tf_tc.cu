@@ -785,6 +785,369 @@ int tf_gemm_ln_tc(const float* A, const float* Whi, const float* Wlo, const floa
   return QX_OK;
 }
 
+
+// ---- the feed-forward block of an encoder layer as ONE kernel ------------------------------------------------------
+//   x <- LayerNorm(x + linear2(relu(linear1(x))))      (transformer_model.py:112-113: nn.TransformerEncoderLayer, post-norm)
+// As two launches the ff-wide intermediate makes 3.4 of the 4.6 GB the block moves per layer (8 192 quadrotor
+// trajectories) and both launches run at the HBM roof.  Here a CTA owns 128 token rows and walks the hidden units in
+// chunks of 128: H_j = relu(X W1_j^T + b1_j) is accumulated in tensor memory, read once by the converter warps (bias, ReLU,
+// fp16 split) and written back to tensor memory as the A operand of Y += H_j W2_j^T; HBM sees X once (plus the residual
+// boxes of the LayerNorm epilogue, L2 hits) and the result once.  fp16 split only (tf_gemm_ta_kernel<F16>); every product,
+// its order of accumulation and every rounding are those of the two-launch path, so the results are the same bits.
+//   tensor memory   Y [0,128) | H_j [128,256) | X hi [256,320) lo [320,384) | H_j hi [384,448) lo [448,512)   (fp16: 2 k / column)
+//   shared memory   4 weight slots (128 rows x 64 k, hi + lo: 32 KB) | X landing: four 32-float blocks | LN staging
+//   warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 split X / convert H_j (thread = row), warps 6-9 LayerNorm epilogue
+// The MMA warp runs one product ahead: G1(0) G1(1) G2(0) G1(2) G2(1) .. G2(C-1), so that the conversion of chunk j has the
+// time of G1(j+1) to finish before the tensor pipe would wait for it; the weight blocks come in that order.
+constexpr uint32_t kFfnY = 0, kFfnH = 128, kFfnX = 256, kFfnH16 = 384;
+struct FfnSmem {
+  float w_hi[kTaW][kBN * kBK];
+  float w_lo[kTaW][kBN * kBK];
+  float raw[4][kBM * kBK];
+  float4 epi[4][2][32][8];
+  uint64_t w_full[kTaW], w_empty[kTaW], raw_full[4], raw_empty[4], x_ready, x_free, hacc_full, hacc_empty, h16_ready, h16_free,
+      y_full, y_empty, res_full[4][2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(FfnSmem) <= 227 * 1024, "fused FFN exceeds the shared memory of an SM");
+
+__global__ void __launch_bounds__(320, 1)
+tf_ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1hi,
+              const __grid_constant__ CUtensorMap tmW1lo, const __grid_constant__ CUtensorMap tmW2hi,
+              const __grid_constant__ CUtensorMap tmW2lo, const __grid_constant__ CUtensorMap tmC,
+              const __grid_constant__ CUtensorMap tmR, const float* __restrict__ b1, const float* __restrict__ b2,
+              const LnArgs ln, int M, int ff) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  FfnSmem& s = *reinterpret_cast<FfnSmem*>(smem_raw);
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u)) __trap();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = ff / 128;                                // hidden chunks
+  const int m_tiles = ceil_div(M, kBM);
+  const int stride = gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kTaW; ++i) {
+      mbar_init(&s.w_full[i], 1);
+      mbar_init(&s.w_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s.raw_full[i], 1);
+      mbar_init(&s.raw_empty[i], 128);
+    }
+    mbar_init(&s.x_ready, 128);
+    mbar_init(&s.x_free, 1);
+    mbar_init(&s.hacc_full, 1);
+    mbar_init(&s.hacc_empty, 128);
+    mbar_init(&s.h16_ready, 128);
+    mbar_init(&s.h16_free, 1);
+    mbar_init(&s.y_full, 1);
+    mbar_init(&s.y_empty, 128);
+    for (int i = 0; i < 8; ++i) mbar_init(&s.res_full[i >> 1][i & 1], 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = s.tmem_base;
+
+  if (warp == 0) {
+    // ---- TMA producer -----------------------------------------------------------------------------------------------
+    if (lane == 0) {
+      uint32_t wit = 0, rit = 0;
+      // the two 64-k weight blocks of product G1(j) (rows = hidden units of chunk j) or G2(j) (k = hidden units of chunk j)
+      auto w_blocks = [&](bool second, int j) {
+        for (int kb = 0; kb < 2; ++kb, ++wit) {
+          const int sw = wit % kTaW;
+          mbar_wait(&s.w_empty[sw], ((wit / kTaW) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&s.w_full[sw], 2 * kTileBytes);
+          if (second) {
+            tma_load_2d(&tmW2hi, &s.w_full[sw], s.w_hi[sw], (2 * j + kb) * kBK, 0);
+            tma_load_2d(&tmW2lo, &s.w_full[sw], s.w_lo[sw], (2 * j + kb) * kBK, 0);
+          } else {
+            tma_load_2d(&tmW1hi, &s.w_full[sw], s.w_hi[sw], kb * kBK, j * 128);
+            tma_load_2d(&tmW1lo, &s.w_full[sw], s.w_lo[sw], kb * kBK, j * 128);
+          }
+        }
+      };
+      for (int mt = blockIdx.x; mt < m_tiles; mt += stride) {
+        for (int kb = 0; kb < 4; ++kb, ++rit) {
+          const int st = rit & 3;
+          mbar_wait(&s.raw_empty[st], ((rit >> 2) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&s.raw_full[st], kTileBytes);
+          tma_load_2d(&tmX, &s.raw_full[st], s.raw[st], kb * kBK, mt * kBM);
+        }
+        w_blocks(false, 0);
+        for (int j = 1; j < C; ++j) {
+          w_blocks(false, j);
+          w_blocks(true, j - 1);
+        }
+        w_blocks(true, C - 1);
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer ---------------------------------------------------------------------------------------------------
+    uint32_t wit = 0, tl = 0, n1 = 0, n2 = 0;
+    // one product of a chunk: acc (+)= A[tensor memory: 64 columns hi, 64 columns lo] W^T over k = 0..127
+    auto product = [&](uint32_t acc, uint32_t a_base, bool fresh) {
+      for (int kb = 0; kb < 2; ++kb, ++wit) {
+        const uint32_t sw = wit % kTaW;
+        mbar_wait(&s.w_full[sw], (wit / kTaW) & 1u);
+        tcgen05_fence_after();
+        const uint64_t dw_hi = umma_desc_sw128(s.w_hi[sw]), dw_lo = umma_desc_sw128(s.w_lo[sw]);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+            const uint32_t a_hi = a_base + kb * 32 + k * 8, a_lo = a_hi + 64;
+            mma_f16_ta(acc, a_lo, dw_hi + adv, kIdescF16, (fresh && kb == 0 && k == 0) ? 0u : 1u);
+            mma_f16_ta(acc, a_hi, dw_lo + adv, kIdescF16, 1u);
+            mma_f16_ta(acc, a_hi, dw_hi + adv, kIdescF16, 1u);
+          }
+          tcgen05_commit(&s.w_empty[sw]);
+        }
+        __syncwarp();
+      }
+    };
+    auto g1 = [&](int j) {
+      mbar_wait(&s.hacc_empty, (n1 & 1u) ^ 1u);            // the converters have read the previous chunk's accumulator
+      tcgen05_fence_after();
+      product(tmem + kFfnH, tmem + kFfnX, true);
+      if (elect_one()) {
+        tcgen05_commit(&s.hacc_full);
+        if (j == C - 1) tcgen05_commit(&s.x_free);         // every product that reads this tile's X halves is issued
+      }
+      __syncwarp();
+      ++n1;
+    };
+    auto g2 = [&](int j) {
+      mbar_wait(&s.h16_ready, n2 & 1u);
+      if (j == 0) mbar_wait(&s.y_empty, (tl & 1u) ^ 1u);   // the epilogue has read the previous tile's result
+      tcgen05_fence_after();
+      product(tmem + kFfnY, tmem + kFfnH16, j == 0);
+      if (elect_one()) {
+        tcgen05_commit(&s.h16_free);
+        if (j == C - 1) tcgen05_commit(&s.y_full);
+      }
+      __syncwarp();
+      ++n2;
+    };
+    for (int mt = blockIdx.x; mt < m_tiles; mt += stride, ++tl) {
+      mbar_wait(&s.x_ready, tl & 1u);
+      tcgen05_fence_after();
+      g1(0);
+      for (int j = 1; j < C; ++j) {
+        g1(j);
+        g2(j - 1);
+      }
+      g2(C - 1);
+    }
+  } else if (warp < 6) {
+    // ---- split X, then convert every hidden chunk: thread = row ----------------------------------------------------
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    uint32_t rit = 0, tl = 0, ct = 0;
+    for (int mt = blockIdx.x; mt < m_tiles; mt += stride, ++tl) {
+      mbar_wait(&s.x_free, (tl & 1u) ^ 1u);                // the previous tile's first products are done with its X
+      for (int kb = 0; kb < 4; ++kb, ++rit) {
+        const int st = rit & 3;
+        mbar_wait(&s.raw_full[st], (rit >> 2) & 1u);
+        const float4* src = reinterpret_cast<const float4*>(s.raw[st]) + row * 8;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 v = src[j ^ (row & 7)];
+          f16_split2(v.x, v.y, hi[2 * j + 0], lo[2 * j + 0]);
+          f16_split2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+        }
+        __syncwarp();
+        tcgen05_fence_after();
+        tmem_st_32x32b_x16(trow + kFfnX + 16 * kb, hi);
+        tmem_st_32x32b_x16(trow + kFfnX + 64 + 16 * kb, lo);
+        mbar_arrive(&s.raw_empty[st]);                     // behind the stores, which consume every loaded value
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tcgen05_fence_before();
+      mbar_arrive(&s.x_ready);
+      for (int j = 0; j < C; ++j, ++ct) {
+        mbar_wait(&s.hacc_full, ct & 1u);
+        __syncwarp();
+        tcgen05_fence_after();
+        uint32_t r[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(trow + kFfnH + 32 * c, r[c]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tcgen05_fence_before();
+        mbar_arrive(&s.hacc_empty);
+        const float* bj = b1 + j * 128;
+        bool waited = false;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t hi[16], lo[16];
+          const float4* b4 = reinterpret_cast<const float4*>(bj + 32 * c);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float4 bb = b4[e];
+            const float v0 = fmaxf(__fadd_rn(unscale<true>(r[c][4 * e + 0]), bb.x), 0.f);
+            const float v1 = fmaxf(__fadd_rn(unscale<true>(r[c][4 * e + 1]), bb.y), 0.f);
+            const float v2 = fmaxf(__fadd_rn(unscale<true>(r[c][4 * e + 2]), bb.z), 0.f);
+            const float v3 = fmaxf(__fadd_rn(unscale<true>(r[c][4 * e + 3]), bb.w), 0.f);
+            f16_split2(v0, v1, hi[2 * e + 0], lo[2 * e + 0]);
+            f16_split2(v2, v3, hi[2 * e + 1], lo[2 * e + 1]);
+          }
+          if (!waited) {
+            mbar_wait(&s.h16_free, (ct & 1u) ^ 1u);        // the previous chunk's second product has read its halves
+            __syncwarp();
+            tcgen05_fence_after();
+            waited = true;
+          }
+          tmem_st_32x32b_x16(trow + kFfnH16 + 16 * c, hi);
+          tmem_st_32x32b_x16(trow + kFfnH16 + 64 + 16 * c, lo);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tcgen05_fence_before();
+        mbar_arrive(&s.h16_ready);
+      }
+    }
+  } else {
+    // ---- epilogue: x <- LayerNorm(x + (Y / 2^8 + b2)), as in tf_gemm_ta_kernel<LN> ---------------------------------
+    const int q = warp & 3;
+    uint32_t tl = 0;
+    if (lane == 0 && (int)blockIdx.x < m_tiles) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        mbar_arrive_expect_tx(&s.res_full[q][c], 32 * 32 * 4);
+        tma_load_2d(&tmR, &s.res_full[q][c], s.epi[q][c], 32 * c, blockIdx.x * kBM + q * 32);
+      }
+    }
+    for (int mt = blockIdx.x; mt < m_tiles; mt += stride, ++tl) {
+      const int m0 = mt * kBM;
+      mbar_wait(&s.y_full, tl & 1u);
+      __syncwarp();
+      tcgen05_fence_after();
+      const uint32_t tacc = tmem + kFfnY + ((uint32_t)(q * 32) << 16);
+      uint32_t r[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tacc + 32 * c, r[c]);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tcgen05_fence_before();
+      mbar_arrive(&s.y_empty);
+      float pc[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float4 (*stg)[8] = s.epi[q][c & 1];
+        mbar_wait(&s.res_full[q][c & 1], (uint32_t)(c >> 1));
+        const float4* b4 = reinterpret_cast<const float4*>(b2 + 32 * c);
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = b4[j];
+          const float4 hh = stg[lane][j ^ (lane & 7)];
+          const float a0 = __fadd_rn(hh.x, __fadd_rn(unscale<true>(r[c][4 * j + 0]), bb.x));
+          const float a1 = __fadd_rn(hh.y, __fadd_rn(unscale<true>(r[c][4 * j + 1]), bb.y));
+          const float a2 = __fadd_rn(hh.z, __fadd_rn(unscale<true>(r[c][4 * j + 2]), bb.z));
+          const float a3 = __fadd_rn(hh.w, __fadd_rn(unscale<true>(r[c][4 * j + 3]), bb.w));
+          t[j] = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
+          r[c][4 * j + 0] = __float_as_uint(a0); r[c][4 * j + 1] = __float_as_uint(a1);
+          r[c][4 * j + 2] = __float_as_uint(a2); r[c][4 * j + 3] = __float_as_uint(a3);
+        }
+        pc[c] = __fadd_rn(__fadd_rn(__fadd_rn(t[0], t[1]), __fadd_rn(t[2], t[3])),
+                          __fadd_rn(__fadd_rn(t[4], t[5]), __fadd_rn(t[6], t[7])));
+        asm volatile("" ::"f"(pc[c]) : "memory");         // every lane has consumed the chunk before it is handed on
+        __syncwarp();
+        if (c < 2 && lane == 0) {
+          mbar_arrive_expect_tx(&s.res_full[q][c & 1], 32 * 32 * 4);
+          tma_load_2d(&tmR, &s.res_full[q][c & 1], stg, 32 * (c + 2), m0 + q * 32);
+        }
+      }
+      const float mu = __fmul_rn(__fadd_rn(__fadd_rn(pc[0], pc[1]), __fadd_rn(pc[2], pc[3])), 1.f / 128.f);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d0 = __fsub_rn(__uint_as_float(r[c][4 * j + 0]), mu), d1 = __fsub_rn(__uint_as_float(r[c][4 * j + 1]), mu);
+          const float d2 = __fsub_rn(__uint_as_float(r[c][4 * j + 2]), mu), d3 = __fsub_rn(__uint_as_float(r[c][4 * j + 3]), mu);
+          t[j] = __fmaf_rn(d3, d3, __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0))));
+          r[c][4 * j + 0] = __float_as_uint(d0); r[c][4 * j + 1] = __float_as_uint(d1);
+          r[c][4 * j + 2] = __float_as_uint(d2); r[c][4 * j + 3] = __float_as_uint(d3);
+        }
+        pc[c] = __fadd_rn(__fadd_rn(__fadd_rn(t[0], t[1]), __fadd_rn(t[2], t[3])),
+                          __fadd_rn(__fadd_rn(t[4], t[5]), __fadd_rn(t[6], t[7])));
+      }
+      const float rs = rsqrtf(__fmaf_rn(__fadd_rn(__fadd_rn(pc[0], pc[1]), __fadd_rn(pc[2], pc[3])), 1.f / 128.f, 1e-5f));
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        const float4* g4 = reinterpret_cast<const float4*>(ln.gamma + 32 * c);
+        const float4* e4 = reinterpret_cast<const float4*>(ln.beta + 32 * c);
+        float4 (*stg)[8] = s.epi[q][c & 1];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 g = g4[j], be = e4[j];
+          float4 o;
+          o.x = __fmaf_rn(__fmul_rn(__uint_as_float(r[c][4 * j + 0]), rs), g.x, be.x);
+          o.y = __fmaf_rn(__fmul_rn(__uint_as_float(r[c][4 * j + 1]), rs), g.y, be.y);
+          o.z = __fmaf_rn(__fmul_rn(__uint_as_float(r[c][4 * j + 2]), rs), g.z, be.z);
+          o.w = __fmaf_rn(__fmul_rn(__uint_as_float(r[c][4 * j + 3]), rs), g.w, be.w);
+          stg[lane][j ^ (lane & 7)] = o;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmC, stg, 32 * c, m0 + q * 32);
+          bulk_commit();
+        }
+      }
+      if (lane == 0 && mt + stride < m_tiles) {
+        bulk_wait_read<0>();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          mbar_arrive_expect_tx(&s.res_full[q][c], 32 * 32 * 4);
+          tma_load_2d(&tmR, &s.res_full[q][c], s.epi[q][c], 32 * c, m0 + stride * kBM + q * 32);
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0) bulk_wait_read<0>();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+  }
+}
+
+// x[M][128] <- LayerNorm(x + linear2(relu(linear1(x)))) with the fp16 halves of W1 [ff][128] and W2 [128][ff] (as
+// tf_split_weights(.., true) writes them).  out may be x.  QX_EUNSUPPORTED when ff is not a multiple of 128.
+int tf_ffn_fused(const float* x, const float* W1hi, const float* W1lo, const float* b1, const float* W2hi, const float* W2lo,
+                 const float* b2, const float* gamma, const float* beta, float* out, int M, int ff, cudaStream_t st) {
+  if (ff % 128 != 0 || ff < 128 || M < 1) return QX_EUNSUPPORTED;
+  CUtensorMap mx, m1h, m1l, m2h, m2l, mc, mr;
+  int rc;
+  if ((rc = make_map(&mx, x, M, kBN)) || (rc = make_map(&m1h, W1hi, ff, kBN / 2)) || (rc = make_map(&m1l, W1lo, ff, kBN / 2)) ||
+      (rc = make_map(&m2h, W2hi, kBN, ff / 2)) || (rc = make_map(&m2l, W2lo, kBN, ff / 2)) ||
+      (rc = make_map(&mc, out, M, kBN, 32, 32)) || (rc = make_map(&mr, x, M, kBN, 32, 32)))
+    return rc;
+  static bool cfgd[kMaxDevices] = {};
+  if (!cfgd[current_device_slot()]) {
+    cudaFuncSetAttribute(tf_ffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FfnSmem));
+    cfgd[current_device_slot()] = true;
+  }
+  const int num_sms = device_sm_count();
+  const int m_tiles = ceil_div(M, kBM);
+  const int grid = num_sms < m_tiles ? num_sms : m_tiles;
+  tf_ffn_kernel<<<grid, 320, sizeof(FfnSmem), st>>>(mx, m1h, m1l, m2h, m2l, mc, mr, b1, b2, LnArgs{gamma, beta}, M, ff);
+  QX_CHECK_LAUNCH("tf_ffn_kernel");
+  return QX_OK;
+}
+
 int tf_split_weights(const float* w, float* hi, float* lo, size_t count, cudaStream_t st, bool f16) {
   if (f16) tf_split16_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(w, reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), count);
   else tf_split_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(w, hi, lo, count);
