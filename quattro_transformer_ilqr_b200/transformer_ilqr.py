@@ -228,9 +228,13 @@ class TransformerILQR:
                                          C.c_void_p(ws.data_ptr()), engine.B, engine.stream), "qx_tf_forward")
         # embed, head, unpack + per layer QKV, attention, out-proj, add+LN, linear1, linear2, add+LN; on the tensor-core
         # path the two add+LN ride in the GEMM epilogues (QX_TF_FUSE_LN, qx_tf_simt.cu), except norm1 of the pruned last layer
+        # (d = 128), and with the fp16 split linear1 + linear2 + norm2 are ONE launch (tf_ffn_kernel, QX_TF_FFN_FUSE)
         fuse = int(os.environ.get("QX_TF_FUSE_LN", "3")) if self.tensor_cores else 0
         pruned = self.tensor_cores and os.environ.get("QX_TF_NO_PRUNE", "0") != "1"
-        engine.launches += (3 + (7 - (fuse & 1) - ((fuse >> 1) & 1)) * self.num_decoder_layers
+        f16 = (self.tensor_cores and os.environ.get("QX_TF_GEMM_F16", "1") != "0"
+               and os.environ.get("QX_TF_GEMM_STREAM", "0") != "1")
+        ffn = 1 if f16 and (fuse & 2) and os.environ.get("QX_TF_FFN_FUSE", "1") != "0" else 0
+        engine.launches += (3 + (7 - (fuse & 1) - ((fuse >> 1) & 1) - ffn) * self.num_decoder_layers
                             + (1 if (fuse & 1) and pruned else 0))
 
     def predict(self, x_seq, kK_seq):
