@@ -177,12 +177,14 @@ int qx_forward_pass(const QxParams* p, const double* x_in, const double* u_in, c
  * last prompt_len gain records, writes gain records for t in [0, target_len). */
 size_t qx_tf_weight_floats(const QxTfConfig* cfg);
 size_t qx_tf_workspace_bytes(const QxTfConfig* cfg, int B);
-/* Tensor-core path: the four dense weights of every layer split once into (hi, lo) TF32 halves
- * (3xTF32, fp32-accurate products).  wsplit has qx_tf_split_floats() floats. */
+/* Tensor-core path: the four dense weights of every layer (and the padded output head) split once into (hi, lo)
+ * halves for three-term fp32-accurate products hi hi + hi lo + lo hi - as fp16 halves of 2^8 W (kind::f16, what the
+ * forward pass uses) and as TF32 halves (kind::tf32; QX_TF_GEMM_F16=0).  wsplit has qx_tf_split_floats() floats. */
 size_t qx_tf_split_floats(const QxTfConfig* cfg);
 int qx_tf_prepare(const QxTfConfig* cfg, const float* weights, float* wsplit, void* stream);
-/* wsplit == NULL selects the exact-fp32 CUDA-core GEMMs; otherwise the dense layers run on
- * tcgen05 (kind::tf32, TMEM accumulators, TMA-staged operands). */
+/* wsplit == NULL selects the exact-fp32 CUDA-core GEMMs; otherwise the dense layers run on tcgen05 (TMEM accumulators
+ * and A operands, TMA-staged weights), the feed-forward block of a layer as one launch whose ff-wide intermediate
+ * never leaves the SM (QX_TF_FFN_FUSE=0: two launches, same bits), attention as kind::tf32 products. */
 int qx_tf_forward(const QxTfConfig* cfg, const float* weights, const float* wsplit, const double* x,
                   const double* x_shift, float* gains, int model_id, const int32_t* status, void* workspace, int B,
                   void* stream);

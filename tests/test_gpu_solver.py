@@ -429,6 +429,29 @@ def test_fp16_split_dense_layers_match_tf32_split_and_exact_path(system, golden_
 
 
 @pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
+@pytest.mark.parametrize("n_traj", [3, 1200])
+def test_fused_ffn_equals_two_launches_bitwise(system, n_traj, golden_dir, monkeypatch):
+    """tf_ffn_kernel (linear1 + ReLU + linear2 + residual + norm2 in one launch, the ff-wide intermediate kept in tensor
+    memory) issues the products of the two-launch path in the same order with the same roundings: identical predictions.
+    ff = 512 (quadrotor, four hidden chunks) and 256 (cart-pole, two); 3 trajectories = fewer tiles than SMs and a ragged
+    last tile, 1 200 = several tiles per CTA (every barrier phase, the weight ring wrapping many times), plus the compact
+    row stream of the pruned last layer in both."""
+    g = np.load(f"{golden_dir}/tf_forward_{system}.npz")
+    w = _wrapper(system, "rand")
+    rng = np.random.default_rng(17)
+    reps = max(1, n_traj // len(g["x_err"]))
+    x = np.concatenate([g["x_err"] * (1.0 + 0.05 * rng.standard_normal(g["x_err"].shape)) for _ in range(reps)])[:max(n_traj, 1)]
+    kK = np.concatenate([g["kK"] * (1.0 + 0.05 * rng.standard_normal(g["kK"].shape)) for _ in range(reps)])[:max(n_traj, 1)]
+    monkeypatch.setenv("QX_TF_FFN_FUSE", "0")
+    two = w.predict(x, kK)
+    monkeypatch.setenv("QX_TF_FFN_FUSE", "1")
+    one = w.predict(x, kK)
+    assert np.isfinite(one).all()
+    assert np.array_equal(one, two), f"{relmax(one, two):.2e}"
+    assert np.array_equal(one, w.predict(x, kK))          # and the same bits from run to run
+
+
+@pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
 def test_resident_weight_gemm_equals_streaming_gemm_bitwise(system, golden_dir, monkeypatch):
     """The K = 128 layers run on the resident-weight tcgen05 kernel (weights parked in shared memory, A streamed
     through a 3 + 2 block ring); it issues the same MMAs in the same order as the streaming kernel, so the
