@@ -64,6 +64,19 @@ constexpr uint32_t idesc_tf32(int n, bool b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (b_mn_major ? (1u << 16) : 0u) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
 }
 
+// The operand split of this kernel: hi = x rounded to the nearest TF32, lo = x - hi, exact and NOT rounded: the tensor
+// core reads the upper 19 bits of a kind::tf32 operand and ignores the rest, so lo enters the products truncated to its
+// top 11 bits - an error of 2^-10 |lo| <= 2^-21 |x| where the rounded lo of tf32_split() has 2^-22 |x|, for three
+// instructions per element instead of five (the splits were 45 % of the kernel's instructions and it is bound by them).
+__device__ __forceinline__ void attn_split(float v, float& hi, float& lo) {
+  hi = tf32_rn(v);
+#ifdef QX_ATTN_SPLIT_RN
+  lo = tf32_rn(v - hi);
+#else
+  lo = v - hi;
+#endif
+}
+
 template <int W>
 struct TmemRow;      // tcgen05.ld / st of W consecutive columns of this thread's lane (32x32b shape)
 template <>
@@ -126,10 +139,10 @@ __device__ __forceinline__ void split_tile_row(float* hi_tile, float* lo_tile, i
     const int c = (4 * half + jj) ^ (row & 7);
     const float4 v = hi4[c];
     float4 h, l;
-    tf32_split(v.x, h.x, l.x);
-    tf32_split(v.y, h.y, l.y);
-    tf32_split(v.z, h.z, l.z);
-    tf32_split(v.w, h.w, l.w);
+    attn_split(v.x, h.x, l.x);
+    attn_split(v.y, h.y, l.y);
+    attn_split(v.z, h.z, l.z);
+    attn_split(v.w, h.w, l.w);
     hi4[c] = h;
     lo4[c] = l;
   }
@@ -145,10 +158,10 @@ __device__ __forceinline__ void split_raw_row(const float* raw_tile, float* hi_t
     const int c = (4 * half + jj) ^ (row & 7);
     const float4 v = raw4[c];
     float4 h, l;
-    tf32_split(v.x, h.x, l.x);
-    tf32_split(v.y, h.y, l.y);
-    tf32_split(v.z, h.z, l.z);
-    tf32_split(v.w, h.w, l.w);
+    attn_split(v.x, h.x, l.x);
+    attn_split(v.y, h.y, l.y);
+    attn_split(v.z, h.z, l.z);
+    attn_split(v.w, h.w, l.w);
     hi4[c] = h;
     lo4[c] = l;
   }
@@ -164,10 +177,10 @@ __device__ __forceinline__ void split_q_row(float* hi_tile, float* lo_tile, int 
     float4 v = hi4[c];
     v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
     float4 h, l;
-    tf32_split(v.x, h.x, l.x);
-    tf32_split(v.y, h.y, l.y);
-    tf32_split(v.z, h.z, l.z);
-    tf32_split(v.w, h.w, l.w);
+    attn_split(v.x, h.x, l.x);
+    attn_split(v.y, h.y, l.y);
+    attn_split(v.z, h.z, l.z);
+    attn_split(v.w, h.w, l.w);
     hi4[c] = h;
     lo4[c] = l;
   }
@@ -226,7 +239,7 @@ __device__ __forceinline__ float softmax_half_row(uint32_t tmem_row, int lrev, i
       if (c == Q && HW * half + t > lrev) p = 0.f;
       l4[t & 3] += p;
       float h, lw;
-      tf32_split(p, h, lw);
+      attn_split(p, h, lw);
       r[c][t] = __float_as_uint(h);
       lo[t] = __float_as_uint(lw);
     }
@@ -291,7 +304,7 @@ __device__ __forceinline__ float softmax_pair_row(uint32_t tmem_row, uint32_t s_
       if (c == Q && 16 * half + t > lrev) p = 0.f;
       l4[t & 3] += p;
       float h, lw;
-      tf32_split(p, h, lw);
+      attn_split(p, h, lw);
       r[c][t] = __float_as_uint(h);
       lo[t] = __float_as_uint(lw);
     }
@@ -405,10 +418,10 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     for (int jj = 0; jj < 4; ++jj) {
       const float4 v = src[(4 * half + jj) ^ (row & 7)];
       float h, l;
-      tf32_split(v.x * scale_log2, h, l); hi[4 * jj + 0] = __float_as_uint(h); lo[4 * jj + 0] = __float_as_uint(l);
-      tf32_split(v.y * scale_log2, h, l); hi[4 * jj + 1] = __float_as_uint(h); lo[4 * jj + 1] = __float_as_uint(l);
-      tf32_split(v.z * scale_log2, h, l); hi[4 * jj + 2] = __float_as_uint(h); lo[4 * jj + 2] = __float_as_uint(l);
-      tf32_split(v.w * scale_log2, h, l); hi[4 * jj + 3] = __float_as_uint(h); lo[4 * jj + 3] = __float_as_uint(l);
+      attn_split(v.x * scale_log2, h, l); hi[4 * jj + 0] = __float_as_uint(h); lo[4 * jj + 0] = __float_as_uint(l);
+      attn_split(v.y * scale_log2, h, l); hi[4 * jj + 1] = __float_as_uint(h); lo[4 * jj + 1] = __float_as_uint(l);
+      attn_split(v.z * scale_log2, h, l); hi[4 * jj + 2] = __float_as_uint(h); lo[4 * jj + 2] = __float_as_uint(l);
+      attn_split(v.w * scale_log2, h, l); hi[4 * jj + 3] = __float_as_uint(h); lo[4 * jj + 3] = __float_as_uint(l);
     }
     __syncwarp();        // reconverge after the per-lane spins: tcgen05.st / wait::st are .sync.aligned
     TmemRow<16>::st(tmem_row + kColQ + 16 * half, hi);
