@@ -406,10 +406,12 @@ static bool tf_ops_f16() {
   const char* e = getenv("QX_TF_DENSE_F16");
   return e != nullptr && e[0] == '1';
 }
-static bool tf_use_f16() {
+// The fp16 kernel needs K % 128 == 0 for every dense layer (K = d or ff); other shapes stay on the TF32 split, whose
+// streaming kernel takes any K % 32 == 0.
+static bool tf_use_f16(const TfLayout& lay) {
   const char* e = getenv("QX_TF_GEMM_F16");
   const char* s1 = getenv("QX_TF_GEMM_STREAM");
-  return !(e != nullptr && e[0] == '0') && !(s1 != nullptr && s1[0] == '1');
+  return lay.d % 128 == 0 && lay.ff % 128 == 0 && !(e != nullptr && e[0] == '0') && !(s1 != nullptr && s1[0] == '1');
 }
 
 int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, const double* x, const double* x_shift,
@@ -441,7 +443,7 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
     att_cfg[current_device_slot()] = true;
   }
   const SplitLayout sp(lay);
-  const bool f16 = tf_use_f16();
+  const bool f16 = tf_use_f16(lay);
   // the (hi, lo) halves the tensor-core kernels read for the weight whose TF32 halves sit at p: p itself, or its fp16 twin
   auto wh = [&](const float* p) -> const float* { return f16 ? wsplit + sp.total32 + (size_t)(p - wsplit) / 2 : p; };
   // dense contraction: tcgen05 three-term split when split weights are supplied, exact-fp32 CUDA cores otherwise

@@ -233,7 +233,8 @@ class TransformerILQR:
         fuse = int(os.environ.get("QX_TF_FUSE_LN", "3")) if self.tensor_cores else 0
         pruned = self.tensor_cores and os.environ.get("QX_TF_NO_PRUNE", "0") != "1"
         f16 = (self.tensor_cores and os.environ.get("QX_TF_GEMM_F16", "1") != "0"
-               and os.environ.get("QX_TF_GEMM_STREAM", "0") != "1")
+               and os.environ.get("QX_TF_GEMM_STREAM", "0") != "1"
+               and self.d_model % 128 == 0 and self.dim_feedforward % 128 == 0)
         ffn = 1 if f16 and (fuse & 2) and os.environ.get("QX_TF_FFN_FUSE", "1") != "0" else 0
         engine.launches += (3 + (7 - (fuse & 1) - ((fuse >> 1) & 1) - ffn) * self.num_decoder_layers
                             + (1 if (fuse & 1) and pruned else 0))
