@@ -796,7 +796,7 @@ int tf_gemm_ln_tc(const float* A, const float* Whi, const float* Wlo, const floa
 // its order of accumulation and every rounding are those of the two-launch path, so the results are the same bits.
 //   tensor memory   Y [0,128) | H_j [128,256) | X hi [256,320) lo [320,384) | H_j hi [384,448) lo [448,512)   (fp16: 2 k / column)
 //   shared memory   4 weight slots (128 rows x 64 k, hi + lo: 32 KB) | X landing: four 32-float blocks | LN staging
-//   warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 split X / convert H_j (thread = row), warps 6-9 LayerNorm epilogue
+//   warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 split X / convert H_j (two threads per row), warps 10-13 LayerNorm epilogue
 // The MMA warp runs one product ahead: G1(0) G1(1) G2(0) G1(2) G2(1) .. G2(C-1), so that the conversion of chunk j has the
 // time of G1(j+1) to finish before the tensor pipe would wait for it; the weight blocks come in that order.
 constexpr uint32_t kFfnY = 0, kFfnH = 128, kFfnX = 256, kFfnH16 = 384;
@@ -811,7 +811,7 @@ struct FfnSmem {
 };
 static_assert(sizeof(FfnSmem) <= 227 * 1024, "fused FFN exceeds the shared memory of an SM");
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(448, 1)
 tf_ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1hi,
               const __grid_constant__ CUtensorMap tmW1lo, const __grid_constant__ CUtensorMap tmW2hi,
               const __grid_constant__ CUtensorMap tmW2lo, const __grid_constant__ CUtensorMap tmC,
@@ -834,11 +834,11 @@ tf_ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       mbar_init(&s.raw_full[i], 1);
       mbar_init(&s.raw_empty[i], 128);
     }
-    mbar_init(&s.x_ready, 128);
+    mbar_init(&s.x_ready, 256);
     mbar_init(&s.x_free, 1);
     mbar_init(&s.hacc_full, 1);
-    mbar_init(&s.hacc_empty, 128);
-    mbar_init(&s.h16_ready, 128);
+    mbar_init(&s.hacc_empty, 256);
+    mbar_init(&s.h16_ready, 256);
     mbar_init(&s.h16_free, 1);
     mbar_init(&s.y_full, 1);
     mbar_init(&s.y_empty, 128);
@@ -946,18 +946,20 @@ tf_ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       }
       g2(C - 1);
     }
-  } else if (warp < 6) {
-    // ---- split X, then convert every hidden chunk: thread = row ----------------------------------------------------
-    const int q = warp & 3;
+  } else if (warp < 10) {
+    // ---- split X, then convert every hidden chunk: two threads per row (warps w and w + 4 share a lane quarter and take
+    //      64 of the 128 k each) - the conversion of a chunk has to fit into the time of one product -----------------
+    const int q = warp & 3, part = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-    uint32_t rit = 0, tl = 0, ct = 0;
+    uint32_t tl = 0, ct = 0;
     for (int mt = blockIdx.x; mt < m_tiles; mt += stride, ++tl) {
       mbar_wait(&s.x_free, (tl & 1u) ^ 1u);                // the previous tile's first products are done with its X
-      for (int kb = 0; kb < 4; ++kb, ++rit) {
-        const int st = rit & 3;
-        mbar_wait(&s.raw_full[st], (rit >> 2) & 1u);
-        const float4* src = reinterpret_cast<const float4*>(s.raw[st]) + row * 8;
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int kb = 2 * part + kk;                      // landing block = ring slot: four blocks per tile, four slots
+        mbar_wait(&s.raw_full[kb], tl & 1u);
+        const float4* src = reinterpret_cast<const float4*>(s.raw[kb]) + row * 8;
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -969,7 +971,7 @@ tf_ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         tcgen05_fence_after();
         tmem_st_32x32b_x16(trow + kFfnX + 16 * kb, hi);
         tmem_st_32x32b_x16(trow + kFfnX + 64 + 16 * kb, lo);
-        mbar_arrive(&s.raw_empty[st]);                     // behind the stores, which consume every loaded value
+        mbar_arrive(&s.raw_empty[kb]);                     // behind the stores, which consume every loaded value
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tcgen05_fence_before();
@@ -978,16 +980,16 @@ tf_ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         mbar_wait(&s.hacc_full, ct & 1u);
         __syncwarp();
         tcgen05_fence_after();
-        uint32_t r[4][32];
+        uint32_t r[2][32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(trow + kFfnH + 32 * c, r[c]);
+        for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(trow + kFfnH + 32 * (2 * part + c), r[c]);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         tcgen05_fence_before();
         mbar_arrive(&s.hacc_empty);
-        const float* bj = b1 + j * 128;
+        const float* bj = b1 + j * 128 + 64 * part;
         bool waited = false;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t hi[16], lo[16];
           const float4* b4 = reinterpret_cast<const float4*>(bj + 32 * c);
 #pragma unroll
@@ -1006,8 +1008,8 @@ tf_ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             tcgen05_fence_after();
             waited = true;
           }
-          tmem_st_32x32b_x16(trow + kFfnH16 + 16 * c, hi);
-          tmem_st_32x32b_x16(trow + kFfnH16 + 64 + 16 * c, lo);
+          tmem_st_32x32b_x16(trow + kFfnH16 + 16 * (2 * part + c), hi);
+          tmem_st_32x32b_x16(trow + kFfnH16 + 64 + 16 * (2 * part + c), lo);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tcgen05_fence_before();
@@ -1143,7 +1145,7 @@ int tf_ffn_fused(const float* x, const float* W1hi, const float* W1lo, const flo
   const int num_sms = device_sm_count();
   const int m_tiles = ceil_div(M, kBM);
   const int grid = num_sms < m_tiles ? num_sms : m_tiles;
-  tf_ffn_kernel<<<grid, 320, sizeof(FfnSmem), st>>>(mx, m1h, m1l, m2h, m2l, mc, mr, b1, b2, LnArgs{gamma, beta}, M, ff);
+  tf_ffn_kernel<<<grid, 448, sizeof(FfnSmem), st>>>(mx, m1h, m1l, m2h, m2l, mc, mr, b1, b2, LnArgs{gamma, beta}, M, ff);
   QX_CHECK_LAUNCH("tf_ffn_kernel");
   return QX_OK;
 }
