@@ -379,6 +379,9 @@ int tf_gemm_ln_tc(const float* A, const float* Whi, const float* Wlo, const floa
                   const float* beta, float* C, int M, int K, cudaStream_t st, bool f16);
 int tf_ffn_fused(const float* x, const float* W1hi, const float* W1lo, const float* b1, const float* W2hi, const float* W2lo,
                  const float* b2, const float* gamma, const float* beta, float* out, int M, int ff, cudaStream_t st);
+int tf_tail_fused(const float* att, const float* Wohi, const float* Wolo, const float* bo, const float* g1, const float* be1,
+                  float* x, const float* W1hi, const float* W1lo, const float* b1, const float* W2hi, const float* W2lo,
+                  const float* b2, const float* g2, const float* be2, int M, int ff, cudaStream_t st);
 
 // offsets of the (hi, lo) copies of the four GEMM weights of one layer inside the split buffer
 struct SplitLayout {
@@ -532,6 +535,17 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
       if (rc) return rc;
       hfinal = hc;
       break;
+    }
+    // out-proj + norm1 + the feed-forward block + norm2 in ONE launch (tf_tail_kernel) when ff <= 256, where it is faster
+    // than out-proj + norm1 as a launch of their own (QX_TF_TAIL_FUSE=0: never, =2: whatever ff is; same bits)
+    const char* env_tl = getenv("QX_TF_TAIL_FUSE");
+    const bool tail = env_tl != nullptr ? (env_tl[0] == '2' || (env_tl[0] == '1' && ff <= 256)) : ff <= 256;
+    if (fuse_ffn && (fuse & 1) && tail) {
+      rc = tf_tail_fused(att, wh(sw + sp.out_hi), wh(sw + sp.out_lo), lw + lay.l_outb, lw + lay.l_n1w, lw + lay.l_n1b, h,
+                         wh(sw + sp.w1_hi), wh(sw + sp.w1_lo), lw + lay.l_b1, wh(sw + sp.w2_hi), wh(sw + sp.w2_lo), lw + lay.l_b2,
+                         lw + lay.l_n2w, lw + lay.l_n2b, rows, ff, st);
+      if (rc == QX_OK) continue;
+      if (rc != QX_EUNSUPPORTED) return rc;
     }
     if ((rc = dense_ln(fuse & 1, att, lay.l_outw, lay.l_outb, sp.out_hi, sp.out_lo, d, h, lay.l_n1w, lay.l_n1b, h, rows, rows, rows, 0)))
       return rc;

@@ -1126,6 +1126,552 @@ tf_ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   }
 }
 
+// ---- the whole tail of an encoder layer as ONE kernel ---------------------------------------------------------------
+//   h1 = LayerNorm1(x + out_proj(att));   x <- LayerNorm2(h1 + linear2(relu(linear1(h1))))
+// tf_ffn_kernel with one more product in front: G0 = att W_out^T goes through the SAME tensor-memory regions (att halves
+// where X's will be, its accumulator where the hidden chunks' will be).  norm1 runs on the eight CONVERTER warps (two
+// threads per row, partial sums exchanged through shared memory): they read G0's accumulator and the residual rows (a
+// TMA load into the landing blocks the att tile has left), and write h1 twice - as fp16 halves straight into the X
+// columns of tensor memory, and as fp32 over the residual in the landing blocks, from where one TMA store per half
+// puts it into x for the residual of norm2.  The separate out-proj launch (1.27 GB at the HBM roof) is gone and h1 is
+// never read from HBM by a product.  A tile's G0 is issued inside the previous tile's last chunk:
+//   MMA warp     .. G1(C-1) G2(C-2) | G0' | G2(C-1) | G1'(0) ..         (' = next tile)
+//   converters   .. read H(C-1), split att', convert H(C-1), norm1' ..
+// (With norm1 on the four thread-per-row LayerNorm warps - ~8 000 cycles per normalisation under the 128-register cap -
+// the kernel took 0.93 ms against 0.52 + 0.24 for the two launches: the converters waited for h1 45 % of the time.)
+// Same products, accumulation order and roundings as the separate launches: same bits.
+// The converter warps are the bottleneck of this kernel (83 % busy): with two hidden chunks a tile (cart-pole, ff = 256)
+// it beats out-proj + feed-forward as two launches (step 1.39 -> 1.32 ms), with four (quadrotor, ff = 512: 0.85 ms
+// against 0.52 + 0.24) it does not, so the forward pass takes it for ff <= 256 only (QX_TF_TAIL_FUSE=2: always, =0: never).
+struct TailSmem {
+  float w_hi[kTaW][kBN * kBK];
+  float w_lo[kTaW][kBN * kBK];
+  float raw[4][kBM * kBK];       // att tile as four 32-float blocks (TMA), then the residual x rows (TMA), then h1 (norm1)
+  float4 epi[4][2][32][8];
+  float xch[2][2][kBM];          // [sum | centred second moment][column half][row]: the two threads of a row meet here
+  uint64_t w_full[kTaW], w_empty[kTaW], att_full[4], att_done, res_in[4], a_ready, o_full, h1_done, x_ready, x_free, hacc_full,
+      hacc_empty, h16_ready, h16_free, y_full, y_empty, res_full[4][2];
+  uint32_t tmem_base;
+  uint32_t h1_cnt;               // h1 stores completed (two per tile): a COUNT, the norm2 warps may be two tiles behind
+};
+static_assert(sizeof(TailSmem) <= 227 * 1024, "fused layer tail exceeds the shared memory of an SM");
+
+struct TailArgs {
+  const float* bo;       // out_proj.bias
+  const float* g1;       // norm1
+  const float* be1;
+  const float* b1;       // linear1.bias
+  const float* b2;       // linear2.bias
+  const float* g2;       // norm2
+  const float* be2;
+};
+
+__global__ void __launch_bounds__(448, 1)
+tf_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmX,
+               const __grid_constant__ CUtensorMap tmWohi, const __grid_constant__ CUtensorMap tmWolo,
+               const __grid_constant__ CUtensorMap tmW1hi, const __grid_constant__ CUtensorMap tmW1lo,
+               const __grid_constant__ CUtensorMap tmW2hi, const __grid_constant__ CUtensorMap tmW2lo,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TailArgs a, int M, int ff) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  TailSmem& s = *reinterpret_cast<TailSmem*>(smem_raw);
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u)) __trap();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = ff / 128;
+  const int m_tiles = ceil_div(M, kBM);
+  const int stride = gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kTaW; ++i) {
+      mbar_init(&s.w_full[i], 1);
+      mbar_init(&s.w_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s.att_full[i], 1);
+      mbar_init(&s.res_in[i], 1);
+    }
+    mbar_init(&s.att_done, 256);
+    mbar_init(&s.a_ready, 256);
+    mbar_init(&s.o_full, 1);
+    mbar_init(&s.h1_done, 2);
+    s.h1_cnt = 0u;
+    mbar_init(&s.x_ready, 256);
+    mbar_init(&s.x_free, 1);
+    mbar_init(&s.hacc_full, 1);
+    mbar_init(&s.hacc_empty, 256);
+    mbar_init(&s.h16_ready, 256);
+    mbar_init(&s.h16_free, 1);
+    mbar_init(&s.y_full, 1);
+    mbar_init(&s.y_empty, 128);
+    for (int i = 0; i < 8; ++i) mbar_init(&s.res_full[i >> 1][i & 1], 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = s.tmem_base;
+  const bool have = (int)blockIdx.x < m_tiles;
+
+  if (warp == 0) {
+    // ---- TMA producer: att tiles, residual rows, and the weight blocks in the order the MMA warp consumes them ------
+    if (lane == 0 && have) {
+      uint32_t wit = 0, tl = 0;
+      // kind 0: W_out (G0), 1: W1 rows of chunk j (G1), 2: W2 columns of chunk j (G2)
+      auto w_blocks = [&](int kind, int j) {
+        for (int kb = 0; kb < 2; ++kb, ++wit) {
+          const int sw = wit % kTaW;
+          mbar_wait(&s.w_empty[sw], ((wit / kTaW) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&s.w_full[sw], 2 * kTileBytes);
+          if (kind == 0) {
+            tma_load_2d(&tmWohi, &s.w_full[sw], s.w_hi[sw], kb * kBK, 0);
+            tma_load_2d(&tmWolo, &s.w_full[sw], s.w_lo[sw], kb * kBK, 0);
+          } else if (kind == 1) {
+            tma_load_2d(&tmW1hi, &s.w_full[sw], s.w_hi[sw], kb * kBK, j * 128);
+            tma_load_2d(&tmW1lo, &s.w_full[sw], s.w_lo[sw], kb * kBK, j * 128);
+          } else {
+            tma_load_2d(&tmW2hi, &s.w_full[sw], s.w_hi[sw], (2 * j + kb) * kBK, 0);
+            tma_load_2d(&tmW2lo, &s.w_full[sw], s.w_lo[sw], (2 * j + kb) * kBK, 0);
+          }
+        }
+      };
+      auto load_att = [&](int mt) {
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_arrive_expect_tx(&s.att_full[kb], kTileBytes);
+          tma_load_2d(&tmA, &s.att_full[kb], s.raw[kb], kb * kBK, mt * kBM);
+        }
+      };
+      auto load_res = [&](int mt, uint32_t t) {             // the tile's x rows, once its att blocks have been split
+        mbar_wait(&s.att_done, t & 1u);
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_arrive_expect_tx(&s.res_in[kb], kTileBytes);
+          tma_load_2d(&tmX, &s.res_in[kb], s.raw[kb], kb * kBK, mt * kBM);
+        }
+      };
+      load_att(blockIdx.x);
+      w_blocks(0, 0);
+      load_res(blockIdx.x, 0);
+      for (int mt = blockIdx.x; mt < m_tiles; mt += stride, ++tl) {
+        const bool next = mt + stride < m_tiles;
+        w_blocks(1, 0);
+        if (next) {
+          mbar_wait(&s.h1_done, tl & 1u);                  // this tile's h1 has left the landing blocks
+          load_att(mt + stride);
+        }
+        for (int j = 1; j < C; ++j) {
+          w_blocks(1, j);
+          w_blocks(2, j - 1);
+        }
+        if (next) w_blocks(0, 0);
+        w_blocks(2, C - 1);
+        if (next) load_res(mt + stride, tl + 1);
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer ---------------------------------------------------------------------------------------------------
+    if (have) {
+      uint32_t wit = 0, tl = 0, n1 = 0, n2 = 0;
+      auto product = [&](uint32_t acc, uint32_t a_base, bool fresh) {
+        for (int kb = 0; kb < 2; ++kb, ++wit) {
+          const uint32_t sw = wit % kTaW;
+          mbar_wait(&s.w_full[sw], (wit / kTaW) & 1u);
+          tcgen05_fence_after();
+          const uint64_t dw_hi = umma_desc_sw128(s.w_hi[sw]), dw_lo = umma_desc_sw128(s.w_lo[sw]);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+              const uint32_t a_hi = a_base + kb * 32 + k * 8, a_lo = a_hi + 64;
+              mma_f16_ta(acc, a_lo, dw_hi + adv, kIdescF16, (fresh && kb == 0 && k == 0) ? 0u : 1u);
+              mma_f16_ta(acc, a_hi, dw_lo + adv, kIdescF16, 1u);
+              mma_f16_ta(acc, a_hi, dw_hi + adv, kIdescF16, 1u);
+            }
+            tcgen05_commit(&s.w_empty[sw]);
+          }
+          __syncwarp();
+        }
+      };
+      auto g0 = [&](uint32_t t) {                           // out-proj of tile t into the hidden accumulator's columns
+        mbar_wait(&s.a_ready, t & 1u);
+        mbar_wait(&s.hacc_empty, (n1 & 1u) ^ 1u);          // the last hidden chunk's accumulator has been read
+        tcgen05_fence_after();
+        product(tmem + kFfnH, tmem + kFfnX, true);
+        if (elect_one()) tcgen05_commit(&s.o_full);
+        __syncwarp();
+      };
+      auto g1 = [&](int j) {
+        mbar_wait(&s.hacc_empty, (n1 & 1u) ^ 1u);
+        tcgen05_fence_after();
+        product(tmem + kFfnH, tmem + kFfnX, true);
+        if (elect_one()) {
+          tcgen05_commit(&s.hacc_full);
+          if (j == C - 1) tcgen05_commit(&s.x_free);
+        }
+        __syncwarp();
+        ++n1;
+      };
+      auto g2 = [&](int j) {
+        mbar_wait(&s.h16_ready, n2 & 1u);
+        if (j == 0) mbar_wait(&s.y_empty, (tl & 1u) ^ 1u);
+        tcgen05_fence_after();
+        product(tmem + kFfnY, tmem + kFfnH16, j == 0);
+        if (elect_one()) {
+          tcgen05_commit(&s.h16_free);
+          if (j == C - 1) tcgen05_commit(&s.y_full);
+        }
+        __syncwarp();
+        ++n2;
+      };
+      g0(0);
+      for (int mt = blockIdx.x; mt < m_tiles; mt += stride, ++tl) {
+        mbar_wait(&s.x_ready, tl & 1u);                    // norm1 has read G0's accumulator and written the X halves
+        tcgen05_fence_after();
+        g1(0);
+        for (int j = 1; j < C; ++j) {
+          g1(j);
+          g2(j - 1);
+        }
+        if (mt + stride < m_tiles) g0(tl + 1);
+        g2(C - 1);
+      }
+    }
+  } else if (warp < 10) {
+    // ---- converters: two threads per row (64 of the 128 columns each) ---------------------------------------------------
+    const int q = warp & 3, part = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    auto pair_bar = [&]() {          // the two warps of a lane quarter (named barriers 1-4)
+      switch (q) {
+        case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+        case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+        case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+        default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+      }
+    };
+    auto split_att = [&](uint32_t t) {
+      mbar_wait(&s.att_full[2 * part], t & 1u);
+      mbar_wait(&s.att_full[2 * part + 1], t & 1u);
+      __syncwarp();
+      tcgen05_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int kb = 2 * part + kk;
+        const float4* src = reinterpret_cast<const float4*>(s.raw[kb]) + row * 8;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 v = src[j ^ (row & 7)];
+          f16_split2(v.x, v.y, hi[2 * j + 0], lo[2 * j + 0]);
+          f16_split2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+        }
+        __syncwarp();
+        tmem_st_32x32b_x16(trow + kFfnX + 16 * kb, hi);
+        tmem_st_32x32b_x16(trow + kFfnX + 64 + 16 * kb, lo);
+      }
+      mbar_arrive(&s.att_done);                            // behind the stores, which consume every loaded value
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tcgen05_fence_before();
+      mbar_arrive(&s.a_ready);
+    };
+    // h1 = LayerNorm1(x + (G0 / 2^8 + bo)) for this thread's 64 columns of its row; arithmetic of tf_gemm_ta_kernel<LN>
+    auto norm1 = [&](uint32_t t, int m0) {
+      mbar_wait(&s.o_full, t & 1u);
+      __syncwarp();
+      tcgen05_fence_after();
+      uint32_t r[2][32];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) tmem_ld_32x32b_x32(trow + kFfnH + 32 * (2 * part + cc), r[cc]);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tcgen05_fence_before();
+      mbar_wait(&s.res_in[2 * part], t & 1u);
+      mbar_wait(&s.res_in[2 * part + 1], t & 1u);
+      float pc[2];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * part + cc;
+        const float4* blk = reinterpret_cast<const float4*>(s.raw[c]) + row * 8;
+        const float4* b4 = reinterpret_cast<const float4*>(a.bo + 32 * c);
+        float tt[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = b4[j];
+          const float4 hh = blk[j ^ (row & 7)];
+          const float a0 = __fadd_rn(hh.x, __fadd_rn(unscale<true>(r[cc][4 * j + 0]), bb.x));
+          const float a1 = __fadd_rn(hh.y, __fadd_rn(unscale<true>(r[cc][4 * j + 1]), bb.y));
+          const float a2 = __fadd_rn(hh.z, __fadd_rn(unscale<true>(r[cc][4 * j + 2]), bb.z));
+          const float a3 = __fadd_rn(hh.w, __fadd_rn(unscale<true>(r[cc][4 * j + 3]), bb.w));
+          tt[j] = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
+          r[cc][4 * j + 0] = __float_as_uint(a0); r[cc][4 * j + 1] = __float_as_uint(a1);
+          r[cc][4 * j + 2] = __float_as_uint(a2); r[cc][4 * j + 3] = __float_as_uint(a3);
+        }
+        pc[cc] = __fadd_rn(__fadd_rn(__fadd_rn(tt[0], tt[1]), __fadd_rn(tt[2], tt[3])),
+                           __fadd_rn(__fadd_rn(tt[4], tt[5]), __fadd_rn(tt[6], tt[7])));
+      }
+      // (pc0 + pc1) + (pc2 + pc3): each thread has one of the brackets
+      float mine = __fadd_rn(pc[0], pc[1]);
+      s.xch[0][part][row] = mine;
+      pair_bar();
+      float other = s.xch[0][part ^ 1][row];
+      const float mu = __fmul_rn(part == 0 ? __fadd_rn(mine, other) : __fadd_rn(other, mine), 1.f / 128.f);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        float tt[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d0 = __fsub_rn(__uint_as_float(r[cc][4 * j + 0]), mu), d1 = __fsub_rn(__uint_as_float(r[cc][4 * j + 1]), mu);
+          const float d2 = __fsub_rn(__uint_as_float(r[cc][4 * j + 2]), mu), d3 = __fsub_rn(__uint_as_float(r[cc][4 * j + 3]), mu);
+          tt[j] = __fmaf_rn(d3, d3, __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0))));
+          r[cc][4 * j + 0] = __float_as_uint(d0); r[cc][4 * j + 1] = __float_as_uint(d1);
+          r[cc][4 * j + 2] = __float_as_uint(d2); r[cc][4 * j + 3] = __float_as_uint(d3);
+        }
+        pc[cc] = __fadd_rn(__fadd_rn(__fadd_rn(tt[0], tt[1]), __fadd_rn(tt[2], tt[3])),
+                           __fadd_rn(__fadd_rn(tt[4], tt[5]), __fadd_rn(tt[6], tt[7])));
+      }
+      mine = __fadd_rn(pc[0], pc[1]);
+      s.xch[1][part][row] = mine;
+      pair_bar();
+      other = s.xch[1][part ^ 1][row];
+      const float rs = rsqrtf(__fmaf_rn(part == 0 ? __fadd_rn(mine, other) : __fadd_rn(other, mine), 1.f / 128.f, 1e-5f));
+      tcgen05_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * part + cc;
+        float4* blk = reinterpret_cast<float4*>(s.raw[c]) + row * 8;
+        const float4* g4 = reinterpret_cast<const float4*>(a.g1 + 32 * c);
+        const float4* e4 = reinterpret_cast<const float4*>(a.be1 + 32 * c);
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 g = g4[j], be = e4[j];
+          float4 o;
+          o.x = __fmaf_rn(__fmul_rn(__uint_as_float(r[cc][4 * j + 0]), rs), g.x, be.x);
+          o.y = __fmaf_rn(__fmul_rn(__uint_as_float(r[cc][4 * j + 1]), rs), g.y, be.y);
+          o.z = __fmaf_rn(__fmul_rn(__uint_as_float(r[cc][4 * j + 2]), rs), g.z, be.z);
+          o.w = __fmaf_rn(__fmul_rn(__uint_as_float(r[cc][4 * j + 3]), rs), g.w, be.w);
+          blk[j ^ (row & 7)] = o;                          // over the residual value this thread has consumed
+          f16_split2(o.x, o.y, hi[2 * j + 0], lo[2 * j + 0]);
+          f16_split2(o.z, o.w, hi[2 * j + 1], lo[2 * j + 1]);
+        }
+        __syncwarp();
+        tmem_st_32x32b_x16(trow + kFfnX + 16 * c, hi);      // G0 is complete (o_full): its att halves are dead
+        tmem_st_32x32b_x16(trow + kFfnX + 64 + 16 * c, lo);
+      }
+      fence_proxy_async();                                 // h1 in the landing blocks -> visible to the TMA store
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tcgen05_fence_before();
+      mbar_arrive(&s.x_ready);
+      // this half's two blocks (all 128 rows) go to x as the residual of norm2, then back to the producer
+      if (part == 0) asm volatile("bar.sync 5, 128;" ::: "memory");
+      else asm volatile("bar.sync 6, 128;" ::: "memory");
+      if (q == 0 && lane == 0) {                            // completion is awaited a chunk later (h1_flush): not here, where
+        tma_store_2d(&tmX, s.raw[2 * part], 32 * (2 * part), m0);          // the whole warp would stand still for it
+        tma_store_2d(&tmX, s.raw[2 * part + 1], 32 * (2 * part + 1), m0);
+        bulk_commit();
+      }
+    };
+    auto h1_flush = [&]() {
+      if (q == 0 && lane == 0) {
+        bulk_wait<0>();
+        __threadfence();
+        mbar_arrive(&s.h1_done);                           // the producer (never behind): the landing blocks are free
+        atomicAdd(&s.h1_cnt, 1u);                          // the norm2 warps: h1 is in memory
+      }
+    };
+    if (have) {
+      uint32_t tl = 0, ct = 0;
+      split_att(0);
+      norm1(0, blockIdx.x * kBM);
+      for (int mt = blockIdx.x; mt < m_tiles; mt += stride, ++tl) {
+        const bool next = mt + stride < m_tiles;
+        for (int j = 0; j < C; ++j, ++ct) {
+          mbar_wait(&s.hacc_full, ct & 1u);
+          __syncwarp();
+          tcgen05_fence_after();
+          uint32_t r[2][32];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(trow + kFfnH + 32 * (2 * part + c), r[c]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          tcgen05_fence_before();
+          mbar_arrive(&s.hacc_empty);
+          if (j == 0) h1_flush();                          // the tile's h1 store was issued a product ago
+          if (j == C - 1 && next) {
+            mbar_wait(&s.x_free, tl & 1u);                 // the tile's first products are done with its X halves
+            split_att(tl + 1);
+          }
+          const float* bj = a.b1 + j * 128 + 64 * part;
+          bool waited = false;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t hi[16], lo[16];
+            const float4* b4 = reinterpret_cast<const float4*>(bj + 32 * c);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float4 bb = b4[e];
+              const float v0 = fmaxf(__fadd_rn(unscale<true>(r[c][4 * e + 0]), bb.x), 0.f);
+              const float v1 = fmaxf(__fadd_rn(unscale<true>(r[c][4 * e + 1]), bb.y), 0.f);
+              const float v2 = fmaxf(__fadd_rn(unscale<true>(r[c][4 * e + 2]), bb.z), 0.f);
+              const float v3 = fmaxf(__fadd_rn(unscale<true>(r[c][4 * e + 3]), bb.w), 0.f);
+              f16_split2(v0, v1, hi[2 * e + 0], lo[2 * e + 0]);
+              f16_split2(v2, v3, hi[2 * e + 1], lo[2 * e + 1]);
+            }
+            if (!waited) {
+              mbar_wait(&s.h16_free, (ct & 1u) ^ 1u);
+              __syncwarp();
+              tcgen05_fence_after();
+              waited = true;
+            }
+            tmem_st_32x32b_x16(trow + kFfnH16 + 16 * (2 * part + c), hi);
+            tmem_st_32x32b_x16(trow + kFfnH16 + 64 + 16 * (2 * part + c), lo);
+          }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tcgen05_fence_before();
+          mbar_arrive(&s.h16_ready);
+        }
+        if (next) norm1(tl + 1, (mt + stride) * kBM);
+      }
+    }
+  } else {
+    // ---- norm2 (thread = row): x <- LayerNorm(h1 + (Y / 2^8 + b2)), as in tf_ffn_kernel; h1 comes back from x ---------
+    const int q = warp & 3;
+    uint32_t tl = 0;
+    // The first two residual boxes of a tile, once its h1 is in memory.  Not a parity wait: with two hidden chunks a tile
+    // is shorter than a normalisation, the converters can be two tiles ahead of these warps, and a barrier that has
+    // completed phases t AND t + 1 looks, to a wait for phase t, like one that has not completed it.
+    auto res_first = [&](int m0, uint32_t t) {
+      while (*reinterpret_cast<volatile uint32_t*>(&s.h1_cnt) < 2u * (t + 1u)) __nanosleep(64);
+      __threadfence();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        mbar_arrive_expect_tx(&s.res_full[q][c], 32 * 32 * 4);
+        tma_load_2d(&tmR, &s.res_full[q][c], s.epi[q][c], 32 * c, m0 + q * 32);
+      }
+    };
+    if (lane == 0 && have) res_first(blockIdx.x * kBM, 0);
+    for (int mt = blockIdx.x; mt < m_tiles; mt += stride, ++tl) {
+      const int m0 = mt * kBM;
+      mbar_wait(&s.y_full, tl & 1u);
+      __syncwarp();
+      tcgen05_fence_after();
+      const uint32_t tacc = tmem + kFfnY + ((uint32_t)(q * 32) << 16);
+      uint32_t r[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tacc + 32 * c, r[c]);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tcgen05_fence_before();
+      mbar_arrive(&s.y_empty);
+      float pc[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float4 (*stg)[8] = s.epi[q][c & 1];
+        mbar_wait(&s.res_full[q][c & 1], (uint32_t)(c >> 1));
+        const float4* b4 = reinterpret_cast<const float4*>(a.b2 + 32 * c);
+        float tt[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = b4[j];
+          const float4 hh = stg[lane][j ^ (lane & 7)];
+          const float a0 = __fadd_rn(hh.x, __fadd_rn(unscale<true>(r[c][4 * j + 0]), bb.x));
+          const float a1 = __fadd_rn(hh.y, __fadd_rn(unscale<true>(r[c][4 * j + 1]), bb.y));
+          const float a2 = __fadd_rn(hh.z, __fadd_rn(unscale<true>(r[c][4 * j + 2]), bb.z));
+          const float a3 = __fadd_rn(hh.w, __fadd_rn(unscale<true>(r[c][4 * j + 3]), bb.w));
+          tt[j] = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
+          r[c][4 * j + 0] = __float_as_uint(a0); r[c][4 * j + 1] = __float_as_uint(a1);
+          r[c][4 * j + 2] = __float_as_uint(a2); r[c][4 * j + 3] = __float_as_uint(a3);
+        }
+        pc[c] = __fadd_rn(__fadd_rn(__fadd_rn(tt[0], tt[1]), __fadd_rn(tt[2], tt[3])),
+                          __fadd_rn(__fadd_rn(tt[4], tt[5]), __fadd_rn(tt[6], tt[7])));
+        asm volatile("" ::"f"(pc[c]) : "memory");
+        __syncwarp();
+        if (c < 2 && lane == 0) {
+          mbar_arrive_expect_tx(&s.res_full[q][c & 1], 32 * 32 * 4);
+          tma_load_2d(&tmR, &s.res_full[q][c & 1], stg, 32 * (c + 2), m0 + q * 32);
+        }
+      }
+      const float mu = __fmul_rn(__fadd_rn(__fadd_rn(pc[0], pc[1]), __fadd_rn(pc[2], pc[3])), 1.f / 128.f);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float tt[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d0 = __fsub_rn(__uint_as_float(r[c][4 * j + 0]), mu), d1 = __fsub_rn(__uint_as_float(r[c][4 * j + 1]), mu);
+          const float d2 = __fsub_rn(__uint_as_float(r[c][4 * j + 2]), mu), d3 = __fsub_rn(__uint_as_float(r[c][4 * j + 3]), mu);
+          tt[j] = __fmaf_rn(d3, d3, __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0))));
+          r[c][4 * j + 0] = __float_as_uint(d0); r[c][4 * j + 1] = __float_as_uint(d1);
+          r[c][4 * j + 2] = __float_as_uint(d2); r[c][4 * j + 3] = __float_as_uint(d3);
+        }
+        pc[c] = __fadd_rn(__fadd_rn(__fadd_rn(tt[0], tt[1]), __fadd_rn(tt[2], tt[3])),
+                          __fadd_rn(__fadd_rn(tt[4], tt[5]), __fadd_rn(tt[6], tt[7])));
+      }
+      const float rs = rsqrtf(__fmaf_rn(__fadd_rn(__fadd_rn(pc[0], pc[1]), __fadd_rn(pc[2], pc[3])), 1.f / 128.f, 1e-5f));
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        const float4* g4 = reinterpret_cast<const float4*>(a.g2 + 32 * c);
+        const float4* e4 = reinterpret_cast<const float4*>(a.be2 + 32 * c);
+        float4 (*stg)[8] = s.epi[q][c & 1];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 g = g4[j], be = e4[j];
+          float4 o;
+          o.x = __fmaf_rn(__fmul_rn(__uint_as_float(r[c][4 * j + 0]), rs), g.x, be.x);
+          o.y = __fmaf_rn(__fmul_rn(__uint_as_float(r[c][4 * j + 1]), rs), g.y, be.y);
+          o.z = __fmaf_rn(__fmul_rn(__uint_as_float(r[c][4 * j + 2]), rs), g.z, be.z);
+          o.w = __fmaf_rn(__fmul_rn(__uint_as_float(r[c][4 * j + 3]), rs), g.w, be.w);
+          stg[lane][j ^ (lane & 7)] = o;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmC, stg, 32 * c, m0 + q * 32);
+          bulk_commit();
+        }
+      }
+      if (lane == 0 && mt + stride < m_tiles) {
+        bulk_wait_read<0>();
+        res_first(m0 + stride * kBM, tl + 1);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) bulk_wait_read<0>();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+  }
+}
+
+// x[M][128] <- LayerNorm2(h1 + linear2(relu(linear1(h1)))), h1 = LayerNorm1(x + att Wo^T + bo): out-proj, both LayerNorms
+// and the feed-forward block of an encoder layer in one launch.  All weight halves as tf_split_weights(.., true) writes them.
+int tf_tail_fused(const float* att, const float* Wohi, const float* Wolo, const float* bo, const float* g1, const float* be1,
+                  float* x, const float* W1hi, const float* W1lo, const float* b1, const float* W2hi, const float* W2lo,
+                  const float* b2, const float* g2, const float* be2, int M, int ff, cudaStream_t st) {
+  if (ff % 128 != 0 || ff < 128 || M < 1) return QX_EUNSUPPORTED;
+  CUtensorMap ma, mx, moh, mol, m1h, m1l, m2h, m2l, mc, mr;
+  int rc;
+  if ((rc = make_map(&ma, att, M, kBN)) || (rc = make_map(&mx, x, M, kBN)) || (rc = make_map(&moh, Wohi, kBN, kBN / 2)) ||
+      (rc = make_map(&mol, Wolo, kBN, kBN / 2)) || (rc = make_map(&m1h, W1hi, ff, kBN / 2)) || (rc = make_map(&m1l, W1lo, ff, kBN / 2)) ||
+      (rc = make_map(&m2h, W2hi, kBN, ff / 2)) || (rc = make_map(&m2l, W2lo, kBN, ff / 2)) ||
+      (rc = make_map(&mc, x, M, kBN, 32, 32)) || (rc = make_map(&mr, x, M, kBN, 32, 32)))
+    return rc;
+  static bool cfgd[kMaxDevices] = {};
+  if (!cfgd[current_device_slot()]) {
+    cudaFuncSetAttribute(tf_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailSmem));
+    cfgd[current_device_slot()] = true;
+  }
+  const int num_sms = device_sm_count();
+  const int m_tiles = ceil_div(M, kBM);
+  const int grid = num_sms < m_tiles ? num_sms : m_tiles;
+  tf_tail_kernel<<<grid, 448, sizeof(TailSmem), st>>>(ma, mx, moh, mol, m1h, m1l, m2h, m2l, mc, mr,
+                                                     TailArgs{bo, g1, be1, b1, b2, g2, be2}, M, ff);
+  QX_CHECK_LAUNCH("tf_tail_kernel");
+  return QX_OK;
+}
+
 // x[M][128] <- LayerNorm(x + linear2(relu(linear1(x)))) with the fp16 halves of W1 [ff][128] and W2 [128][ff] (as
 // tf_split_weights(.., true) writes them).  out may be x.  QX_EUNSUPPORTED when ff is not a multiple of 128.
 int tf_ffn_fused(const float* x, const float* W1hi, const float* W1lo, const float* b1, const float* W2hi, const float* W2lo,

@@ -188,7 +188,7 @@ class TransformerILQR:
         ws = getattr(engine, "_tf_ws", None)
         env = tuple(os.environ.get(k, "") for k in ("QX_TF_FUSE_LN", "QX_TF_NO_PRUNE", "QX_TF_GEMM_STREAM", "QX_TF_GEMM_VARIANT",
                                                      "QX_TF_ATTN_PAIR", "QX_TF_ATTN_MMA", "QX_TF_ATTN_DBG", "QX_TF_GEMM_DBG", "QX_TF_GEMM_F16",
-                                                     "QX_TF_FFN_FUSE"))
+                                                     "QX_TF_FFN_FUSE", "QX_TF_TAIL_FUSE"))
         return (id(self), bool(self.tensor_cores), None if packed is None else (packed[1].data_ptr(), packed[2].data_ptr()),
                 None if shift is None else shift.data_ptr(), None if ws is None else ws.data_ptr(), env)
 
@@ -236,7 +236,11 @@ class TransformerILQR:
                and os.environ.get("QX_TF_GEMM_STREAM", "0") != "1"
                and self.d_model % 128 == 0 and self.dim_feedforward % 128 == 0)
         ffn = 1 if f16 and (fuse & 2) and os.environ.get("QX_TF_FFN_FUSE", "1") != "0" else 0
-        engine.launches += (3 + (7 - (fuse & 1) - ((fuse >> 1) & 1) - ffn) * self.num_decoder_layers
+        # ... and out-proj + norm1 ride along when ff <= 256 (tf_tail_kernel, QX_TF_TAIL_FUSE), except in a pruned last layer
+        tl = os.environ.get("QX_TF_TAIL_FUSE", "1")
+        tail = ffn and (fuse & 1) and (tl == "2" or (tl == "1" and self.dim_feedforward <= 256))
+        tail_layers = (self.num_decoder_layers - (1 if pruned else 0)) if tail else 0
+        engine.launches += (3 + (7 - (fuse & 1) - ((fuse >> 1) & 1) - ffn) * self.num_decoder_layers - tail_layers
                             + (1 if (fuse & 1) and pruned else 0))
 
     def predict(self, x_seq, kK_seq):

@@ -429,7 +429,7 @@ def test_fp16_split_dense_layers_match_tf32_split_and_exact_path(system, golden_
 
 
 @pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
-@pytest.mark.parametrize("n_traj", [3, 1200])
+@pytest.mark.parametrize("n_traj", [3, 800, 1200])
 def test_fused_ffn_equals_two_launches_bitwise(system, n_traj, golden_dir, monkeypatch):
     """tf_ffn_kernel (linear1 + ReLU + linear2 + residual + norm2 in one launch, the ff-wide intermediate kept in tensor
     memory) issues the products of the two-launch path in the same order with the same roundings: identical predictions.
@@ -442,6 +442,7 @@ def test_fused_ffn_equals_two_launches_bitwise(system, n_traj, golden_dir, monke
     reps = max(1, n_traj // len(g["x_err"]))
     x = np.concatenate([g["x_err"] * (1.0 + 0.05 * rng.standard_normal(g["x_err"].shape)) for _ in range(reps)])[:max(n_traj, 1)]
     kK = np.concatenate([g["kK"] * (1.0 + 0.05 * rng.standard_normal(g["kK"].shape)) for _ in range(reps)])[:max(n_traj, 1)]
+    monkeypatch.setenv("QX_TF_TAIL_FUSE", "0")
     monkeypatch.setenv("QX_TF_FFN_FUSE", "0")
     two = w.predict(x, kK)
     monkeypatch.setenv("QX_TF_FFN_FUSE", "1")
@@ -449,6 +450,11 @@ def test_fused_ffn_equals_two_launches_bitwise(system, n_traj, golden_dir, monke
     assert np.isfinite(one).all()
     assert np.array_equal(one, two), f"{relmax(one, two):.2e}"
     assert np.array_equal(one, w.predict(x, kK))          # and the same bits from run to run
+    # tf_tail_kernel: out-proj + norm1 in front of the block, norm1 on the converter warps; forced on for ff = 512 too
+    monkeypatch.setenv("QX_TF_TAIL_FUSE", "2")
+    tail = w.predict(x, kK)
+    assert np.array_equal(tail, two), f"{relmax(tail, two):.2e}"
+    assert np.array_equal(tail, w.predict(x, kK))
 
 
 @pytest.mark.parametrize("system", ["cartpole", "quadrotor"])

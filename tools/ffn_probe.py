@@ -25,6 +25,7 @@ def main():
     reps = max(1, args.traj // len(g["x_err"]))
     x = np.concatenate([g["x_err"] * (1.0 + 0.05 * rng.standard_normal(g["x_err"].shape)) for _ in range(reps)])
     kK = np.concatenate([g["kK"] * (1.0 + 0.05 * rng.standard_normal(g["kK"].shape)) for _ in range(reps)])
+    os.environ["QX_TF_TAIL_FUSE"] = "0"
     os.environ["QX_TF_FFN_FUSE"] = "0"
     two = w.predict(x, kK)
     os.environ["QX_TF_FFN_FUSE"] = "1"
@@ -32,6 +33,11 @@ def main():
     again = w.predict(x, kK)
     print(f"{args.system}: {len(x)} trajectories, fused == two launches bitwise: {np.array_equal(one, two)}"
           f" (max rel diff {relmax(one, two):.2e}), run-to-run identical: {np.array_equal(one, again)}, finite: {np.isfinite(one).all()}")
+    os.environ["QX_TF_TAIL_FUSE"] = "2"
+    tail = w.predict(x, kK)
+    again = w.predict(x, kK)
+    print(f"{args.system}: layer tail in one launch == separate launches bitwise: {np.array_equal(tail, two)}"
+          f" (max rel diff {relmax(tail, two):.2e}), run-to-run identical: {np.array_equal(tail, again)}, finite: {np.isfinite(tail).all()}")
 
 
 if __name__ == "__main__":
