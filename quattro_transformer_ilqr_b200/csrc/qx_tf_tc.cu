@@ -1541,7 +1541,11 @@ tf_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // is shorter than a normalisation, the converters can be two tiles ahead of these warps, and a barrier that has
     // completed phases t AND t + 1 looks, to a wait for phase t, like one that has not completed it.
     auto res_first = [&](int m0, uint32_t t) {
-      while (*reinterpret_cast<volatile uint32_t*>(&s.h1_cnt) < 2u * (t + 1u)) __nanosleep(64);
+      uint32_t spins = 0;
+      while (*reinterpret_cast<volatile uint32_t*>(&s.h1_cnt) < 2u * (t + 1u)) {
+        __nanosleep(64);
+        if (++spins > (1u << 26)) __trap();                 // like mbar_wait: a lost hand-off must not hang the GPU
+      }
       __threadfence();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
