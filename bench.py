@@ -84,14 +84,16 @@ def ncu_reference(kernel, blk, system):
     """DRAM traffic and pipe utilisation of the dominant kernel from the committed `ncu --set full` summary of the
     same workload (profiles/): counters cannot be read live, the launch duration is (CUDA events, above)."""
     path = os.path.join(ROOT, "profiles", "r2_ncu_full_classic_summary.txt")
-    sym = {("riccati", True): "riccati_quad_thr_kernel", ("linearize", True): "linearize_quad_blk_kernel"}.get((kernel, blk))
+    sym = {("riccati", True): "riccati_quad_thr_kernel", ("linearize", True): "linearize_quad_blk_kernel",
+           ("ls_phaseA", True): "ls_qd_phaseA_kernel", ("ls_phaseB", True): "ls_qd_phaseB_kernel",
+           ("ls_phaseW", True): "ls_qd_phaseW_kernel"}.get((kernel, blk))
     if system != "quadrotor" or sym is None or not os.path.exists(path):
         return None
     vals, inside = {}, False
     for line in open(path):
         if line.startswith("-----"):
             inside = False
-        elif line.startswith(sym) or (" " + sym) in line[:80]:
+        elif line.startswith(sym) or (" " + sym) in line[:80] or ("::" + sym) in line[:80]:
             inside = True
         elif inside and line.startswith("  "):
             parts = line.split()
@@ -107,8 +109,11 @@ def ncu_reference(kernel, blk, system):
     def byt(k):
         v, u = vals[k]
         return v * scale.get(u, 1.0)
-    return {"source": "profiles/r2_ncu_full_classic_summary.txt", "traffic": byt("dram__bytes_read.sum") + byt("dram__bytes_write.sum"),
+    return {"source": "profiles/r2_ncu_full_classic_summary.txt", "captured": "iteration 6 of a forced solve (13 007 trajectories queued)",
+            "traffic": byt("dram__bytes_read.sum") + byt("dram__bytes_write.sum"),
             "fma_pipe_pct": vals.get("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", (None,))[0],
+            "fp64_pipe_pct": vals.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", (None,))[0],
+            "duration_us": vals.get("gpu__time_duration.sum", (None,))[0],
             "issue_active_pct": vals.get("smsp__issue_active.avg.pct_of_peak_sustained_active", (None,))[0],
             "dram_pct": vals.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", (None,))[0]}
 
@@ -395,25 +400,46 @@ def gpu_bench(args):
                              "iterations in between; consecutive calls pipeline over the slice streams"}
 
     # ---- per-kernel durations (CUDA events on the launching stream), rank 0 only --------------------
+    # One window of RESET_EVERY forced iterations from the reset - the iterations the timed region consists of - after
+    # an untimed one.  The staged quadrotor line search is three launches inside ONE C-ABI call; the library records
+    # caller-owned events between them (qx_linesearch_stage_events), so each launch is timed on its own.
     kernels = {}
     if rank == 0:
+        import ctypes
         names = ["linearize", "riccati"] + (["transformer"] if use_tf else []) + ["linesearch"]
         acc = {k: [] for k in names}
-        eng.set_problem(x0_d, u0_d)
-        for it in range(6):
-            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
-            start = 0 if tf is None else N - tf.prompt_len
-            evs[0].record()
-            eng.linearize(start); evs[1].record()
-            eng.riccati(start); evs[2].record()
-            j = 2
-            if use_tf:
-                tf.forward_device(eng); j += 1; evs[j].record()
-            eng.linesearch(tol, force=True); evs[j + 1].record()
-            torch.cuda.synchronize(dev)
-            if it >= 1:
-                for q, k in enumerate(names):
-                    acc[k].append(evs[q].elapsed_time(evs[q + 1]))
+        staged = system == "quadrotor" and eng.ls_workspace is not None and bool(eng.params.diag_cost)
+        stage_acc = {"ls_phaseA": [], "ls_phaseB": [], "ls_phaseW": []}
+        queued = []
+        if staged:
+            sev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            for e in sev:
+                e.record()                           # creates the cudaEvent_t handles
+            handles = (ctypes.c_void_p * 4)(*[e.cuda_event for e in sev])
+            qlib_h = eng.lib
+            assert qlib_h.qx_linesearch_stage_events(handles, 4) == 0
+        start = 0 if tf is None else N - tf.prompt_len
+        for window in range(2):
+            eng.set_problem(x0_d, u0_d)
+            for it in range(RESET_EVERY):
+                evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+                evs[0].record()
+                eng.linearize(start); evs[1].record()
+                eng.riccati(start); evs[2].record()
+                j = 2
+                if use_tf:
+                    tf.forward_device(eng); j += 1; evs[j].record()
+                eng.linesearch(tol, force=True); evs[j + 1].record()
+                torch.cuda.synchronize(dev)
+                if window == 1:
+                    for q, k in enumerate(names):
+                        acc[k].append(evs[q].elapsed_time(evs[q + 1]))
+                    if staged:
+                        for q, k in enumerate(stage_acc):
+                            stage_acc[k].append(sev[q].elapsed_time(sev[q + 1]))
+                        queued.append(int(eng.ls_workspace[:4].view(torch.int32)[0].item()))
+        if staged:
+            assert eng.lib.qx_linesearch_stage_events(None, 0) == 0
         hbm, how = peaks()
         from quattro_transformer_ilqr_b200 import _lib as qlib
         blk = eng.exp_layout == qlib.QX_LAYOUT_BLK
@@ -428,6 +454,21 @@ def gpu_bench(args):
                 gbs = by * B / (ms_k * 1e-3) / 1e9
                 entry.update({"algo_bytes_per_traj": by, "GBps": round(gbs, 1), "frac_hbm": round(gbs / hbm, 4)})
             kernels[k] = entry
+        if staged:
+            # algorithmic bytes per launch: A rolls every trajectory (read x, u, K, k 16 896 B, write x^, u^, cost
+            # 6 552 B); B reads the nominal and the gains of a QUEUED trajectory once (its five probes share the lines)
+            # and writes five costs; W rolls the queued ones again.  Queue lengths are read back per iteration.
+            ls_in, ls_out = 16896.0, 6552.0
+            per = {"ls_phaseA": [(ls_in + ls_out) * B] * len(queued),
+                   "ls_phaseB": [(ls_in + 40.0) * q for q in queued],
+                   "ls_phaseW": [(ls_in + ls_out) * q for q in queued]}
+            for k, t in stage_acc.items():
+                ms_k = float(np.mean(t))
+                by = float(np.mean(per[k]))
+                gbs = float(np.sum(per[k])) / (float(np.sum(t)) * 1e-3) / 1e9
+                kernels[k] = {"ms": round(ms_k, 4), "ms_max": round(float(np.max(t)), 4), "algo_bytes_per_launch": by,
+                              "GBps": round(gbs, 1), "frac_hbm": round(gbs / hbm, 4)}
+            kernels["ls_phaseB"]["queued_per_iteration"] = queued
 
     # ---- run-to-convergence mode: one full solve with the reference's stopping rule, rank 0 ----------
     converge = None
@@ -452,10 +493,15 @@ def gpu_bench(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    # dominant KERNEL = the longest single launch: linearise and Riccati are one launch each, the line search is
-    # three (stages A, B, W: a rollout each), so it is reported in `kernels` but is not "a kernel"
+    # dominant KERNEL = the single launch with the longest mean duration over the window (linearise, Riccati and - where
+    # the library can time them separately - the three stages of the line search; otherwise the line search, which is
+    # then a sequence of launches, is reported in `kernels` only)
+    stage_names = [k for k in ("ls_phaseA", "ls_phaseB", "ls_phaseW") if k in kernels]
     single = [k for k in kernels if "GBps" in kernels[k] and k != "linesearch"] or [k for k in kernels if "GBps" in kernels[k]]
     dom = max(single, key=lambda k: kernels[k]["ms"])
+    step_ms = sum(kernels[k]["ms"] for k in kernels if k not in stage_names)
+    for k in kernels:
+        kernels[k]["share_of_step"] = round(kernels[k]["ms"] / step_ms, 3)
     hbm, how = peaks()
     ncu = ncu_reference(dom, blk, system) if B == WORKLOADS[args.workload][2] else None
     if use_tf:
@@ -472,15 +518,32 @@ def gpu_bench(args):
                     "note": "fp32-accurate products cost three tensor-core MMAs each: the tensor pipe does 3x the algorithmic "
                             "flops counted here; per-kernel tensor-pipe activity is in profiles/r2_ncu_full_transformer_summary.txt"}
     else:
+        per_launch = kernels[dom].get("algo_bytes_per_launch", kernels[dom].get("algo_bytes_per_traj", 0.0) * B)
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["GBps"], "peak": hbm, "unit": "GB/s",
                     "frac": kernels[dom]["frac_hbm"], "traffic": ncu["traffic"] if ncu else None, "peak_source": how,
-                    "algo_bytes_per_launch": kernels[dom]["algo_bytes_per_traj"] * B}
+                    "algo_bytes_per_launch": per_launch, "ms": kernels[dom]["ms"],
+                    "share_of_step": kernels[dom]["share_of_step"]}
     if ncu and not use_tf:
         roofline["ncu"] = ncu
-    if dom == "riccati" and not use_tf:
-        roofline["note"] = ("one thread per trajectory, 50 dependent steps: at 16 384 trajectories there is one warp per scheduler "
-                            "and the kernel runs at its fp32 latency floor (SURVEY 8d asks for both figures: ncu.fma_pipe_pct, "
-                            "ncu.issue_active_pct); from 32 768 trajectories on it is HBM-bound")
+    if not use_tf:
+        notes = {
+            "riccati": "one thread per trajectory, 50 dependent steps: at 16 384 trajectories there is one warp per scheduler "
+                       "and the kernel runs at its fp32 latency floor (SURVEY 8d asks for both figures: ncu.fma_pipe_pct, "
+                       "ncu.issue_active_pct); from 32 768 trajectories on it is HBM-bound",
+            "ls_phaseB": "costs-only probes of the five smaller alphas, one thread per (queued trajectory, alpha): the launch does "
+                         "not run in iterations 0-2 of the window (nothing is rejected there) and is the longest launch from "
+                         "iteration 3 on (ms_max).  It moves little (the five probes of a trajectory share its nominal and gain "
+                         "lines in L2) and is bound by the fp64 pipe, not by HBM: ncu.fp64_pipe_pct is the figure that says how "
+                         "close it is to its own ceiling; frac is the algorithmic bytes against the copy peak, as the bench "
+                         "contract defines it",
+            "ls_phaseA": "alpha = 1 rollout of every trajectory, one thread each: one warp per scheduler at 16 384 trajectories "
+                         "(fp64 latency floor); HBM-bound from 32 768 trajectories on",
+        }
+        if dom in notes:
+            roofline["note"] = notes[dom]
+        roofline["all_launches"] = {k: {"ms": kernels[k]["ms"], "frac_hbm": kernels[k]["frac_hbm"],
+                                        "share_of_step": kernels[k]["share_of_step"]}
+                                    for k in single}
     if world == 1:      # the CPU leg runs at N = 1 only (at N > 1 the other ranks' host threads share the cores)
         cpu_val, cores, _, sample = cpu_reference(system, steps=2, warmup=1, iters_per_step=2)
         cpu_baseline = {"value": cpu_val, "unit": "trajectory-iterations/s", "cores": cores, "kind": "port", "sample": sample}

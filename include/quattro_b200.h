@@ -165,6 +165,12 @@ int qx_linesearch(const QxParams* p, double* x_in, double* u_in, const float* ga
                   int32_t* status, int32_t* iters, int32_t* alpha, double* x_out, double* u_out,
                   int32_t* n_active, void* workspace, double tol, uint32_t flags, int B, int N, void* stream);
 
+/* Measurement hook (no reference counterpart): four caller-owned cudaEvent_t handles that the staged quadrotor line
+ * search records on its stream in front of stage A and behind stages A, B and W, so that bench.py can time the three
+ * launches of one qx_linesearch call separately.  Per host thread; count = 0 clears the hook.  Never set it while a
+ * stream is being captured into a CUDA graph. */
+int qx_linesearch_stage_events(void* const* events, int count);
+
 /* forward_pass with a caller-chosen alpha (quattro_ilqr_tf.py:377-390): candidate trajectory and its
  * total cost for every trajectory, no accept test.  (x_in,u_in) is the nominal, gains as above. */
 int qx_forward_pass(const QxParams* p, const double* x_in, const double* u_in, const float* gains, double alpha,

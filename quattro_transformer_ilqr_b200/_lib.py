@@ -56,6 +56,7 @@ SIGNATURES = {
     "qx_linesearch_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "qx_linesearch": (C.c_int, [C.POINTER(QxParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_uint32,
                                 C.c_int, C.c_int, _P]),
+    "qx_linesearch_stage_events": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "qx_forward_pass": (C.c_int, [C.POINTER(QxParams), _P, _P, _P, C.c_double, _P, _P, _P, C.c_int, C.c_int, _P]),
     "qx_tf_weight_floats": (C.c_size_t, [C.POINTER(QxTfConfig)]),
     "qx_tf_workspace_bytes": (C.c_size_t, [C.POINTER(QxTfConfig), C.c_int]),

@@ -612,6 +612,18 @@ int qd_launch_rollout(const QxParams* p, const double* x0, const double* u, doub
   return QX_OK;
 }
 
+// Optional probe (qx_linesearch_stage_events): four caller-owned events recorded on the launching stream in front of
+// stage A and behind stages A, B, W, so that a benchmark can time the three launches of one call separately.
+static thread_local cudaEvent_t g_stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+void qd_set_stage_events(void* const* ev) {
+  for (int i = 0; i < 4; ++i) g_stage_ev[i] = ev ? static_cast<cudaEvent_t>(ev[i]) : nullptr;
+}
+
+static inline void qd_stage_mark(int i, cudaStream_t st) {
+  if (g_stage_ev[i] != nullptr) cudaEventRecord(g_stage_ev[i], st);
+}
+
 template <int INTEG>
 static int qd_linesearch_t(const QxParams* p, double* x_in, double* u_in, const float* gains, double* cost,
                            int32_t* status, int32_t* iters, int32_t* alpha, double* x_out, double* u_out,
@@ -629,14 +641,18 @@ static int qd_linesearch_t(const QxParams* p, double* x_in, double* u_in, const 
   const QdWork ws = qd_carve(workspace, B);
   cudaError_t e = cudaMemsetAsync(ws.ctl, 0, 32, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(ctl)");
+  qd_stage_mark(0, st);
   ls_qd_phaseA_kernel<1, INTEG><<<grid, 32, 0, st>>>(k, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out,
                                                      n_active, ws, tol, flags, B, N);
   QX_CHECK_LAUNCH("ls_qd_phaseA_kernel<1>");
+  qd_stage_mark(1, st);
   ls_qd_phaseB_kernel<INTEG><<<grid * (QX_NUM_ALPHA - 1), 32, 0, st>>>(k, x_in, u_in, gains, ws, B, N);
   QX_CHECK_LAUNCH("ls_qd_phaseB_kernel");
+  qd_stage_mark(2, st);
   ls_qd_phaseW_kernel<INTEG><<<grid, 32, 0, st>>>(k, x_in, u_in, gains, cost, status, iters, alpha, x_out, u_out, n_active, ws,
                                                   tol, flags, B, N);
   QX_CHECK_LAUNCH("ls_qd_phaseW_kernel");
+  qd_stage_mark(3, st);
   if (!(flags & QX_LS_FORCE_ACTIVE)) {      // forced mode never finishes a trajectory: nothing to mirror
     ls_qd_mirror_kernel<<<dim3(ceil_div(B, 128), 16), 128, 0, st>>>(x_in, u_in, x_out, u_out, ws.mirror, B, N);
     QX_CHECK_LAUNCH("ls_qd_mirror_kernel");

@@ -416,6 +416,7 @@ int qd_launch_rollout(const QxParams* p, const double* x0, const double* u, doub
                       const int32_t* status, int B, int N, cudaStream_t st);
 int qd_launch_forward_pass(const QxParams* p, const double* x_in, const double* u_in, const float* gains, double alpha,
                            double* x_out, double* u_out, double* cost_out, int B, int N, cudaStream_t st);
+void qd_set_stage_events(void* const* ev);
 int qd_launch_linesearch(const QxParams* p, double* x_in, double* u_in, const float* gains, double* cost,
                          int32_t* status, int32_t* iters, int32_t* alpha, double* x_out, double* u_out,
                          int32_t* n_active, void* workspace, double tol, uint32_t flags, int B, int N,
@@ -443,6 +444,12 @@ extern "C" size_t qx_linesearch_workspace_bytes(int model_id, int B, int N) {
   if (model_id == QX_MODEL_CARTPOLE) return ((size_t)B * sizeof(int32_t) + 127) & ~(size_t)127;   // winner hints
   if (model_id != QX_MODEL_QUADROTOR) return 0;
   return qx::qd_workspace_bytes(B, N);
+}
+
+extern "C" int qx_linesearch_stage_events(void* const* events, int count) {
+  QX_CHECK_ARG(count == 0 || (count == 4 && events != nullptr), "pass four cudaEvent_t handles, or count = 0 to clear");
+  qx::qd_set_stage_events(count == 4 ? events : nullptr);
+  return QX_OK;
 }
 
 extern "C" int qx_linesearch(const QxParams* p, double* x_in, double* u_in, const float* gains, double* cost,
