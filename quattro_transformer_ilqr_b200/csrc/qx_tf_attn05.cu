@@ -64,6 +64,17 @@ constexpr uint32_t idesc_tf32(int n, bool b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (b_mn_major ? (1u << 16) : 0u) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
 }
 
+// QK16: Q and K arrive as fp16 (hi, lo) pairs - D = F32, A = B = F16 (format bits 0), both K-major
+constexpr uint32_t idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24); }
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
 // The operand split of this kernel: hi = x rounded to the nearest TF32, lo = x - hi, exact and NOT rounded: the tensor
 // core reads the upper 19 bits of a kind::tf32 operand and ignores the rest, so lo enters the products truncated to its
 // top 11 bits - an error of 2^-10 |lo| <= 2^-21 |x| where the rounded lo of tf32_split() has 2^-22 |x|, for three
@@ -346,7 +357,13 @@ __device__ long long g_attn_trace[2][16];
 // an SM, so that the long causal rows of two co-resident CTAs do not share a lane quarter - 0.63 ms against 0.57 ms.
 // The hardware already spreads the warps of the two CTAs evenly: smsp__inst_executed differs by 3 % across the
 // schedulers (profiles/r2_ncu_full_attention_summary.txt).)
-template <bool PAIR>
+// QK16: the Q and K columns of qkv hold fp16 (hi, lo) pairs written by the QKV projection (tf_gemm_ta_kernel,
+// kGemmPackQk; Q already scaled): per head slice and token 64 B of hi halves, then 64 B of lo halves.  The same TMA box
+// (32 "floats" x tokens, 128-B swizzle) lands them as ONE K-major fp16 tile of 64 k per row - k 0-31 the hi halves,
+// k 32-63 the lo halves - so the three products hi hi + hi lo + lo hi are six kind::f16 MMAs (K = 16 each) whose
+// descriptors start 0 / 32 / 64 / 96 B into the swizzle atom.  Neither tile is touched by a thread: the Q / K splits
+// (a quarter of the kernel's CUDA-core instructions) and the Q detour through tensor memory are gone.
+template <bool PAIR, bool QK16>
 __global__ void __launch_bounds__(256, 2)
 tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmOut, float* __restrict__ out_rows, int n_items, int n_traj, int nhead, int L,
@@ -359,7 +376,7 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
   const int row = wq * 32 + lane;                   // tile row / TMEM lane of this thread
   const int NK = PAIR ? kRows : (L + 15) & ~15;     // keys padded to the UMMA N granularity (PAIR: 2 x 64)
   const int nks = (L + 7) >> 3;                     // K = 8 steps of the second product
-  const uint32_t idesc_s = idesc_tf32(NK, false), idesc_o = idesc_tf32(kHd, true);
+  const uint32_t idesc_s = QK16 ? idesc_f16(NK) : idesc_tf32(NK, false), idesc_o = idesc_tf32(kHd, true);
   const int th = PAIR ? (wq >> 1) : 0;              // PAIR: which trajectory of the tile this row belongs to
   const int qrev = PAIR ? (wq & 1) : wq, lrev = lane;   // this thread's token is 32 qrev + lrev
 
@@ -433,8 +450,10 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
       load_qk(blockIdx.x);
       load_v(blockIdx.x);
     }
-    split_qk(0);
-    if (!PAIR) split_q_tmem();
+    if (!QK16) {
+      split_qk(0);
+      if (!PAIR) split_q_tmem();
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -448,7 +467,23 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     QX_TRACE(10);    // loop top
 
     // ---- S = (scaled Q) K^T ---------------------------------------------------------------------------------------
-    if (warp == 0) {
+    if (QK16 && warp == 0) {
+      mbar_wait(&s.bar_qk, ph);          // the tiles are MMA-ready as TMA wrote them (async proxy both ways: no fence)
+      __syncwarp();
+      tcgen05_fence_after();
+      const uint64_t dq = umma_desc_sw128(s.q_hi), dk = umma_desc_sw128(s.k_hi);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < kHd / 16; ++k) {
+          const uint64_t hi = (uint64_t)((k * 16 * 2) >> 4), lo = hi + (uint64_t)((kHd * 2) >> 4);   // 16-B units
+          mma_f16(tmem, dq + lo, dk + hi, idesc_s, k ? 1u : 0u);
+          mma_f16(tmem, dq + hi, dk + lo, idesc_s, 1u);
+          mma_f16(tmem, dq + hi, dk + hi, idesc_s, 1u);
+        }
+        tcgen05_commit(&s.bar_s);
+      }
+      __syncwarp();
+    } else if (warp == 0) {
       tcgen05_fence_after();
       const uint64_t dq_hi = umma_desc_sw128(s.q_hi), dq_lo = umma_desc_sw128(s.q_lo);
       const uint64_t dk_hi = umma_desc_sw128(s.k_hi), dk_lo = umma_desc_sw128(s.k_lo);
@@ -572,12 +607,12 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     }
     QX_TRACE(12);    // O issue
     // the next item's Q, K are split while the tensor core works on O
-    if (next < n_items) split_qk(ph ^ 1u);
+    if (!QK16 && next < n_items) split_qk(ph ^ 1u);
     QX_TRACE(6);     // split of the next Q, K
     mbar_wait(&s.bar_o, ph);
     QX_TRACE(7);     // wait O
     tcgen05_fence_after();
-    if (!PAIR && next < n_items && !(dbg & 8)) split_q_tmem();     // P_lo is dead: the next item's Q halves move in
+    if (!QK16 && !PAIR && next < n_items && !(dbg & 8)) split_q_tmem();     // P_lo is dead: the next item's Q halves move in
     if (PAIR && tid == 0 && next < n_items) load_v(next);
     __syncwarp();
     // ---- epilogue: each thread 16 of the row's 32 output dims -----------------------------------------------------
@@ -654,7 +689,7 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
 // Returns QX_EUNSUPPORTED when the shape is outside the kernel's range (the caller then falls back to the mma.sync
 // kernel of qx_tf_attn.cu).  qkv: [B*L][3d] packed rows, out: [B][L - row_lo][d] = the rows row_lo .. L-1 of every
 // trajectory (row_lo = 0: all of them).
-int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhead, int row_lo, cudaStream_t st) {
+int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhead, int row_lo, cudaStream_t st, bool qk16) {
   if (d != nhead * kHd || L > kMaxKeys || L < 1 || B < 1 || row_lo < 0 || row_lo >= L) return QX_EUNSUPPORTED;
   // QX_TF_ATTN_PAIR=0 keeps one trajectory per tile whatever L is (A/B runs and the equality test)
   const char* env_pair = getenv("QX_TF_ATTN_PAIR");
@@ -683,8 +718,10 @@ int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhe
   }
   static bool cfg[kMaxDevices] = {};
   if (!cfg[current_device_slot()]) {
-    cudaFuncSetAttribute(tf_attention_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmemT<false>));
-    cudaFuncSetAttribute(tf_attention_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmemT<true>));
+    cudaFuncSetAttribute(tf_attention_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmemT<false>));
+    cudaFuncSetAttribute(tf_attention_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmemT<true>));
+    cudaFuncSetAttribute(tf_attention_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmemT<false>));
+    cudaFuncSetAttribute(tf_attention_umma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmemT<true>));
     cfg[current_device_slot()] = true;
   }
   const int num_sms = device_sm_count();
@@ -694,8 +731,10 @@ int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhe
   const char* env_dbg = getenv("QX_TF_ATTN_DBG");
   const int dbg = env_dbg ? atoi(env_dbg) : 0;
   const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;
-  if (pair) tf_attention_umma_kernel<true><<<grid, 256, sizeof(AttnSmemT<true>), st>>>(mq, mk, mv, mo, out, n_items, B, nhead, L, d, row_lo, dbg);
-  else tf_attention_umma_kernel<false><<<grid, 256, sizeof(AttnSmemT<false>), st>>>(mq, mk, mv, mo, out, n_items, B, nhead, L, d, row_lo, dbg);
+  if (pair && qk16) tf_attention_umma_kernel<true, true><<<grid, 256, sizeof(AttnSmemT<true>), st>>>(mq, mk, mv, mo, out, n_items, B, nhead, L, d, row_lo, dbg);
+  else if (pair) tf_attention_umma_kernel<true, false><<<grid, 256, sizeof(AttnSmemT<true>), st>>>(mq, mk, mv, mo, out, n_items, B, nhead, L, d, row_lo, dbg);
+  else if (qk16) tf_attention_umma_kernel<false, true><<<grid, 256, sizeof(AttnSmemT<false>), st>>>(mq, mk, mv, mo, out, n_items, B, nhead, L, d, row_lo, dbg);
+  else tf_attention_umma_kernel<false, false><<<grid, 256, sizeof(AttnSmemT<false>), st>>>(mq, mk, mv, mo, out, n_items, B, nhead, L, d, row_lo, dbg);
   QX_CHECK_LAUNCH("tf_attention_umma_kernel");
 #ifdef QX_ATTN_TRACE
   {

@@ -305,6 +305,7 @@ struct LnArgs {
 // block (128 rows x 128 B) then spans 64 k: two A blocks.
 constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);   // D = F32, A = B = F16
 constexpr float kW16Scale = 256.f;
+constexpr int kGemmPackQk = 16;      // flag bit of the kernel's `dbg` argument: n tiles 0 and 1 (Q, K) leave as fp16 (hi, lo) pairs
 
 template <bool RELU, bool STREAM_W, int kSets, bool LN = false, bool F16 = false>
 __global__ void __launch_bounds__(ta_threads(kSets), 1)
@@ -609,16 +610,43 @@ tf_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c0);
           float4 (*stg)[8] = s.epi[q][chunk & 1u];
+          if (F16 && !RELU && (dbg & kGemmPackQk) && n0 < 2 * kBN) {
+            // Q / K columns of the QKV projection for the tcgen05 attention (qx_tf_attn05.cu, QK16): the 32 floats of a
+            // head slice leave as (hi, lo) fp16 halves - 16-B pieces 0-3 hold hi of dims 0-31, pieces 4-7 lo - the same
+            // 128 B per row, which the attention's TMA box lands as a K-major fp16 tile of 64 k: no split over there.
+            // Q carries the softmax scale log2(e) / sqrt(head dim) already (what split_q_row applied).
+            const float qs = n0 == 0 ? rsqrtf(32.f) * 1.4426950408889634f : 1.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bb = b4[j];
-            float4 o;
-            o.x = __fadd_rn(unscale<F16>(r[4 * j + 0]), bb.x);
-            o.y = __fadd_rn(unscale<F16>(r[4 * j + 1]), bb.y);
-            o.z = __fadd_rn(unscale<F16>(r[4 * j + 2]), bb.z);
-            o.w = __fadd_rn(unscale<F16>(r[4 * j + 3]), bb.w);
-            if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            stg[lane][j ^ (lane & 7)] = o;
+            for (int u = 0; u < 4; ++u) {
+              const float4 b0 = b4[2 * u], b1 = b4[2 * u + 1];
+              const float v0 = __fmul_rn(__fadd_rn(unscale<F16>(r[8 * u + 0]), b0.x), qs);
+              const float v1 = __fmul_rn(__fadd_rn(unscale<F16>(r[8 * u + 1]), b0.y), qs);
+              const float v2 = __fmul_rn(__fadd_rn(unscale<F16>(r[8 * u + 2]), b0.z), qs);
+              const float v3 = __fmul_rn(__fadd_rn(unscale<F16>(r[8 * u + 3]), b0.w), qs);
+              const float v4 = __fmul_rn(__fadd_rn(unscale<F16>(r[8 * u + 4]), b1.x), qs);
+              const float v5 = __fmul_rn(__fadd_rn(unscale<F16>(r[8 * u + 5]), b1.y), qs);
+              const float v6 = __fmul_rn(__fadd_rn(unscale<F16>(r[8 * u + 6]), b1.z), qs);
+              const float v7 = __fmul_rn(__fadd_rn(unscale<F16>(r[8 * u + 7]), b1.w), qs);
+              uint32_t h[4], l[4];
+              f16_split2(v0, v1, h[0], l[0]);
+              f16_split2(v2, v3, h[1], l[1]);
+              f16_split2(v4, v5, h[2], l[2]);
+              f16_split2(v6, v7, h[3], l[3]);
+              stg[lane][u ^ (lane & 7)] = make_float4(__uint_as_float(h[0]), __uint_as_float(h[1]), __uint_as_float(h[2]), __uint_as_float(h[3]));
+              stg[lane][(4 + u) ^ (lane & 7)] = make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]), __uint_as_float(l[2]), __uint_as_float(l[3]));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = b4[j];
+              float4 o;
+              o.x = __fadd_rn(unscale<F16>(r[4 * j + 0]), bb.x);
+              o.y = __fadd_rn(unscale<F16>(r[4 * j + 1]), bb.y);
+              o.z = __fadd_rn(unscale<F16>(r[4 * j + 2]), bb.z);
+              o.w = __fadd_rn(unscale<F16>(r[4 * j + 3]), bb.w);
+              if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              stg[lane][j ^ (lane & 7)] = o;
+            }
           }
           fence_proxy_async();                          // generic-proxy writes -> visible to the TMA store
           __syncwarp();
@@ -670,7 +698,11 @@ static int make_map(CUtensorMap* map, const float* base, int rows, int cols, int
 
 // f16: Whi / Wlo hold the fp16 halves tf_split_weights(.., true) wrote (N x K halves each; the maps see K / 2 floats a row)
 int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* bias, float* C, int M, int N, int K,
-               bool relu, cudaStream_t st, bool f16) {
+               bool relu, cudaStream_t st, bool f16, bool pack_qk) {
+  if (pack_qk && !(f16 && !relu && N == 3 * kBN && K == kTaW * kBK)) {
+    set_error("fp16-pair Q / K output needs the fp16-split QKV projection of a d = 128 model (got N=%d K=%d)", N, K);
+    return QX_EINVAL;
+  }
   if (N % kBN != 0 || K % kBK != 0) {
     set_error("tensor-core GEMM needs N %% 128 == 0 and K %% 32 == 0 (got N=%d K=%d)", N, K);
     return QX_EINVAL;
@@ -702,7 +734,7 @@ int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* 
     if (groups > m_tiles) groups = m_tiles;
     const int grid = groups * n_tiles_n;
     const char* env_dbg = getenv("QX_TF_GEMM_DBG");
-    const int dbg = env_dbg ? atoi(env_dbg) : 0;
+    const int dbg = ((env_dbg ? atoi(env_dbg) : 0) & ~kGemmPackQk) | (pack_qk ? kGemmPackQk : 0);
     const char* env_var = getenv("QX_TF_GEMM_VARIANT");
     const int variant = env_var ? atoi(env_var) : 0;
     CUtensorMap mc;

@@ -507,6 +507,38 @@ def test_tcgen05_attention_matches_mma_sync_and_exact_attention(system, mode, go
     assert e_mma < tol and e_exact < tol
 
 
+@pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
+@pytest.mark.parametrize("mode", ["rand", "fp32"])
+def test_fp16_pair_q_k_from_the_qkv_projection(system, mode, golden_dir, monkeypatch):
+    """Default path: the QKV projection writes Q (scaled) and K as fp16 (hi, lo) pairs and the tcgen05 attention takes
+    them as MMA-ready K-major tiles (six kind::f16 products, no split in the attention kernel).  QX_TF_ATTN_QK16=0: fp32
+    q, k and the in-kernel TF32 split.  Both carry 22 bits per operand: within 5e-6 of the exact fp32 path and of each
+    other; run-to-run identical; 1 200 trajectories = 16 items per persistent CTA, both tile modes (L = 61 paired,
+    L = 101 single), pruned last layer included."""
+    g = np.load(f"{golden_dir}/tf_forward_{system}.npz")
+    w = _wrapper(system, mode)
+    rng = np.random.default_rng(21)
+    reps = 1200 // len(g["x_err"])
+    x = np.concatenate([g["x_err"] * (1.0 + 0.05 * rng.standard_normal(g["x_err"].shape)) for _ in range(reps)])
+    kK = np.concatenate([g["kK"] * (1.0 + 0.05 * rng.standard_normal(g["kK"].shape)) for _ in range(reps)])
+    monkeypatch.setenv("QX_TF_ATTN_QK16", "1")
+    packed = w.predict(x, kK)
+    assert np.isfinite(packed).all() and np.array_equal(w.predict(x, kK), packed)
+    monkeypatch.setenv("QX_TF_NO_PRUNE", "1")
+    assert np.array_equal(w.predict(x, kK), packed)
+    monkeypatch.setenv("QX_TF_NO_PRUNE", "0")
+    monkeypatch.setenv("QX_TF_ATTN_QK16", "0")
+    split = w.predict(x, kK)
+    assert not np.array_equal(packed, split)           # the switch does select another path
+    w.tensor_cores = False
+    exact = w.predict(x, kK)
+    e_p, e_s = relmax(packed, exact), relmax(split, exact)
+    print(f"{system}/{mode}: fp16-pair Q, K {e_p:.2e}, in-kernel TF32 split {e_s:.2e} from the exact fp32 path; "
+          f"between them {relmax(packed, split):.2e}")
+    tol = 5e-6 if mode == "rand" else 5e-5
+    assert e_p < tol and e_s < tol and relmax(packed, split) < tol
+
+
 @pytest.mark.parametrize("mode", ["rand", "fp32"])
 @pytest.mark.parametrize("batch", [1, 2, 1201])
 def test_two_cartpole_trajectories_per_attention_tile(mode, batch, golden_dir, monkeypatch):
