@@ -3,6 +3,7 @@
 // descriptor for 128-B-swizzled tiles, the 3xTF32 operand split, and the host-side tensor-map encoder.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "qx_async.cuh"
 #include "qx_common.cuh"
@@ -75,6 +76,43 @@ __device__ __forceinline__ void mma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, ui
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
+}
+// (a, b) -> packed fp16 (hi, hi) and (lo, lo), a in the low halves: x = hi + lo carries 22 significant bits
+__device__ __forceinline__ void f16_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// kind::f16 products: A from tensor memory (a column holds two consecutive k) or from shared memory
+__device__ __forceinline__ void mma_f16_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// MN-major 16-bit operand, plain 128-B swizzle (what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B for rows of 128 B along
+// MN): an atom is 8 rows (k) x 64 elements; 8-row groups 1024 B apart along K (SBO); one atom along MN (LBO unused but
+// must hold an atom-aligned value)
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_f16(const void* smem) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_u32(smem) >> 4) & 0x3fff);       // start address
+  d |= (uint64_t)(1024 >> 4) << 16;                      // leading byte offset: next 64-element atom along MN
+  d |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset: next 8-row group along K
+  d |= (uint64_t)1 << 46;                                // descriptor version
+  d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
+  return d;
 }
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(

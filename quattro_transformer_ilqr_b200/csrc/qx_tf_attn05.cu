@@ -66,14 +66,6 @@ constexpr uint32_t idesc_tf32(int n, bool b_mn_major) {
 
 // QK16: Q and K arrive as fp16 (hi, lo) pairs - D = F32, A = B = F16 (format bits 0), both K-major
 constexpr uint32_t idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24); }
-__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
 
 // The operand split of this kernel: hi = x rounded to the nearest TF32, lo = x - hi, exact and NOT rounded: the tensor
 // core reads the upper 19 bits of a kind::tf32 operand and ignores the rest, so lo enters the products truncated to its
@@ -686,10 +678,377 @@ tf_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
   }
 }
 
+// =====================================================================================================================
+// P16: q, k AND v arrive as fp16 (hi, lo) pairs (QKV projection, kGemmPackQk | kGemmPackV; q carries the softmax scale,
+// v a factor 2^4 that keeps its lo halves out of the fp16 subnormals) and the probabilities are split into fp16 pairs
+// too (times 2^8, folded into the exponent: P = 2^(s - m + 8)), so that BOTH products are kind::f16 and no operand is
+// split by a thread any more:
+//   S = Q K^T   six MMAs (K = 16), Q and K tiles exactly as TMA landed them (see QK16 above);
+//   O = P V     A = P from tensor memory - a column holds two consecutive keys, P_hi in columns [0, NK/2), P_lo behind
+//               them, both INSIDE the columns of the scores they replace (a row's two threads have loaded all their
+//               scores before either stores: the partial maxima are exchanged in between) - and B = the V tile as an
+//               MN-major operand in the plain 128-B swizzle: row = key, 64 fp16 along MN = hi dims | lo dims, so the hi
+//               and lo halves are the same tile entered 0 / 64 B into the row; K = 16 keys per MMA, 3 x NK/16 MMAs.
+//   epilogue    O / (rowsum * 2^4): rowsum is the sum of the scaled probabilities (2^8 P), the accumulator holds 2^12 O.
+// V is double buffered (no split means the landing tile IS the operand): the next item's V is requested when this
+// item's has arrived.  Shared memory 77 KB (single trajectory) / 81 KB (PAIR) per CTA, two CTAs per SM as before.
+namespace {
+
+template <bool PAIR>
+struct AttnSmem16 {
+  static constexpr int kKeyRows = PAIR ? kRows : kMaxKeys;
+  float q[kTile];
+  float k[kKeyRows * kHd];
+  float v[2][kKeyRows * kHd];
+  float4 stage[4][32][8];                // per quarter 32 rows x 32 dims in the TMA 128-B swizzle layout
+  float pmax[256], psum[256];
+  uint64_t bar_qk, bar_v, bar_s, bar_o;
+  uint32_t tmem_base;
+};
+static_assert(2 * (sizeof(AttnSmem16<false>) + 1024) <= 228 * 1024 && 2 * (sizeof(AttnSmem16<true>) + 1024) <= 228 * 1024,
+              "two attention CTAs must fit the shared memory of an SM");
+
+constexpr uint32_t kPlo16 = kMaxKeys / 2;      // single trajectory: P_hi [0,56) | P_lo [56,112) | O [224,256)
+constexpr uint32_t kPairPlo16 = 32;            // PAIR: P_hi [0,32) | P_lo [32,64) | O_a, O_b, exchange as in the fp32 kernel
+constexpr float kPShift = 8.f;                 // P is kept times 2^8
+constexpr float kPvUnscale = 1.f / 16.f;       // ... and V times 2^4: O = acc / (2^4 * sum of 2^8 P)
+
+template <int W>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t* r);
+template <>
+__device__ __forceinline__ void tmem_st_cols<8>(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_st_cols<4>(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+
+// n (16 or 8) probabilities of one thread -> n / 2 packed columns of P_hi and P_lo.  sc: the scores (registers of the
+// sweep), m: row maximum minus the shift, first_masked: index of the first masked key among these n (n: none)
+template <int N>
+__device__ __forceinline__ void p16_chunk(const uint32_t* sc, float m, int first_masked, float (&l4)[4], uint32_t taddr_hi,
+                                          uint32_t taddr_lo) {
+  uint32_t hi[N / 2], lo[N / 2];
+#pragma unroll
+  for (int t = 0; t < N; t += 2) {
+    float p0 = ex2_approx(__uint_as_float(sc[t]) - m);
+    float p1 = ex2_approx(__uint_as_float(sc[t + 1]) - m);
+    if (t >= first_masked) p0 = 0.f;
+    if (t + 1 >= first_masked) p1 = 0.f;
+    l4[t & 3] += p0;
+    l4[(t + 1) & 3] += p1;
+    f16_split2(p0, p1, hi[t >> 1], lo[t >> 1]);
+  }
+  tmem_st_cols<N / 2>(taddr_hi, hi);
+  tmem_st_cols<N / 2>(taddr_lo, lo);
+}
+
+// softmax_half_row with fp16-pair probabilities (see there for the sweep); returns the partial sum of 2^8 P
+template <int Q, int WD>
+__device__ __forceinline__ float softmax_half_row16(uint32_t tmem_row, int lrev, int half, int wq, float* pmax, int tid) {
+  constexpr int HW = WD / 2;
+  uint32_t r[Q + 1][16];
+#pragma unroll
+  for (int c = 0; c < Q; ++c) TmemRow<16>::ld(tmem_row + 32 * c + 16 * half, r[c]);
+  TmemRow<HW>::ld(tmem_row + 32 * Q + HW * half, r[Q]);
+  tmem_wait_ld();
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+  for (int c = 0; c < Q; ++c) {
+#pragma unroll
+    for (int t = 0; t < 16; ++t) m4[t & 3] = fmaxf(m4[t & 3], __uint_as_float(r[c][t]));
+  }
+#pragma unroll
+  for (int t = 0; t < HW; ++t) {
+    if (HW * half + t <= lrev) m4[t & 3] = fmaxf(m4[t & 3], __uint_as_float(r[Q][t]));
+  }
+  float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+  pmax[tid] = m;
+  pair_sync(wq);                            // both threads of the row have loaded ALL their scores: P may overwrite them
+  m = fmaxf(m, pmax[tid ^ 128]) - kPShift;
+  float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < Q; ++c) {
+    const uint32_t col = 16 * c + 8 * half;
+    p16_chunk<16>(r[c], m, 16, l4, tmem_row + col, tmem_row + kPlo16 + col);
+  }
+  {
+    const uint32_t col = 16 * Q + (HW / 2) * half;
+    int fm = lrev + 1 - HW * half;          // keys HW half + t with t > lrev - HW half are masked
+    fm = fm < 0 ? 0 : fm;
+    p16_chunk<HW>(r[Q], m, fm, l4, tmem_row + col, tmem_row + kPlo16 + col);
+  }
+  return (l4[0] + l4[1]) + (l4[2] + l4[3]);
+}
+
+template <int Q>
+__device__ __forceinline__ float softmax_pair_row16(uint32_t tmem_row, uint32_t s_col, int lrev, int half, int wq) {
+  uint32_t r[Q + 1][16];
+#pragma unroll
+  for (int c = 0; c <= Q; ++c) TmemRow<16>::ld(tmem_row + s_col + 32 * c + 16 * half, r[c]);
+  tmem_wait_ld();
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+  for (int c = 0; c < Q; ++c) {
+#pragma unroll
+    for (int t = 0; t < 16; ++t) m4[t & 3] = fmaxf(m4[t & 3], __uint_as_float(r[c][t]));
+  }
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    if (16 * half + t <= lrev) m4[t & 3] = fmaxf(m4[t & 3], __uint_as_float(r[Q][t]));
+  }
+  float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+  tmem_st1(tmem_row + kPairX + half, m);
+  tmem_wait_st();
+  tcgen05_fence_before();
+  pair_sync(wq);
+  tcgen05_fence_after();
+  m = fmaxf(m, tmem_ld1(tmem_row + kPairX + (half ^ 1))) - kPShift;
+  float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < Q; ++c) {
+    const uint32_t col = 16 * c + 8 * half;
+    p16_chunk<16>(r[c], m, 16, l4, tmem_row + col, tmem_row + kPairPlo16 + col);
+  }
+  {
+    const uint32_t col = 16 * Q + 8 * half;
+    int fm = lrev + 1 - 16 * half;
+    fm = fm < 0 ? 0 : fm;
+    p16_chunk<16>(r[Q], m, fm, l4, tmem_row + col, tmem_row + kPairPlo16 + col);
+  }
+  return (l4[0] + l4[1]) + (l4[2] + l4[3]);
+}
+
+}  // namespace
+
+template <bool PAIR>
+__global__ void __launch_bounds__(256, 2)
+tf_attention_p16_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmOut,
+                        float* __restrict__ out_rows, int n_items, int n_traj, int nhead, int L, int d, int row_lo) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  using Smem = AttnSmem16<PAIR>;
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wq = warp & 3, half = warp >> 2;
+  const int NK = PAIR ? kRows : (L + 15) & ~15;
+  const int nks = PAIR ? 4 : NK >> 4;               // K = 16 steps of the second product (per trajectory)
+  const uint32_t idesc_s = idesc_f16(NK), idesc_o = idesc_f16(kHd) | (1u << 16);      // bit 16: B is MN-major
+  const int th = PAIR ? (wq >> 1) : 0;
+  const int qrev = PAIR ? (wq & 1) : wq, lrev = lane;
+
+  if (tid == 0) {
+    if (smem_u32(smem_raw) & 1023u) __trap();
+    mbar_init(&s.bar_qk, 1);
+    mbar_init(&s.bar_v, 1);
+    mbar_init(&s.bar_s, 1);
+    mbar_init(&s.bar_o, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "n"(256)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = s.tmem_base;
+  const uint32_t tmem_row = tmem + ((uint32_t)(wq * 32) << 16);
+
+  auto load_qk = [&](int item) {
+    const int b = (PAIR ? 2 : 1) * (item / nhead), h = item % nhead;
+    mbar_arrive_expect_tx(&s.bar_qk, (kTile + Smem::kKeyRows * kHd) * 4);
+    tma_load_3d(&tmQkv, &s.bar_qk, s.q, h * kHd, 0, b);
+    tma_load_3d(&tmK, &s.bar_qk, s.k, d + h * kHd, 0, b);
+  };
+  auto load_v = [&](int item, uint32_t buf) {
+    const int b = (PAIR ? 2 : 1) * (item / nhead), h = item % nhead;
+    mbar_arrive_expect_tx(&s.bar_v, Smem::kKeyRows * kHd * 4);
+    tma_load_3d(&tmV, &s.bar_v, s.v[buf], 2 * d + h * kHd, 0, b);
+  };
+  float* const pmax = s.pmax;
+  float* const psum = s.psum;
+  if ((int)blockIdx.x < n_items && tid == 0) {
+    load_qk(blockIdx.x);
+    load_v(blockIdx.x, 0);
+  }
+
+  uint32_t it = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    const uint32_t ph = it & 1u;
+    const int h = item % nhead;
+    const int b = PAIR ? 2 * (item / nhead) + th : item / nhead;
+    const int next = item + gridDim.x;
+
+    // ---- S = (scaled Q) K^T: both tiles as TMA wrote them ------------------------------------------------------------
+    if (warp == 0) {
+      mbar_wait(&s.bar_qk, ph);
+      __syncwarp();
+      tcgen05_fence_after();
+      const uint64_t dq = umma_desc_sw128(s.q), dk = umma_desc_sw128(s.k);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < kHd / 16; ++k) {
+          const uint64_t hi = (uint64_t)((k * 16 * 2) >> 4), lo = hi + (uint64_t)((kHd * 2) >> 4);
+          mma_f16(tmem, dq + lo, dk + hi, idesc_s, k ? 1u : 0u);
+          mma_f16(tmem, dq + hi, dk + lo, idesc_s, 1u);
+          mma_f16(tmem, dq + hi, dk + hi, idesc_s, 1u);
+        }
+        tcgen05_commit(&s.bar_s);
+      }
+      __syncwarp();
+    }
+    mbar_wait(&s.bar_s, ph);
+    tcgen05_fence_after();
+    if (tid == 0 && next < n_items) load_qk(next);          // Q, K tiles are free
+    __syncwarp();
+    // ---- softmax ----------------------------------------------------------------------------------------------------
+    const bool active = qrev * 32 < L && qrev * 32 + 31 >= row_lo;
+    if (PAIR && active) {
+      const float l = qrev == 0 ? softmax_pair_row16<0>(tmem_row, 64u * th, lrev, half, wq)
+                                : softmax_pair_row16<1>(tmem_row, 64u * th, lrev, half, wq);
+      tmem_st1(tmem_row + kPairX + 2 + half, l);
+      if (qrev == 0) {                                        // keys 32-63 are beyond this quarter's causal range: P = 0
+        const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        tmem_st_cols<8>(tmem_row + 16 + 8 * half, z);
+        tmem_st_cols<8>(tmem_row + kPairPlo16 + 16 + 8 * half, z);
+      }
+      tmem_wait_st();
+    } else if (active) {
+      const bool wide = NK - 32 * qrev >= 32;
+      float l;
+      switch (qrev * 2 + (wide ? 1 : 0)) {
+        case 0: l = softmax_half_row16<0, 16>(tmem_row, lrev, half, wq, pmax, tid); break;
+        case 1: l = softmax_half_row16<0, 32>(tmem_row, lrev, half, wq, pmax, tid); break;
+        case 2: l = softmax_half_row16<1, 16>(tmem_row, lrev, half, wq, pmax, tid); break;
+        case 3: l = softmax_half_row16<1, 32>(tmem_row, lrev, half, wq, pmax, tid); break;
+        case 4: l = softmax_half_row16<2, 16>(tmem_row, lrev, half, wq, pmax, tid); break;
+        case 5: l = softmax_half_row16<2, 32>(tmem_row, lrev, half, wq, pmax, tid); break;
+        case 6: l = softmax_half_row16<3, 16>(tmem_row, lrev, half, wq, pmax, tid); break;
+        default: l = softmax_half_row16<3, 32>(tmem_row, lrev, half, wq, pmax, tid); break;
+      }
+      psum[tid] = l;
+      const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      for (int c = qrev + 1; 32 * c < NK; ++c) {             // keys beyond the quarter's causal range: P = 0
+        if (NK - 32 * c >= 32) {
+          tmem_st_cols<8>(tmem_row + 16 * c + 8 * half, z);
+          tmem_st_cols<8>(tmem_row + kPlo16 + 16 * c + 8 * half, z);
+        } else {
+          tmem_st_cols<4>(tmem_row + 16 * c + 4 * half, z);
+          tmem_st_cols<4>(tmem_row + kPlo16 + 16 * c + 4 * half, z);
+        }
+      }
+      tmem_wait_st();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    // ---- O = P V ----------------------------------------------------------------------------------------------------
+    if (warp == 0) {
+      mbar_wait(&s.bar_v, ph);
+      if (lane == 0 && next < n_items) load_v(next, ph ^ 1u);   // the other buffer: its last reader was item - 1's P V
+      __syncwarp();
+      tcgen05_fence_after();
+      const float* vt = s.v[ph];
+      if (elect_one()) {
+        for (int ks = 0; ks < nks; ++ks) {
+          if (PAIR) {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {                     // O_t = P V_t: valid in the rows of trajectory t
+              const uint64_t dv = umma_desc_mn_sw128_f16(vt + (64 * t + ks * 16) * kHd);
+              const uint32_t acc = tmem + kPairO + 32 * t, a_hi = tmem + 8 * ks, a_lo = tmem + kPairPlo16 + 8 * ks;
+              mma_f16_ta(acc, a_lo, dv, idesc_o, ks ? 1u : 0u);
+              mma_f16_ta(acc, a_hi, dv + 4, idesc_o, 1u);             // + 64 B: the lo halves of the dims
+              mma_f16_ta(acc, a_hi, dv, idesc_o, 1u);
+            }
+          } else {
+            const uint64_t dv = umma_desc_mn_sw128_f16(vt + ks * 16 * kHd);
+            const uint32_t a_hi = tmem + 8 * ks, a_lo = tmem + kPlo16 + 8 * ks;
+            mma_f16_ta(tmem + kColO, a_lo, dv, idesc_o, ks ? 1u : 0u);
+            mma_f16_ta(tmem + kColO, a_hi, dv + 4, idesc_o, 1u);
+            mma_f16_ta(tmem + kColO, a_hi, dv, idesc_o, 1u);
+          }
+        }
+        tcgen05_commit(&s.bar_o);
+      }
+      __syncwarp();
+    }
+    mbar_wait(&s.bar_o, ph);
+    tcgen05_fence_after();
+    __syncwarp();
+    // ---- epilogue: each thread 16 of the row's 32 output dims -----------------------------------------------------
+    const uint32_t col_o = PAIR ? kPairO + 32 * th : kColO;
+    auto row_sum = [&]() -> float {
+      if (PAIR) {
+        const float l0 = tmem_ld1(tmem_row + kPairX + 2);
+        return l0 + tmem_ld1(tmem_row + kPairX + 3);
+      }
+      return psum[tid & 127] + psum[(tid & 127) + 128];
+    };
+    if (active && row_lo == 0) {
+      uint32_t r[16];
+      TmemRow<16>::ld(tmem_row + col_o + 16 * half, r);
+      if (half == 0 && lane == 0) bulk_wait_read<0>();       // the previous item's store has read the staging chunk
+      pair_sync(wq);
+      tmem_wait_ld();
+      const float inv = kPvUnscale / row_sum();
+      float4 (*stg)[8] = s.stage[wq];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        float4 o;
+        o.x = __uint_as_float(r[4 * jj + 0]) * inv;
+        o.y = __uint_as_float(r[4 * jj + 1]) * inv;
+        o.z = __uint_as_float(r[4 * jj + 2]) * inv;
+        o.w = __uint_as_float(r[4 * jj + 3]) * inv;
+        stg[lrev][(4 * half + jj) ^ (lrev & 7)] = o;
+      }
+      fence_proxy_async();
+      pair_sync(wq);
+      if (half == 0 && lane == 0 && b < n_traj) {
+        tma_store_3d(&tmOut, stg, h * kHd, qrev * 32, b);
+        bulk_commit();
+      }
+    } else if (active) {
+      uint32_t r[16];
+      TmemRow<16>::ld(tmem_row + col_o + 16 * half, r);
+      tmem_wait_ld();
+      const int tok = qrev * 32 + lrev;
+      const float rsum = row_sum();
+      if (tok >= row_lo && tok < L && b < n_traj) {
+        const float inv = kPvUnscale / rsum;
+        float4* dst = reinterpret_cast<float4*>(out_rows + ((size_t)b * (L - row_lo) + (tok - row_lo)) * d + h * kHd + 16 * half);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          float4 o;
+          o.x = __uint_as_float(r[4 * jj + 0]) * inv;
+          o.y = __uint_as_float(r[4 * jj + 1]) * inv;
+          o.z = __uint_as_float(r[4 * jj + 2]) * inv;
+          o.w = __uint_as_float(r[4 * jj + 3]) * inv;
+          dst[jj] = o;
+        }
+      }
+    }
+    tcgen05_fence_before();      // the next item's MMAs overwrite S and O
+    __syncthreads();
+  }
+  if (half == 0 && lane == 0) bulk_wait_read<0>();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256) : "memory");
+  }
+}
+
 // Returns QX_EUNSUPPORTED when the shape is outside the kernel's range (the caller then falls back to the mma.sync
 // kernel of qx_tf_attn.cu).  qkv: [B*L][3d] packed rows, out: [B][L - row_lo][d] = the rows row_lo .. L-1 of every
 // trajectory (row_lo = 0: all of them).
-int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhead, int row_lo, cudaStream_t st, bool qk16) {
+// qk16: 0 = fp32 q, k, v; 1 = q, k as fp16 (hi, lo) pairs; 2 = q, k, v as pairs (tf_attention_p16_kernel)
+int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhead, int row_lo, cudaStream_t st, int qk16) {
   if (d != nhead * kHd || L > kMaxKeys || L < 1 || B < 1 || row_lo < 0 || row_lo >= L) return QX_EUNSUPPORTED;
   // QX_TF_ATTN_PAIR=0 keeps one trajectory per tile whatever L is (A/B runs and the equality test)
   const char* env_pair = getenv("QX_TF_ATTN_PAIR");
@@ -705,7 +1064,8 @@ int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhe
     rc = make_map_nd(&mk, qkv, 3, dims, strides, pair ? box2 : boxk);
     if (rc) return rc;
     // V is an MN-major operand of the second product: 32-B swizzle atoms (see umma_desc_mn_sw128_32b)
-    rc = make_map_nd(&mv, qkv, 3, dims, strides, pair ? box2 : boxk, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    rc = make_map_nd(&mv, qkv, 3, dims, strides, pair ? box2 : boxk,
+                     qk16 == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   }
   {
@@ -722,6 +1082,8 @@ int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhe
     cudaFuncSetAttribute(tf_attention_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmemT<true>));
     cudaFuncSetAttribute(tf_attention_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmemT<false>));
     cudaFuncSetAttribute(tf_attention_umma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmemT<true>));
+    cudaFuncSetAttribute(tf_attention_p16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmem16<false>));
+    cudaFuncSetAttribute(tf_attention_p16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmem16<true>));
     cfg[current_device_slot()] = true;
   }
   const int num_sms = device_sm_count();
@@ -731,7 +1093,9 @@ int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhe
   const char* env_dbg = getenv("QX_TF_ATTN_DBG");
   const int dbg = env_dbg ? atoi(env_dbg) : 0;
   const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;
-  if (pair && qk16) tf_attention_umma_kernel<true, true><<<grid, 256, sizeof(AttnSmemT<true>), st>>>(mq, mk, mv, mo, out, n_items, B, nhead, L, d, row_lo, dbg);
+  if (qk16 == 2 && pair) tf_attention_p16_kernel<true><<<grid, 256, sizeof(AttnSmem16<true>), st>>>(mq, mk, mv, mo, out, n_items, B, nhead, L, d, row_lo);
+  else if (qk16 == 2) tf_attention_p16_kernel<false><<<grid, 256, sizeof(AttnSmem16<false>), st>>>(mq, mk, mv, mo, out, n_items, B, nhead, L, d, row_lo);
+  else if (pair && qk16) tf_attention_umma_kernel<true, true><<<grid, 256, sizeof(AttnSmemT<true>), st>>>(mq, mk, mv, mo, out, n_items, B, nhead, L, d, row_lo, dbg);
   else if (pair) tf_attention_umma_kernel<true, false><<<grid, 256, sizeof(AttnSmemT<true>), st>>>(mq, mk, mv, mo, out, n_items, B, nhead, L, d, row_lo, dbg);
   else if (qk16) tf_attention_umma_kernel<false, true><<<grid, 256, sizeof(AttnSmemT<false>), st>>>(mq, mk, mv, mo, out, n_items, B, nhead, L, d, row_lo, dbg);
   else tf_attention_umma_kernel<false, false><<<grid, 256, sizeof(AttnSmemT<false>), st>>>(mq, mk, mv, mo, out, n_items, B, nhead, L, d, row_lo, dbg);

@@ -372,9 +372,9 @@ static int gemm(const float* A, const float* W, const float* bias, float* C, int
 // tensor-core GEMM (qx_tf_tc.cu)
 int tf_attention_tc(const float* qkv, float* out, int B, int L, int d, int nhead, cudaStream_t st);   // qx_tf_attn.cu
 int tf_attention_umma(const float* qkv, float* out, int B, int L, int d, int nhead, int row_lo, cudaStream_t st,
-                      bool qk16 = false); // qx_tf_attn05.cu
+                      int qk16 = 0); // qx_tf_attn05.cu
 int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* bias, float* C, int M, int N, int K,
-               bool relu, cudaStream_t st, bool f16, bool pack_qk = false);
+               bool relu, cudaStream_t st, bool f16, int pack_qk = 0);
 int tf_split_weights(const float* w, float* hi, float* lo, size_t count, cudaStream_t st, bool f16);
 int tf_gemm_ln_tc(const float* A, const float* Whi, const float* Wlo, const float* bias, const float* res, const float* gamma,
                   const float* beta, float* C, int M, int K, cudaStream_t st, bool f16);
@@ -464,13 +464,15 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
   // Q K V for all rows, then attention, out-proj, both LayerNorms, the FFN and the head on a compact [B][T] row stream
   // (49 of 101 rows for the quadrotor).  Row-wise arithmetic is unchanged, so the predictions are bit-identical
   // (QX_TF_NO_PRUNE=1 switches it off for the equality test).
-  // Q and K leave the QKV projection as fp16 (hi, lo) pairs, MMA-ready for the tcgen05 attention (qx_tf_attn05.cu, QK16),
-  // when the dense layers run on the fp16 split and that attention kernel takes the shape; QX_TF_ATTN_QK16=0 keeps fp32
-  // q, k and the in-kernel TF32 split (A/B runs, accuracy test)
+  // q, k, v leave the QKV projection as fp16 (hi, lo) pairs, MMA-ready for the tcgen05 attention (qx_tf_attn05.cu), when
+  // the dense layers run on the fp16 split and that attention kernel takes the shape.  QX_TF_ATTN_QK16: 2 (default) q, k
+  // and v packed, both attention products kind::f16; 1: q and k only (P V stays on the in-kernel TF32 split); 0: fp32
+  // q, k, v and the TF32 splits (A/B runs, accuracy test).
   const char* env_qk = getenv("QX_TF_ATTN_QK16");
   const char* env_mma0 = getenv("QX_TF_ATTN_MMA");
-  const bool qk16 = wsplit != nullptr && f16 && d == 128 && cfg->nhead == 4 && L <= 112 &&
-                    !(env_qk != nullptr && env_qk[0] == '0') && !(env_mma0 != nullptr && env_mma0[0] == '1');
+  int qk16 = 0;
+  if (wsplit != nullptr && f16 && d == 128 && cfg->nhead == 4 && L <= 112 && !(env_mma0 != nullptr && env_mma0[0] == '1'))
+    qk16 = env_qk == nullptr ? 2 : (env_qk[0] == '0' ? 0 : (env_qk[0] == '1' ? 1 : 2));
   const char* env_np = getenv("QX_TF_NO_PRUNE");
   const bool prune = wsplit != nullptr && per_traj && !(env_np != nullptr && env_np[0] == '1') && lay.T < L;
   const int rows_c = B * lay.T;
@@ -481,7 +483,7 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
     int rc;
     if (qk16) {
       const float* sw = wsplit + (size_t)l * sp.stride;
-      rc = tf_gemm_tc(h, wh(sw + sp.in_hi), wh(sw + sp.in_lo), lw + lay.l_inb, qkv, rows, 3 * d, d, false, st, true, true);
+      rc = tf_gemm_tc(h, wh(sw + sp.in_hi), wh(sw + sp.in_lo), lw + lay.l_inb, qkv, rows, 3 * d, d, false, st, true, qk16);
     } else {
       rc = dense(h, lw, lay.l_inw, lay.l_inb, sp.in_hi, sp.in_lo, l, qkv, 3 * d, d, false);
     }

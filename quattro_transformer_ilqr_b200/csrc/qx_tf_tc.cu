@@ -241,14 +241,6 @@ tf_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // of (32 hi + 32 lo) columns.  Results are bit-identical to the streaming kernel (same MMAs, same order).
 constexpr int kTaW = 4, kTaRaw = 4, kTaA = 4;
 
-// (a, b) -> packed fp16 (hi, hi) and (lo, lo), a in the low halves
-__device__ __forceinline__ void f16_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(a, b);
-  const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
 // accumulator -> product: the fp16 weights carry a factor 2^8 (exact to undo)
 template <bool F16>
 __device__ __forceinline__ float unscale(uint32_t acc) {
@@ -260,14 +252,6 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
       "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void mma_f16_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
 constexpr int ta_threads(int sets) { return 64 + 128 * sets + 128; }
@@ -306,6 +290,7 @@ struct LnArgs {
 constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);   // D = F32, A = B = F16
 constexpr float kW16Scale = 256.f;
 constexpr int kGemmPackQk = 16;      // flag bit of the kernel's `dbg` argument: n tiles 0 and 1 (Q, K) leave as fp16 (hi, lo) pairs
+constexpr int kGemmPackV = 32;       // ... and so does n tile 2 (V, times 2^4)
 
 template <bool RELU, bool STREAM_W, int kSets, bool LN = false, bool F16 = false>
 __global__ void __launch_bounds__(ta_threads(kSets), 1)
@@ -610,12 +595,14 @@ tf_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c0);
           float4 (*stg)[8] = s.epi[q][chunk & 1u];
-          if (F16 && !RELU && (dbg & kGemmPackQk) && n0 < 2 * kBN) {
+          if (F16 && !RELU && (dbg & kGemmPackQk) && (n0 < 2 * kBN || (dbg & kGemmPackV))) {
             // Q / K columns of the QKV projection for the tcgen05 attention (qx_tf_attn05.cu, QK16): the 32 floats of a
             // head slice leave as (hi, lo) fp16 halves - 16-B pieces 0-3 hold hi of dims 0-31, pieces 4-7 lo - the same
             // 128 B per row, which the attention's TMA box lands as a K-major fp16 tile of 64 k: no split over there.
-            // Q carries the softmax scale log2(e) / sqrt(head dim) already (what split_q_row applied).
-            const float qs = n0 == 0 ? rsqrtf(32.f) * 1.4426950408889634f : 1.f;
+            // Q carries the softmax scale log2(e) / sqrt(head dim) already (what split_q_row applied); with kGemmPackV the
+            // V columns are packed as well, times 2^4 (their lo halves then stay out of the fp16 subnormals; undone
+            // exactly by the attention epilogue).
+            const float qs = n0 == 0 ? rsqrtf(32.f) * 1.4426950408889634f : (n0 == 2 * kBN ? 16.f : 1.f);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const float4 b0 = b4[2 * u], b1 = b4[2 * u + 1];
@@ -698,7 +685,7 @@ static int make_map(CUtensorMap* map, const float* base, int rows, int cols, int
 
 // f16: Whi / Wlo hold the fp16 halves tf_split_weights(.., true) wrote (N x K halves each; the maps see K / 2 floats a row)
 int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* bias, float* C, int M, int N, int K,
-               bool relu, cudaStream_t st, bool f16, bool pack_qk) {
+               bool relu, cudaStream_t st, bool f16, int pack_qk) {
   if (pack_qk && !(f16 && !relu && N == 3 * kBN && K == kTaW * kBK)) {
     set_error("fp16-pair Q / K output needs the fp16-split QKV projection of a d = 128 model (got N=%d K=%d)", N, K);
     return QX_EINVAL;
@@ -734,7 +721,8 @@ int tf_gemm_tc(const float* A, const float* Whi, const float* Wlo, const float* 
     if (groups > m_tiles) groups = m_tiles;
     const int grid = groups * n_tiles_n;
     const char* env_dbg = getenv("QX_TF_GEMM_DBG");
-    const int dbg = ((env_dbg ? atoi(env_dbg) : 0) & ~kGemmPackQk) | (pack_qk ? kGemmPackQk : 0);
+    const int dbg = ((env_dbg ? atoi(env_dbg) : 0) & ~(kGemmPackQk | kGemmPackV)) | (pack_qk ? kGemmPackQk : 0) |
+                    (pack_qk == 2 ? kGemmPackV : 0);
     const char* env_var = getenv("QX_TF_GEMM_VARIANT");
     const int variant = env_var ? atoi(env_var) : 0;
     CUtensorMap mc;

@@ -509,34 +509,35 @@ def test_tcgen05_attention_matches_mma_sync_and_exact_attention(system, mode, go
 
 @pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
 @pytest.mark.parametrize("mode", ["rand", "fp32"])
-def test_fp16_pair_q_k_from_the_qkv_projection(system, mode, golden_dir, monkeypatch):
-    """Default path: the QKV projection writes Q (scaled) and K as fp16 (hi, lo) pairs and the tcgen05 attention takes
-    them as MMA-ready K-major tiles (six kind::f16 products, no split in the attention kernel).  QX_TF_ATTN_QK16=0: fp32
-    q, k and the in-kernel TF32 split.  Both carry 22 bits per operand: within 5e-6 of the exact fp32 path and of each
+def test_fp16_pair_q_k_v_from_the_qkv_projection(system, mode, golden_dir, monkeypatch):
+    """Default path (QX_TF_ATTN_QK16=2): the QKV projection writes q (scaled), k and v (times 2^4) as fp16 (hi, lo) pairs
+    and the tcgen05 attention takes all three tiles as TMA landed them - S and P V are kind::f16 products, P is split into
+    fp16 pairs (times 2^8), no operand split by a thread.  =1: q and k only, P V on the in-kernel TF32 split.  =0: fp32
+    q, k, v and TF32 splits throughout.  All carry 22 bits per operand: within 5e-6 of the exact fp32 path and of each
     other; run-to-run identical; 1 200 trajectories = 16 items per persistent CTA, both tile modes (L = 61 paired,
-    L = 101 single), pruned last layer included."""
+    L = 101 single), pruned and full-width last layer."""
     g = np.load(f"{golden_dir}/tf_forward_{system}.npz")
     w = _wrapper(system, mode)
     rng = np.random.default_rng(21)
     reps = 1200 // len(g["x_err"])
     x = np.concatenate([g["x_err"] * (1.0 + 0.05 * rng.standard_normal(g["x_err"].shape)) for _ in range(reps)])
     kK = np.concatenate([g["kK"] * (1.0 + 0.05 * rng.standard_normal(g["kK"].shape)) for _ in range(reps)])
-    monkeypatch.setenv("QX_TF_ATTN_QK16", "1")
-    packed = w.predict(x, kK)
-    assert np.isfinite(packed).all() and np.array_equal(w.predict(x, kK), packed)
-    monkeypatch.setenv("QX_TF_NO_PRUNE", "1")
-    assert np.array_equal(w.predict(x, kK), packed)
-    monkeypatch.setenv("QX_TF_NO_PRUNE", "0")
-    monkeypatch.setenv("QX_TF_ATTN_QK16", "0")
-    split = w.predict(x, kK)
-    assert not np.array_equal(packed, split)           # the switch does select another path
+    out = {}
+    for sw in ("2", "1", "0"):
+        monkeypatch.setenv("QX_TF_ATTN_QK16", sw)
+        out[sw] = w.predict(x, kK)
+        assert np.isfinite(out[sw]).all() and np.array_equal(w.predict(x, kK), out[sw])
+        monkeypatch.setenv("QX_TF_NO_PRUNE", "1")
+        assert np.array_equal(w.predict(x, kK), out[sw])
+        monkeypatch.setenv("QX_TF_NO_PRUNE", "0")
+    assert not np.array_equal(out["2"], out["1"]) and not np.array_equal(out["1"], out["0"])    # three different paths
     w.tensor_cores = False
     exact = w.predict(x, kK)
-    e_p, e_s = relmax(packed, exact), relmax(split, exact)
-    print(f"{system}/{mode}: fp16-pair Q, K {e_p:.2e}, in-kernel TF32 split {e_s:.2e} from the exact fp32 path; "
-          f"between them {relmax(packed, split):.2e}")
+    errs = {sw: relmax(o, exact) for sw, o in out.items()}
+    print(f"{system}/{mode}: q, k, v pairs {errs['2']:.2e}, q, k pairs {errs['1']:.2e}, TF32 splits {errs['0']:.2e} from the exact "
+          f"fp32 path; 2 vs 0 {relmax(out['2'], out['0']):.2e}")
     tol = 5e-6 if mode == "rand" else 5e-5
-    assert e_p < tol and e_s < tol and relmax(packed, split) < tol
+    assert max(errs.values()) < tol and relmax(out["2"], out["0"]) < tol
 
 
 @pytest.mark.parametrize("mode", ["rand", "fp32"])
