@@ -352,6 +352,58 @@ tf_unpack128_kernel(const QxTfConfig cfg, const float* __restrict__ w, const flo
   }
 }
 
+// the same for 32 trajectories x one target row per CTA, transposed through shared memory: the head rows are read as
+// whole 4 c-byte pieces and the gains leave as 512-B lines along the trajectory index (a warp of the per-trajectory
+// kernel above scattered 13 sixteen-byte pieces 16 B lines apart: 77 us at 8 192 quadrotor trajectories, 24 % of DRAM)
+template <int LAYOUT>
+__global__ void __launch_bounds__(128)
+tf_unpack_tile_kernel(const QxTfConfig cfg, const float* __restrict__ w, const float* __restrict__ y,
+                      float* __restrict__ gains, const int32_t* __restrict__ status, int B, int compact) {
+  const TfLayout lay(cfg);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b0 = blockIdx.x * 32, t = blockIdx.y;
+  const int c = lay.c, m = cfg.m, n = lay.n, G = m + m * n;
+  __shared__ float tile[64][33];
+  float v[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int b = b0 + warp + 4 * i;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int o = lane + 32 * k;
+      if (b < B && o < c) {
+        const float* row = compact ? y + ((size_t)b * lay.T + t) * 128 : y + ((size_t)b * lay.L + (lay.L - lay.T + t)) * 128;
+        v[i][k] = row[o];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int o = lane + 32 * k;
+    if (o < c) {
+      const float sd = w[lay.u_std + o], mu = w[lay.u_mean + o];
+      const int a = o / (1 + n), j = o % (1 + n);
+      const int slot = (j == 0) ? a : (m + a * n + (j - 1));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tile[slot][warp + 4 * i] = v[i][k] * sd + mu;
+    }
+  }
+  __syncthreads();
+  if (LAYOUT == QX_LAYOUT_REC) {
+    for (int e = threadIdx.x; e < (G >> 2) * 32; e += 128) {
+      const int q = e >> 5, bl = e & 31, b = b0 + bl;
+      if (b < B && (status == nullptr || status[b] == 0))
+        *reinterpret_cast<float4*>(&gains[gain_index<LAYOUT>(t, 4 * q, b, B, G)]) =
+            make_float4(tile[4 * q][bl], tile[4 * q + 1][bl], tile[4 * q + 2][bl], tile[4 * q + 3][bl]);
+    }
+  } else {
+    for (int e = threadIdx.x; e < G * 32; e += 128) {
+      const int slot = e >> 5, bl = e & 31, b = b0 + bl;
+      if (b < B && (status == nullptr || status[b] == 0)) gains[gain_index<LAYOUT>(t, slot, b, B, G)] = tile[slot][bl];
+    }
+  }
+}
+
 // zero-padded copy of the output head: W_out [c][d] -> [128][d], bias [c] -> [128]
 __global__ void tf_pad_head_kernel(const float* __restrict__ wo, const float* __restrict__ bo, float* __restrict__ wpad,
                                    float* __restrict__ bpad, int c, int d) {
@@ -581,8 +633,17 @@ int tf_forward_simt(const QxTfConfig* cfg, const float* w, const float* wsplit, 
                         false, st, f16);
     if (rc) return rc;
     if (per_traj) {
-      if (layout == QX_LAYOUT_REC) tf_unpack128_kernel<QX_LAYOUT_REC><<<B, 128, 0, st>>>(*cfg, w, y, gains, status, B, pruned ? 1 : 0);
-      else tf_unpack128_kernel<QX_LAYOUT_SOA><<<B, 128, 0, st>>>(*cfg, w, y, gains, status, B, pruned ? 1 : 0);
+      // QX_TF_UNPACK_TILE=0: the per-trajectory kernel (A/B runs; same values)
+      const char* env_ut = getenv("QX_TF_UNPACK_TILE");
+      const dim3 gt(ceil_div(B, 32), lay.T);
+      if (env_ut != nullptr && env_ut[0] == '0') {
+        if (layout == QX_LAYOUT_REC) tf_unpack128_kernel<QX_LAYOUT_REC><<<B, 128, 0, st>>>(*cfg, w, y, gains, status, B, pruned ? 1 : 0);
+        else tf_unpack128_kernel<QX_LAYOUT_SOA><<<B, 128, 0, st>>>(*cfg, w, y, gains, status, B, pruned ? 1 : 0);
+      } else if (layout == QX_LAYOUT_REC) {
+        tf_unpack_tile_kernel<QX_LAYOUT_REC><<<gt, 128, 0, st>>>(*cfg, w, y, gains, status, B, pruned ? 1 : 0);
+      } else {
+        tf_unpack_tile_kernel<QX_LAYOUT_SOA><<<gt, 128, 0, st>>>(*cfg, w, y, gains, status, B, pruned ? 1 : 0);
+      }
     } else {
       if (layout == QX_LAYOUT_REC) tf_unpack_kernel<QX_LAYOUT_REC><<<go, 64, 0, st>>>(*cfg, w, y, gains, status, B);
       else tf_unpack_kernel<QX_LAYOUT_SOA><<<go, 64, 0, st>>>(*cfg, w, y, gains, status, B);

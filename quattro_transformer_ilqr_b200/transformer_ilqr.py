@@ -188,7 +188,7 @@ class TransformerILQR:
         ws = getattr(engine, "_tf_ws", None)
         env = tuple(os.environ.get(k, "") for k in ("QX_TF_FUSE_LN", "QX_TF_NO_PRUNE", "QX_TF_GEMM_STREAM", "QX_TF_GEMM_VARIANT",
                                                      "QX_TF_ATTN_PAIR", "QX_TF_ATTN_MMA", "QX_TF_ATTN_DBG", "QX_TF_GEMM_DBG", "QX_TF_GEMM_F16",
-                                                     "QX_TF_FFN_FUSE", "QX_TF_TAIL_FUSE", "QX_TF_ATTN_QK16"))
+                                                     "QX_TF_FFN_FUSE", "QX_TF_TAIL_FUSE", "QX_TF_ATTN_QK16", "QX_TF_UNPACK_TILE"))
         return (id(self), bool(self.tensor_cores), None if packed is None else (packed[1].data_ptr(), packed[2].data_ptr()),
                 None if shift is None else shift.data_ptr(), None if ws is None else ws.data_ptr(), env)
 

@@ -540,6 +540,24 @@ def test_fp16_pair_q_k_v_from_the_qkv_projection(system, mode, golden_dir, monke
     assert max(errs.values()) < tol and relmax(out["2"], out["0"]) < tol
 
 
+@pytest.mark.parametrize("system", ["cartpole", "quadrotor"])
+@pytest.mark.parametrize("batch", [1, 33, 1201])
+def test_tiled_unpack_is_bit_identical(system, batch, golden_dir, monkeypatch):
+    """The predictions unpacked 32 trajectories per CTA through shared memory (default: the gains leave as 512-B lines
+    along the trajectory index) or per trajectory (QX_TF_UNPACK_TILE=0): same arithmetic per element, so the same bits;
+    ragged last tiles included."""
+    g = np.load(f"{golden_dir}/tf_forward_{system}.npz")
+    w = _wrapper(system, "rand")
+    rng = np.random.default_rng(31)
+    reps = -(-batch // len(g["x_err"]))
+    x = np.concatenate([g["x_err"] * (1.0 + 0.05 * rng.standard_normal(g["x_err"].shape)) for _ in range(reps)])[:batch]
+    kK = np.concatenate([g["kK"] * (1.0 + 0.05 * rng.standard_normal(g["kK"].shape)) for _ in range(reps)])[:batch]
+    base = w.predict(x, kK)
+    assert np.isfinite(base).all()
+    monkeypatch.setenv("QX_TF_UNPACK_TILE", "0")
+    assert np.array_equal(w.predict(x, kK), base)
+
+
 @pytest.mark.parametrize("mode", ["rand", "fp32"])
 @pytest.mark.parametrize("batch", [1, 2, 1201])
 def test_two_cartpole_trajectories_per_attention_tile(mode, batch, golden_dir, monkeypatch):
