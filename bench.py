@@ -71,12 +71,12 @@ TF_FLOPS = {"quadrotor": 135635456.0, "cartpole": 53757952.0}
 
 def tensor_peak():
     """Tensor peak = the measured dense bf16 / fp16 figure (burst: the forward is timed alone, between events): the dense
-    layers (87 % of the algorithmic flops) run as kind::f16 products of fp16 (hi, lo) halves, the attention products as
-    kind::tf32 at half that rate.  Every product is evaluated as three MMAs; algorithmic flops are counted once."""
+    layers and the attention products all run as kind::f16 products of fp16 (hi, lo) halves.  Every product is evaluated
+    as three MMAs; algorithmic flops are counted once."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         p = json.load(open(path))
-        return float(p["bf16_tflops"]), "measured bf16 burst (MEASURED_PEAKS.json): kind::f16 rate; the attention products (kind::tf32) run at half of it"
+        return float(p["bf16_tflops"]), "measured bf16 burst (MEASURED_PEAKS.json): the kind::f16 rate every product of the forward runs at"
     return 1650.0, "fallback bf16 figure (B200_PROFILING.md)"
 
 
@@ -512,11 +512,11 @@ def gpu_bench(args):
         achieved = TF_FLOPS[system] * B / (tf_ms * 1e-3) / 1e12
         kernels["transformer"].update({"algo_flops_per_traj": TF_FLOPS[system], "TFLOPs": round(achieved, 1),
                                        "frac_tensor": round(achieved / tpeak, 4)})
-        roofline = {"kernel": "transformer forward (three-term fp16 / TF32 splits on tcgen05: dense layers, fused FFN, attention)", "bound": "tensor",
+        roofline = {"kernel": "transformer forward (three-term fp16 splits on tcgen05: dense layers, fused FFN, attention on fp16-pair q, k, v)", "bound": "tensor",
                     "achieved": round(achieved, 1), "peak": tpeak, "unit": "TFLOP/s", "frac": round(achieved / tpeak, 4),
                     "traffic": None, "peak_source": thow, "algo_flops_per_launch": TF_FLOPS[system] * B,
                     "note": "fp32-accurate products cost three tensor-core MMAs each: the tensor pipe does 3x the algorithmic "
-                            "flops counted here; per-kernel tensor-pipe activity is in profiles/r2_ncu_full_transformer_summary.txt"}
+                            "flops counted here; per-kernel tensor-pipe activity is in profiles/r2_ncu_full_transformer_p16_summary.txt"}
     else:
         per_launch = kernels[dom].get("algo_bytes_per_launch", kernels[dom].get("algo_bytes_per_traj", 0.0) * B)
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["GBps"], "peak": hbm, "unit": "GB/s",
