@@ -506,6 +506,40 @@ def test_staged_search_equals_sequential_search_bitwise():
         assert torch.equal(a.x[buf], b.x[buf]) and torch.equal(a.u[buf], b.u[buf])
 
 
+def test_linesearch_stage_events_time_the_three_launches():
+    """qx_linesearch_stage_events: four caller-owned events recorded in front of stage A and behind A, B, W of the staged
+    quadrotor search (what bench.py times the launches with); results are untouched, a cleared hook records nothing."""
+    import ctypes as C
+    x0, u = _problem("quadrotor", 4096, 5, 1.5)
+    outs = []
+    for hooked in (False, True):
+        e = _engine("quadrotor", 4096)
+        e.set_problem(x0, u)
+        e.linearize(0); e.riccati(0)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        for v in ev:
+            v.record()
+        torch.cuda.synchronize()
+        before = [ev[0].elapsed_time(v) for v in ev]
+        if hooked:
+            arr = (C.c_void_p * 4)(*[v.cuda_event for v in ev])
+            assert e.lib.qx_linesearch_stage_events(arr, 4) == 0
+        try:
+            e.linesearch(1e-3)
+            torch.cuda.synchronize()
+        finally:
+            assert e.lib.qx_linesearch_stage_events(None, 0) == 0
+        after = [ev[0].elapsed_time(v) for v in ev]
+        if hooked:
+            d = [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+            assert all(t > 0 for t in d) and d[0] > 0.01         # stage A rolls 4 096 trajectories out: tens of microseconds
+        else:
+            assert after == before                               # the events still hold their own records
+        outs.append((e.cost.clone(), e.alpha.clone(), e.u[e.cur].clone()))
+    assert all(torch.equal(a, b) for a, b in zip(outs[0], outs[1]))
+    assert _engine("quadrotor", 8).lib.qx_linesearch_stage_events(None, 3) != 0      # count must be 0 or 4
+
+
 def test_gain_record_layout_round_trip():
     """float4 [N][13][B] gains of the quadrotor: load_gains / gains_batch are inverse, and element (t, ch, b) sits where
     include/quattro_b200.h says."""

@@ -17,7 +17,7 @@ for (B, L) in [(8192, 101), (4096, 61)]:
 for system in ("quadrotor", "cartpole"):
     g = np.load(f"tests/golden/tf_forward_{system}.npz")
     w = TransformerILQR(1, 1).load(f"tests/golden/checkpoints/{system}")
-    k = 2048 // len(g["x_err"])
+    k = int(os.environ.get("RACE_B", "2048")) // len(g["x_err"])
     x = np.concatenate([g["x_err"]] * k); kK = np.concatenate([g["kK"]] * k)
     ref = w.predict(x, kK); bad = 0
     for i in range(reps // 4):
