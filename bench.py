@@ -56,6 +56,20 @@ FP64_EXTRA = {"quadrotor": {"linearize": 3248, "riccati": 0, "linesearch": 3248 
 BLK_BYTES = {"linearize": 6496 + 50 * 192 + 64, "riccati": 50 * 192 + 64 + 50 * 208}
 
 
+def workload_config(workload, world, B=None):
+    """The `config` object of the JSON line: the workload only (both arms print the same object)."""
+    system, N, B_default, use_tf = WORKLOADS[workload]
+    B = B or B_default
+    n, m = (12, 4) if system == "quadrotor" else (4, 1)
+    return {"workload": f"{workload}: {system} n={n} m={m} horizon={N}, {B} trajectories per GPU, "
+                        f"fixed-iteration mode, problem reset every {RESET_EVERY} steps"
+                        + (", gains of steps 0..N-P-1 predicted by the transformer (random-init fp32 weights)" if use_tf else ""),
+            "global_batch": world * B, "parallelism": f"dp{world} (independent trajectory shards)",
+            "l2": "no flush needed: the working set of an iteration (x, u ping-pong 13 KB + expansion 13 KB + gains 10 KB "
+                  "per quadrotor trajectory = 0.6 GB at 16 384; transformer activations 0.4 MB per trajectory) is larger than "
+                  "the 126 MB L2"}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -555,13 +569,9 @@ def gpu_bench(args):
         "value": value, "unit": "trajectory-iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (linearise/Riccati/transformer) + f64 (rollouts, costs)", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {system} n={n} m={m} horizon={N}, {B} trajectories per GPU, "
-                               f"fixed-iteration mode, problem reset every {RESET_EVERY} steps",
-                   "global_batch": world * B, "parallelism": f"dp{world} (independent trajectory shards)",
-                   "backward_pass": "block records (48 floats per step)" if eng.exp_layout == 2 else "dense records",
-                   "launch": "two iterations per CUDA-graph replay" if args.graph else "one launch per kernel",
-                   "l2": "working set per iteration (x, u ping-pong 0.21 GB + expansion 0.21 GB + gains 0.17 GB at 16 384 "
-                         "trajectories) larger than the 126 MB L2"},
+        "config": workload_config(args.workload, world, B),
+        "implementation": {"backward_pass": "block records (48 floats per step)" if eng.exp_layout == 2 else "dense records",
+                           "launch": "two iterations per CUDA-graph replay" if args.graph else "one launch per kernel"},
         "e2e": {"value": e2e_value, "unit": "trajectory-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "pipeline": f"{chunks} slices on {chunks} streams, consecutive batches overlap" if chunks > 1 else "single stream",
                 "host_numa_bound": numa_bound},
@@ -589,8 +599,11 @@ def reference_arm(args):
         "value": val, "unit": "trajectory-iterations/s", "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)),
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {system} n={n} m={m} horizon={N}; CPU path: scalar finite-difference iLQR "
-                               f"(oracle/ilqr_port.py, bit-identical to the reference's quattro_ilqr_tf.py)"},
+        # the same config object as the GPU arm's line (the driver compares them); what this arm runs of it - the scalar
+        # finite-difference port, a bounded sample per step - is said in `implementation` and `cpu_baseline.sample`
+        "config": workload_config(args.workload, int(os.environ.get("WORLD_SIZE", args.gpus)), args.batch or None),
+        "implementation": {"cpu_path": "scalar finite-difference iLQR (oracle/ilqr_port.py, pinned bit for bit to the "
+                                       "reference's quattro_ilqr_tf.py), one process per host core"},
         "cpu_baseline": {"value": val, "unit": "trajectory-iterations/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "trajectory-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
