@@ -136,7 +136,23 @@ __device__ __forceinline__ void qd_step(double* x, const double* u, const QdK& k
 // L(x, u) (quadrotor_mpc.py:86-93) added to four partial sums: c[g] takes state block g, control g and its barrier
 // term alpha_b * softplus(-u_g; beta)^2 (:80, :92).  log1p(e) by its series when e is tiny (u well on the feasible
 // side), by fast_log1p_unit otherwise.
-__device__ __forceinline__ void qd_running(const double* x, const double* u, const QdK& k, double* c) {
+// The 28 weights of the running cost, copied to shared memory by every CTA of the candidate kernels.  As kernel
+// parameters they are uniform-register operands of the fp64 instructions - and the uniform file holds 63 registers
+// against the ~100 fp64 constants of a step, so the compiler parked these in 56 VECTOR registers for the whole loop and
+// moved each to a uniform pair at its one use per step (56 R2UR per step).  A broadcast LDS.64 per use costs half the
+// instructions and no long-lived register.
+struct QdCostW {
+  double qd[kN], xr[kN], rd[kM];
+};
+__device__ __forceinline__ void qd_stage_cost(const QdK& k, QdCostW& w) {     // all 32 lanes of the (one-warp) CTA
+  const int lane = threadIdx.x & 31;
+  if (lane < kN) { w.qd[lane] = k.qd[lane]; w.xr[lane] = k.xr[lane]; }
+  if (lane < kM) w.rd[lane] = k.rd[lane];
+  __syncwarp();
+}
+
+template <class W>
+__device__ __forceinline__ void qd_running(const double* x, const double* u, const QdK& k, const W& w, double* c) {
   double e[kM], bz[kM], l1p[kM];
   bool need = false;
 #pragma unroll
@@ -158,10 +174,10 @@ __device__ __forceinline__ void qd_running(const double* x, const double* u, con
     double acc = 0.0;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      const double dxv = x[3 * g + r] - k.xr[3 * g + r];
-      acc = fma(k.qd[3 * g + r] * dxv, dxv, acc);
+      const double dxv = x[3 * g + r] - w.xr[3 * g + r];
+      acc = fma(w.qd[3 * g + r] * dxv, dxv, acc);
     }
-    acc = fma(k.rd[g] * u[g], u[g], acc);
+    acc = fma(w.rd[g] * u[g], u[g], acc);
     const double sp = (fmax(bz[g], 0.0) + l1p[g]) * k.inv_beta;
     c[g] += acc + k.alpha_b * sp * sp;
   }
@@ -189,6 +205,7 @@ __device__ __forceinline__ double qd_total(const double* c) { return (c[0] + c[1
 struct QdStage {
   double xu[2][kN + kM][32];
   float4 g[2][kG / 4][32];
+  QdCostW w;
 };
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
@@ -216,6 +233,7 @@ __device__ __forceinline__ double qd_candidate(const QdK& k, QdStage& st, bool r
                                                double alpha, double limit, double* __restrict__ xo,
                                                double* __restrict__ uo, size_t sO, int N) {
   const int lane = threadIdx.x & 31;
+  qd_stage_cost(k, st.w);
   double xh[kN];
 #pragma unroll
   for (int i = 0; i < kN; ++i) xh[i] = run ? xin[(size_t)i * sB] : 0.0;
@@ -281,7 +299,7 @@ __device__ __forceinline__ double qd_candidate(const QdK& k, QdStage& st, bool r
       uo += kM * sO;
       xo += kN * sO;
     }
-    qd_running(xh, uh, k, c);
+    qd_running(xh, uh, k, st.w, c);
     qd_step<INTEG>(xh, uh, k);
     run = run && !(qd_total(c) > limit);
     if (!run) { xh[6] = 0.0; xh[7] = 0.0; xh[8] = 0.0; }      // a dead lane never sends the warp into the slow sincos
@@ -366,7 +384,7 @@ rollout_qd_kernel(const __grid_constant__ QdK k, const double* __restrict__ x0, 
 #pragma unroll
     for (int i = 0; i < kN; ++i) xp[(size_t)i * sB] = xh[i];
     xp += kN * sB;
-    qd_running(xh, uh, k, c);
+    qd_running(xh, uh, k, k, c);
     qd_step<INTEG>(xh, uh, k);
   }
 #pragma unroll
