@@ -433,27 +433,29 @@ def gpu_bench(args):
             qlib_h = eng.lib
             assert qlib_h.qx_linesearch_stage_events(handles, 4) == 0
         start = 0 if tf is None else N - tf.prompt_len
-        for window in range(2):
-            eng.set_problem(x0_d, u0_d)
-            for it in range(RESET_EVERY):
-                evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
-                evs[0].record()
-                eng.linearize(start); evs[1].record()
-                eng.riccati(start); evs[2].record()
-                j = 2
-                if use_tf:
-                    tf.forward_device(eng); j += 1; evs[j].record()
-                eng.linesearch(tol, force=True); evs[j + 1].record()
-                torch.cuda.synchronize(dev)
-                if window == 1:
-                    for q, k in enumerate(names):
-                        acc[k].append(evs[q].elapsed_time(evs[q + 1]))
-                    if staged:
-                        for q, k in enumerate(stage_acc):
-                            stage_acc[k].append(sev[q].elapsed_time(sev[q + 1]))
-                        queued.append(int(eng.ls_workspace[:4].view(torch.int32)[0].item()))
-        if staged:
-            assert eng.lib.qx_linesearch_stage_events(None, 0) == 0
+        try:
+            for window in range(2):
+                eng.set_problem(x0_d, u0_d)
+                for it in range(RESET_EVERY):
+                    evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+                    evs[0].record()
+                    eng.linearize(start); evs[1].record()
+                    eng.riccati(start); evs[2].record()
+                    j = 2
+                    if use_tf:
+                        tf.forward_device(eng); j += 1; evs[j].record()
+                    eng.linesearch(tol, force=True); evs[j + 1].record()
+                    torch.cuda.synchronize(dev)
+                    if window == 1:
+                        for q, k in enumerate(names):
+                            acc[k].append(evs[q].elapsed_time(evs[q + 1]))
+                        if staged:
+                            for q, k in enumerate(stage_acc):
+                                stage_acc[k].append(sev[q].elapsed_time(sev[q + 1]))
+                            queued.append(int(eng.ls_workspace[:4].view(torch.int32)[0].item()))
+        finally:                                     # never leave the hook pointing at events that are about to die
+            if staged:
+                assert eng.lib.qx_linesearch_stage_events(None, 0) == 0
         hbm, how = peaks()
         from quattro_transformer_ilqr_b200 import _lib as qlib
         blk = eng.exp_layout == qlib.QX_LAYOUT_BLK
