@@ -147,3 +147,25 @@ def test_ilqr_constructor_errors():
         iLQR_TF(dm, None, None, np.zeros(4), [np.zeros(1)] * 5, 5, tf_window=5)
     s = iLQR_TF(dm, None, None, np.zeros(4), [np.zeros(1)] * 30, 30)
     assert s.get_state_offset().shape == (4,) and len(s.get_time()) == 3
+
+
+def test_bench_arms_share_the_config_object_and_the_profile_parser_knows_every_launch():
+    """bench.py: both arms print the same `config` (the driver compares them); the reference arm's line carries the keys
+    of the contract; the committed ncu summary has a block for each of the five launches `roofline` may name."""
+    import json
+    import subprocess
+    import sys
+    import bench
+    for wl in bench.WORKLOADS:
+        assert bench.workload_config(wl, 2) == bench.workload_config(wl, 2)
+        c = bench.workload_config(wl, 4)
+        assert c["global_batch"] == 4 * bench.WORKLOADS[wl][2] and set(c) == {"workload", "global_batch", "parallelism", "l2"}
+    for k in ("linearize", "riccati", "ls_phaseA", "ls_phaseB", "ls_phaseW"):
+        ref = bench.ncu_reference(k, True, "quadrotor")
+        assert ref is not None and ref["traffic"] > 0 and ref["duration_us"] > 0, k
+    assert bench.ncu_reference("ls_phaseB", True, "quadrotor")["fp64_pipe_pct"] > 10
+    out = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0", "--workload", "cartpole_classic"],
+                         capture_output=True, text=True, timeout=600, cwd=bench.ROOT)
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["config"] == bench.workload_config("cartpole_classic", 1)
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["value"] == line["value"] > 0
