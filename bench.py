@@ -123,7 +123,7 @@ def ncu_reference(kernel, blk, system):
     def byt(k):
         v, u = vals[k]
         return v * scale.get(u, 1.0)
-    return {"source": "profiles/r2_ncu_full_classic_summary.txt", "captured": "iteration 6 of a forced solve (13 007 trajectories queued)",
+    return {"source": "profiles/r2_ncu_full_classic_summary.txt", "captured": "iteration 6 of a forced solve (13 220 trajectories queued)",
             "traffic": byt("dram__bytes_read.sum") + byt("dram__bytes_write.sum"),
             "fma_pipe_pct": vals.get("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", (None,))[0],
             "fp64_pipe_pct": vals.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", (None,))[0],
